@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the TeXOCR inference hot path on B200 (BASELINE.json metric: decoded equations/sec,
+greedy, max_len 256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                            # the reference's CPU algorithm (oracle port)
+
+A step = one pass of the hot path over one batch: encoder -> cross-K/V -> 256 greedy decode steps for
+B=512 synthetic 64x384 images per GPU (BASELINE.json configs[2]).  N>1: one process per GPU (torchrun), the image
+list is sharded contiguously, every rank decodes its shard independently and the token ids are gathered
+with one NCCL all_gather per step ("scaling": "weak").  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoded equations/sec (greedy, max_len 256)"
+UNIT = "equations/s"
+H, W, MAX_LEN = 64, 384, 256
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+HBM_CLASSES = {"dec_attn_self", "dec_attn_cross", "dec_rowwise", "dec_argmax", "gn_stats", "gn_apply", "enc_rowwise",
+               "stem_conv", "tf_rowwise", "misc"}
+
+
+# ----------------------------------------------------------------------------- data-parallel plumbing (also tested on gloo)
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of rank `rank`."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def gather_tokens(tokens: torch.Tensor, world: int) -> torch.Tensor:
+    """Token ids of every rank's shard, concatenated in rank order (the path's only collective)."""
+    if world == 1:
+        return tokens
+    import torch.distributed as dist
+    outs = [torch.empty_like(tokens) for _ in range(world)]
+    dist.all_gather(outs, tokens.contiguous())
+    return torch.cat(outs, dim=0)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {k: float(d[k]) for k in FALLBACK_PEAKS if k in d}, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ----------------------------------------------------------------------------- CPU arms (oracle port of the reference algorithm)
+def cpu_reference_eq_per_s(n_eq: int, steps: int = 1, warmup: int = 0):
+    """The reference's own algorithm (encoder + O(T^2) full-prefix greedy loop, model/decoder.py:77-122) as restated in
+    oracle/texocr_oracle.py, on all host cores.  Returns (eq/s, cores, seconds per step)."""
+    from oracle import texocr_oracle as O
+    from texocr_b200 import spec, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = spec.dims_from_config(spec.default_config(max_length=MAX_LEN))
+    sd = synth.seeded_state_dict(d, seed=0)
+    img = synth.synth_images(n_eq, H, W, seed=1234)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            tok = O.model_generate(sd, img, MAX_LEN, d.bos, d.eos, cached=False)
+            dt = time.perf_counter() - t0
+            assert tok.shape[0] == n_eq
+            if i >= warmup:
+                times.append(dt)
+    per_step = sum(times) / len(times)
+    return n_eq / per_step, cores, per_step
+
+
+def run_reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    total = max(1, args.steps + args.warmup)
+    n_eq = max(1, min(8, 48 // total))
+    v, cores, per_step = cpu_reference_eq_per_s(n_eq, steps=args.steps, warmup=args.warmup)
+    sample = f"B={n_eq} synthetic {H}x{W} images, full {MAX_LEN}-step greedy loop without KV cache (reference algorithm), fp32 torch CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"greedy generate, {H}x{W}, max_len {MAX_LEN}, default config.yml model, random-init weights",
+                   "batch_per_step": n_eq},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- the B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="equations per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    args.warmup = max(args.warmup, 3)
+
+    import texocr_b200
+    from texocr_b200 import spec, synth
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = spec.default_config(max_length=MAX_LEN)
+    cfg["device"] = f"cuda:{local_rank}"
+    d = spec.dims_from_config(cfg)
+    model = texocr_b200.create_model(cfg, precision=args.precision)
+    model.load_state_dict(synth.seeded_state_dict(d, seed=0))      # same random-init weights on every rank
+    model.eval()
+    eng = model.engine()
+    B = args.batch
+    lo, hi = shard_range(B * world, rank, world)                    # this rank's contiguous shard of the job's image list
+    img_host = synth.synth_images(hi - lo, H, W, seed=1234 + rank).pin_memory()
+    img_dev = img_host.cuda()
+    out_host = torch.empty((hi - lo, MAX_LEN), dtype=torch.int64).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_device():
+        tok = model.generate(img_dev, max_len=MAX_LEN)             # public API; inputs resident in HBM
+        return gather_tokens(tok, world)
+
+    def step_e2e():
+        tok = eng.generate(img_host, MAX_LEN, out=out_host)         # C-ABI with HOST buffers: H2D + D2H inside the call
+        if world > 1:
+            gather_tokens(tok.cuda(non_blocking=True), world)
+        return tok
+
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = eng.kernel_launches()
+    ms = timed(step_device, args.steps)
+    launches = eng.kernel_launches() - l0
+    clk = clocks.stop()
+    value = world * B * args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        ms_e = timed(step_e2e, args.steps)
+        e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(img_host.numel() * 4 * world), "d2h_bytes_per_step": int(out_host.numel() * 8 * world)}
+
+    # ---- roofline of the dominant kernel: one eagerly launched step with CUDA events around every launch
+    peaks, peaks_src = load_peaks()
+    roofline, shares = None, None
+    if rank == 0:
+        eng.profile_enable(True)
+        model.generate(img_dev, max_len=MAX_LEN)
+        rows = eng.profile_read()
+        eng.profile_enable(False)
+        tot = sum(r["ms"] for r in rows) or 1.0
+        rows.sort(key=lambda r: -r["ms"])
+        shares = {r["name"]: round(r["ms"] / tot, 4) for r in rows}
+        top = rows[0]
+        sec = top["ms"] / 1e3 / max(1, top["launches"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(top["name"])
+            except Exception:
+                traffic = None
+        if top["name"] in HBM_CLASSES:
+            ach = top["bytes"] / max(1, top["launches"]) / sec / 1e9
+            roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_src,
+                        "launches": top["launches"], "avg_us": sec * 1e6}
+        else:
+            ach = top["flops"] / max(1, top["launches"]) / sec / 1e12
+            pk = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+            roofline = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": pk, "unit": "TFLOP/s",
+                        "frac": ach / pk, "traffic": traffic, "peak_source": peaks_src + " (sustained)",
+                        "launches": top["launches"], "avg_us": sec * 1e6}
+        # whole-step view against the HBM roofline of SURVEY.md section 8d (bf16 KV cache bytes + per-step weights)
+        s_tok = synth.encoder_tokens(H, W)
+        esz = 2 if args.precision == "bf16" else 4
+        step_bytes = sum(synth.decode_step_bytes(B, t, s_tok) for t in range(1, MAX_LEN + 1)) * (esz / 2)
+        roofline["job_decode_bytes_per_step"] = step_bytes
+        roofline["job_hbm_frac"] = (step_bytes * args.steps / (ms / 1e3) / 1e9) / peaks["hbm_gbs"]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, per_step = cpu_reference_eq_per_s(8)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"B=8 synthetic {H}x{W} images (BASELINE config 1), full {MAX_LEN}-step greedy loop without KV cache "
+                                  f"(reference algorithm, oracle port), fp32 torch CPU, {per_step:.1f} s"}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[2]: full greedy generate with KV cache, batch {B} per GPU, {H}x{W} images, "
+                               f"max_len {MAX_LEN}, default config.yml model (ResNetV2-hybrid ViT encoder + 4-layer decoder), random-init weights",
+                   "batch_per_gpu": B, "max_len": MAX_LEN, "image": [H, W], "precision": args.precision,
+                   "parallelism": f"dp{world} (independent shards, token-id all_gather)",
+                   "l2_policy": "working set (KV cache >= 1 GB, activations >= 3 GB per step) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernel_time_shares": shares,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

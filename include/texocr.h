@@ -1,0 +1,139 @@
+/*
+ * texocr.h -- C-ABI of the B200-native TeXOCR inference path (libtexocr_b200.so).
+ *
+ * The reference (olibridge01/TeXOCR) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md 2.1); its boundary for this path is the nn.Module surface of
+ * model/ocr_model.py.  Each entry point below is what a binding for that surface calls,
+ * and names the reference interface it replaces.  Plain pointers and sizes only: no
+ * torch types cross this line.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative texocr_status otherwise;
+ *    texocr_last_error(h) (or texocr_last_error(NULL) for a failed create) gives the message.
+ *  - data pointers may be HOST or DEVICE memory; the library asks the CUDA runtime which
+ *    (cudaPointerGetAttributes) and stages host buffers through its own pinned/device staging
+ *    on `stream`.  Device pointers must belong to the handle's device.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work is
+ *    enqueued on it; calls that return host-visible results synchronise that stream.
+ *  - one handle per process per GPU; a handle is not thread-safe.
+ *  - hw, enc_len and n_steps are always HOST arrays (they drive the host-side launch plan).
+ *  - images: float32, single channel, row-major, ink = 1 on a 0 background
+ *    (data_wrangling/dataset.py:365-371).  A batch is RAGGED: image i is hw[2*i] x hw[2*i+1],
+ *    stored back to back (image i starts at sum_{j<i} H_j*W_j floats).  H,W must be multiples of
+ *    16 with H <= 160 and W <= 1008 (position grid 10x63, model/encoder.py:137-143).
+ *  - encoder memory: float32, packed tokens [sum_i N_i, 256], N_i = (H_i/16)*(W_i/16)+1,
+ *    cls token first, then row-major patches (model/encoder.py:128-152).
+ */
+#ifndef TEXOCR_H_
+#define TEXOCR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEXOCR_ABI_VERSION 1
+#if defined(__GNUC__)
+#define TEXOCR_API __attribute__((visibility("default")))
+#else
+#define TEXOCR_API
+#endif
+
+typedef struct texocr_handle texocr_handle;
+
+typedef enum {
+    TEXOCR_OK = 0,
+    TEXOCR_ERR_ARG = -1,        /* bad argument / unsupported shape                       */
+    TEXOCR_ERR_CUDA = -2,       /* a CUDA call failed; message holds cudaGetErrorString   */
+    TEXOCR_ERR_STATE = -3,      /* call order (weights not finalised, ...)                 */
+    TEXOCR_ERR_WEIGHT = -4,     /* missing / mis-shaped state_dict entry                  */
+    TEXOCR_ERR_NODEVICE = -5    /* no sm_100 device: there is NO CPU fallback             */
+} texocr_status;
+
+typedef enum { TEXOCR_FP32 = 0, TEXOCR_BF16 = 1 } texocr_precision;
+typedef enum { TEXOCR_ENC_HYBRID = 0, TEXOCR_ENC_PATCH = 1 } texocr_encoder_kind;
+
+/* Hyper-parameters: the keys create_model reads from config.yml
+ * (model/ocr_model.py:113-130, model/encoder.py:172-191, model/decoder.py:148-173). */
+typedef struct {
+    int32_t abi_version;     /* TEXOCR_ABI_VERSION                                            */
+    int32_t vocab_size;      /* config['vocab_size'] (tokenizer_clean_1k.txt:1 -> 1000)       */
+    int32_t max_length;      /* config['max_length']: decoder positional table length         */
+    int32_t enc_layers;      /* encoder.num_layers                                            */
+    int32_t dec_layers;      /* decoder.num_layers                                            */
+    int32_t bos_token, eos_token, pad_token;
+    int32_t encoder_kind;    /* texocr_encoder_kind                                           */
+    int32_t precision;       /* texocr_precision: FP32 = parity tier (FFMA everywhere);
+                                BF16 = bf16 operands / KV cache, fp32 accumulate + statistics  */
+} texocr_config;
+
+/* replaces: create_model(config) (model/ocr_model.py:113-130) */
+TEXOCR_API int texocr_create(const texocr_config* cfg, int device, texocr_handle** out);
+TEXOCR_API void texocr_destroy(texocr_handle* h);
+TEXOCR_API const char* texocr_last_error(const texocr_handle* h);
+
+/* replaces: nn.Module.load_state_dict(state_dict) (utils.py:63-71, model/ocr_model.py:82-90).
+ * One call per state_dict entry, with the reference's key name; float32,
+ * contiguous, host or device.  Aliased keys (layers.{i}.0.*, block.*) may be passed or omitted. */
+TEXOCR_API int texocr_set_weight(texocr_handle* h, const char* name, const float* data, int32_t ndim, const int64_t* shape);
+/* Folds weight standardisation (model/resnet.py:61-64), concatenates q/k/v, interleaves GLU / GeGLU
+ * columns, converts to the compute precision and uploads.  Must be called after the last set_weight. */
+TEXOCR_API int texocr_finalize_weights(texocr_handle* h);
+
+/* replaces: VisionEncoder.forward (model/encoder.py:128-152) incl. the ResNetV2 stem
+ * (model/resnet.py:251-254).  enc_out: float32 [sum N_i, 256]. */
+TEXOCR_API int texocr_encode(texocr_handle* h, const float* images, const int32_t* hw, int32_t batch,
+                  float* enc_out, void* stream);
+
+/* replaces: Transformer.forward(ids, mask=, enc=) (model/decoder.py:41-67) -- teacher-forced logits.
+ * ids int64 [batch, T]; mask uint8 [batch, T] (1 = real token) or NULL; enc packed float32 with
+ * enc_len[batch] tokens per row; logits_out float32 [batch, T, vocab]. */
+TEXOCR_API int texocr_decoder_logits(texocr_handle* h, const int64_t* ids, const uint8_t* mask, const float* enc,
+                          const int32_t* enc_len, int32_t batch, int32_t T, float* logits_out, void* stream);
+
+/* replaces: AutoRegressiveDecoder.generate(start_tokens (B,1), eos_tok, max_len, enc=) (model/decoder.py:77-122),
+ * greedy (argmax; temp -> 0 limit of lines 104-108).  out_ids int64 [batch, max_len] (row stride max_len);
+ * *n_steps = number of valid columns = first step at which every row has produced eos_tok, else max_len
+ * (model/decoder.py:115-118).  eos_tok < 0 disables the early exit.  Requires max_len <= max_length. */
+TEXOCR_API int texocr_decoder_generate(texocr_handle* h, const int64_t* start_tokens, int32_t eos_tok, const float* enc,
+                            const int32_t* enc_len, int32_t batch, int32_t max_len, int64_t* out_ids,
+                            int32_t* n_steps, void* stream);
+
+/* replaces: OCRModel.generate(src, max_len) (model/ocr_model.py:46-66): encoder once, BOS column,
+ * decode loop; bos/eos from the config.  Same outputs as texocr_decoder_generate. */
+TEXOCR_API int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, int32_t batch, int32_t max_len,
+                    int64_t* out_ids, int32_t* n_steps, void* stream);
+
+/* replaces: AutoRegressiveDecoder.forward / OCRModel.forward loss (model/decoder.py:124-145):
+ * mean cross-entropy (no ignore_index) of logits [rows, vocab] against targets int64 [rows]. */
+TEXOCR_API int texocr_cross_entropy(texocr_handle* h, const float* logits, const int64_t* targets, int64_t rows,
+                         float* loss_out, void* stream);
+
+/* ---- instrumentation (bench.py / tests; not part of the reference surface) ---------------- */
+/* Number of kernels this library launched since the handle was created (CUDA-graph replays count
+ * the kernels they contain). */
+TEXOCR_API int64_t texocr_kernel_launches(const texocr_handle* h);
+/* Per-kernel-class device timing: when enabled, every launch is bracketed by CUDA events on the
+ * launching stream (CUDA graphs are bypassed).  texocr_profile_read synchronises and reports, per
+ * class, launches, total milliseconds and total algorithmic bytes / flops as accounted by the engine.
+ * Returns the number of classes written (<= cap). */
+typedef struct {
+    char name[48];
+    int64_t launches;
+    double ms;
+    double bytes;
+    double flops;
+} texocr_profile_row;
+TEXOCR_API int texocr_profile_enable(texocr_handle* h, int32_t on);
+TEXOCR_API int texocr_profile_read(texocr_handle* h, texocr_profile_row* rows, int32_t cap);
+/* Tuning switches (name = "cuda_graph" | "tcgen05" | ...); returns TEXOCR_ERR_ARG for unknown names. */
+TEXOCR_API int texocr_set_option(texocr_handle* h, const char* name, int64_t value);
+/* Debug tap: copy an internal activation of the last texocr_encode call to `out` (host or device).
+ * name = "backbone" -> float32 [sum h_i*w_i, 1024] (NHWC pixels).  Returns element count or <0. */
+TEXOCR_API int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_t cap_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXOCR_H_ */

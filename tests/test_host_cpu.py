@@ -1,0 +1,89 @@
+"""CPU tier: host logic, the C-ABI library's exports, and the N>1 sharding path over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from texocr_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "texocr.h")).read()
+    declared = set(re.findall(r"TEXOCR_API\s+[\w\s\*]+?\b(texocr_\w+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    if not os.path.exists(_lib.LIB_PATH):
+        from texocr_b200.build import build
+        build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_create_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from texocr_b200 import _lib
+    lib = _lib.load_library()
+    cfg = _lib.TexocrConfig(_lib.ABI_VERSION, 1000, 256, 4, 4, 998, 997, 999, 0, 0)
+    h = ctypes.c_void_p()
+    rc = lib.texocr_create(ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc == -5 and b"no CPU fallback" in lib.texocr_last_error(None)
+
+
+def test_model_surface_and_state_dict_roundtrip(dims, sd):
+    import texocr_b200
+    from texocr_b200 import spec
+    cfg = spec.default_config()
+    cfg["device"] = "cpu"
+    m = texocr_b200.create_model(cfg)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    assert m.bos_token == 998 and m.eos_token == 997 and m.trg_pad_idx == 999
+    assert m.decoder.max_len == 256
+    assert torch.equal(m.state_dict()["decoder.net.to_logits.bias"], sd["decoder.net.to_logits.bias"])
+    trg = torch.tensor([[998, 5, 997, 999]])
+    assert m.make_trg_mask(trg).tolist() == [[True, True, True, False]]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.generate(torch.zeros(1, 1, 64, 384), 4)
+    with pytest.raises(AssertionError):
+        spec.dims_from_config({k: v for k, v in cfg.items() if k != "max_length"})
+    with pytest.raises(ValueError):
+        spec.dims_from_config({**cfg, "glu": False})
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under texocr_b200/ may import or execute it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/.]texocr_oracle|texocr_oracle", re.M)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "texocr_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), (dirpath, f)
+
+
+def test_shard_plan_and_gloo_gather_world2(tmp_path):
+    """bench.py's data-parallel plumbing on CPU: contiguous shards per rank, gather of token ids == concatenation."""
+    script = tmp_path / "w2.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r})
+from bench import shard_range, gather_tokens
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+lo, hi = shard_range(1000, r, w)
+tok = torch.arange(lo * 4, hi * 4, dtype=torch.int64).reshape(hi - lo, 4)
+allt = gather_tokens(tok, w)
+if r == 0:
+    assert allt.shape == (1000, 4) and torch.equal(allt.reshape(-1), torch.arange(4000)), allt
+    print("GATHER_OK")
+dist.destroy_process_group()
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert "GATHER_OK" in out.stdout, out.stdout + out.stderr

@@ -1,0 +1,231 @@
+"""ctypes binding of libtexocr_b200.so (include/texocr.h) and the thin ``Engine`` wrapper.
+
+PyTorch is used for device memory and streams only: every tensor crosses the C-ABI as a raw
+pointer (``data_ptr()``), host or device.  There is no CPU implementation behind this module --
+if the shared library is missing or no sm_100 GPU is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from .spec import ModelDims
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtexocr_b200.so")
+ABI_VERSION = 1
+
+# every symbol include/texocr.h declares (tests check the library exports exactly these)
+EXPORTS = (
+    "texocr_create", "texocr_destroy", "texocr_last_error", "texocr_set_weight", "texocr_finalize_weights",
+    "texocr_encode", "texocr_decoder_logits", "texocr_decoder_generate", "texocr_generate", "texocr_cross_entropy",
+    "texocr_kernel_launches", "texocr_profile_enable", "texocr_profile_read", "texocr_set_option", "texocr_debug_read",
+)
+
+
+class TexocrConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "vocab_size", "max_length", "enc_layers", "dec_layers", "bos_token", "eos_token", "pad_token",
+        "encoder_kind", "precision")]
+
+
+class ProfileRow(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("ms", C.c_double), ("bytes", C.c_double),
+                ("flops", C.c_double)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the in-tree shared library; raise (never fall back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m texocr_b200.build` (nvcc, sm_100a). "
+            "texocr_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.texocr_create.argtypes = [C.POINTER(TexocrConfig), C.c_int, C.POINTER(vp)]
+    lib.texocr_destroy.argtypes = [vp]
+    lib.texocr_destroy.restype = None
+    lib.texocr_last_error.argtypes = [vp]
+    lib.texocr_last_error.restype = C.c_char_p
+    lib.texocr_set_weight.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64)]
+    lib.texocr_finalize_weights.argtypes = [vp]
+    lib.texocr_encode.argtypes = [vp, vp, C.POINTER(i32), i32, vp, vp]
+    lib.texocr_decoder_logits.argtypes = [vp, vp, vp, vp, C.POINTER(i32), i32, i32, vp, vp]
+    lib.texocr_decoder_generate.argtypes = [vp, vp, i32, vp, C.POINTER(i32), i32, i32, vp, C.POINTER(i32), vp]
+    lib.texocr_generate.argtypes = [vp, vp, C.POINTER(i32), i32, i32, vp, C.POINTER(i32), vp]
+    lib.texocr_cross_entropy.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.texocr_kernel_launches.argtypes = [vp]
+    lib.texocr_kernel_launches.restype = i64
+    lib.texocr_profile_enable.argtypes = [vp, i32]
+    lib.texocr_profile_read.argtypes = [vp, C.POINTER(ProfileRow), i32]
+    lib.texocr_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.texocr_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.texocr_debug_read.restype = i64
+    for name in EXPORTS:
+        getattr(lib, name)
+    _lib = lib
+    return lib
+
+
+def _i32_array(values: Sequence[int]):
+    return (C.c_int32 * len(values))(*[int(v) for v in values])
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+ImagesArg = Union[torch.Tensor, Sequence[torch.Tensor]]
+
+
+class Engine:
+    """One native handle: packed weights, workspaces, KV cache and the decode-step CUDA graph."""
+
+    def __init__(self, dims: ModelDims, state_dict: Dict[str, torch.Tensor], precision: str = "fp32", device: int = 0):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if not torch.cuda.is_available():
+            raise RuntimeError("texocr_b200 needs a CUDA (sm_100a) device: there is no CPU fallback")
+        self.lib = load_library()
+        self.dims = dims
+        self.precision = precision
+        self.device = torch.device("cuda", device)
+        cfg = TexocrConfig(ABI_VERSION, dims.vocab, dims.max_length, dims.enc_layers, dims.dec_layers, dims.bos, dims.eos,
+                           dims.pad, 0 if dims.encoder_kind == "hybrid" else 1, 1 if precision == "bf16" else 0)
+        h = C.c_void_p()
+        rc = self.lib.texocr_create(C.byref(cfg), device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"texocr_create failed ({rc}): {self.lib.texocr_last_error(None).decode()}")
+        self.h = h
+        for name, t in state_dict.items():
+            if ".block." in name:       # nn.Sequential alias of block_list.* (model/resnet.py:130-139)
+                continue
+            tt = _f32c(t).cpu()
+            shape = (C.c_int64 * tt.dim())(*tt.shape)
+            self._check(self.lib.texocr_set_weight(self.h, name.encode(), tt.data_ptr(), tt.dim(), shape))
+        self._check(self.lib.texocr_finalize_weights(self.h))
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc < 0:
+            raise RuntimeError(f"texocr error {rc}: {self.lib.texocr_last_error(self.h).decode()}")
+        return rc
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.texocr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _pack_images(images: ImagesArg) -> Tuple[torch.Tensor, List[int]]:
+        """(B,1,H,W) tensor or a list of (1,H,W)/(H,W) tensors -> flat float32 buffer + [H0,W0,H1,W1,...]."""
+        if isinstance(images, torch.Tensor):
+            if images.dim() != 4 or images.shape[1] != 1:
+                raise ValueError("src must be (B,1,H,W) single-channel images")
+            B, _, H, W = images.shape
+            return _f32c(images).reshape(-1), [v for _ in range(B) for v in (H, W)]
+        hw: List[int] = []
+        flat = []
+        for im in images:
+            im = im.reshape(im.shape[-2], im.shape[-1])
+            hw += [im.shape[0], im.shape[1]]
+            flat.append(_f32c(im).reshape(-1))
+        return torch.cat(flat), hw
+
+    @staticmethod
+    def token_counts(hw: Sequence[int]) -> List[int]:
+        return [(hw[2 * i] // 16) * (hw[2 * i + 1] // 16) + 1 for i in range(len(hw) // 2)]
+
+    # ------------------------------------------------------------------ entry points
+    def encode_packed(self, images: ImagesArg, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, List[int]]:
+        flat, hw = self._pack_images(images)
+        counts = self.token_counts(hw)
+        if out is None:
+            out = torch.empty((sum(counts), 256), dtype=torch.float32, device=self.device)
+        self._check(self.lib.texocr_encode(self.h, flat.data_ptr(), _i32_array(hw), len(counts), out.data_ptr(), self._stream()))
+        return out, counts
+
+    def decoder_logits(self, ids: torch.Tensor, mask: Optional[torch.Tensor], enc: torch.Tensor, enc_len: Sequence[int],
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, T = ids.shape
+        ids = ids.detach().to(torch.int64).contiguous()
+        m = None if mask is None else mask.detach().to(torch.uint8).contiguous()
+        enc = _f32c(enc).reshape(-1, 256)
+        if out is None:
+            out = torch.empty((B, T, self.dims.vocab), dtype=torch.float32, device=self.device)
+        self._check(self.lib.texocr_decoder_logits(self.h, ids.data_ptr(), None if m is None else m.data_ptr(), enc.data_ptr(),
+                                                   _i32_array(enc_len), B, T, out.data_ptr(), self._stream()))
+        return out
+
+    def decoder_generate(self, start_tokens: torch.Tensor, eos_tok: Optional[int], enc: torch.Tensor, enc_len: Sequence[int],
+                         max_len: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B = start_tokens.shape[0]
+        start = start_tokens.detach().to(torch.int64).reshape(B).contiguous()
+        enc = _f32c(enc).reshape(-1, 256)
+        if out is None:
+            out = torch.empty((B, max_len), dtype=torch.int64, device=self.device)
+        n = C.c_int32(0)
+        self._check(self.lib.texocr_decoder_generate(self.h, start.data_ptr(), -1 if eos_tok is None else int(eos_tok),
+                                                     enc.data_ptr(), _i32_array(enc_len), B, int(max_len), out.data_ptr(),
+                                                     C.byref(n), self._stream()))
+        return out[:, :n.value]
+
+    def generate(self, images: ImagesArg, max_len: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Images (host or device) -> greedy token ids (B, n_steps) int64; `out` may be a pinned host tensor."""
+        flat, hw = self._pack_images(images)
+        B = len(hw) // 2
+        if out is None:
+            out = torch.empty((B, max_len), dtype=torch.int64, device=self.device)
+        n = C.c_int32(0)
+        self._check(self.lib.texocr_generate(self.h, flat.data_ptr(), _i32_array(hw), B, int(max_len), out.data_ptr(), C.byref(n),
+                                             self._stream()))
+        return out[:, :n.value]
+
+    def cross_entropy(self, logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        logits = _f32c(logits).reshape(-1, self.dims.vocab)
+        targets = targets.detach().to(torch.int64).reshape(-1).contiguous()
+        out = torch.empty((), dtype=torch.float32, device=self.device)
+        self._check(self.lib.texocr_cross_entropy(self.h, logits.data_ptr(), targets.data_ptr(), logits.shape[0], out.data_ptr(),
+                                                  self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ instrumentation
+    def kernel_launches(self) -> int:
+        return int(self.lib.texocr_kernel_launches(self.h))
+
+    def profile_enable(self, on: bool):
+        self._check(self.lib.texocr_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self) -> List[dict]:
+        rows = (ProfileRow * 32)()
+        n = self._check(self.lib.texocr_profile_read(self.h, rows, 32))
+        return [dict(name=rows[i].name.decode(), launches=rows[i].launches, ms=rows[i].ms, bytes=rows[i].bytes,
+                     flops=rows[i].flops) for i in range(n)]
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.texocr_set_option(self.h, name.encode(), int(value)))
+
+    def debug_read(self, name: str, numel: int) -> torch.Tensor:
+        out = torch.empty(numel, dtype=torch.float32, device=self.device)
+        n = self.lib.texocr_debug_read(self.h, name.encode(), out.data_ptr(), numel)
+        if n < 0:
+            self._check(int(n))
+        return out[:n]

@@ -1,0 +1,71 @@
+"""Build libtexocr_b200.so in-tree with nvcc for sm_100a (no torch / pybind in the library).
+
+    python -m texocr_b200.build            # rebuilds only what changed
+    python -m texocr_b200.build --force
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libtexocr_b200.so")
+SOURCES = ["engine.cu", "gemm_simt.cu", "tc_gemm.cu", "conv_gn.cu", "rowwise.cu", "attention.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _headers_mtime() -> float:
+    m = 0.0
+    for d in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for f in os.listdir(d):
+            if f.endswith((".h", ".cuh")):
+                m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return m
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    hdr = _headers_mtime()
+    jobs = []
+    for src in SOURCES:
+        s, o = os.path.join(CSRC, src), os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
+            jobs.append((s, o))
+
+    def compile_one(job):
+        s, o = job
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {s}:\n{r.stdout}\n{r.stderr}")
+        return s
+
+    if jobs:
+        if verbose:
+            print(f"[texocr_b200.build] compiling {len(jobs)} file(s) for sm_100a", file=sys.stderr)
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(compile_one, jobs))
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    if jobs or not os.path.exists(LIB) or force:
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

@@ -1,0 +1,86 @@
+// Shared device helpers for the TeXOCR sm_100a kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+#define TX_DEVINL __device__ __forceinline__
+
+template <typename T> TX_DEVINL float to_f(T v);
+template <> TX_DEVINL float to_f<float>(float v) { return v; }
+template <> TX_DEVINL float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> TX_DEVINL T from_f(float v);
+template <> TX_DEVINL float from_f<float>(float v) { return v; }
+template <> TX_DEVINL bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements <-> float4 (pointer must be aligned to 4 elements)
+TX_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+TX_DEVINL float4 ld4(const bf16* p) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+TX_DEVINL void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+TX_DEVINL void st4(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+TX_DEVINL void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+TX_DEVINL void st2(bf16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+// 8 consecutive elements -> 8 floats (aligned to 8 elements)
+TX_DEVINL void ld8(const float* p, float* o) {
+    float4 a = ld4(p), b = ld4(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+TX_DEVINL void ld8(const bf16* p, float* o) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        o[2 * i] = f.x;
+        o[2 * i + 1] = f.y;
+    }
+}
+
+TX_DEVINL float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+TX_DEVINL float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+TX_DEVINL float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)); }
+TX_DEVINL float sigmoidf_(float g) { return 1.0f / (1.0f + expf(-g)); }
+
+// Ragged image batch geometry.  img_off[b] = pixel offset of image b at full resolution
+// (sum of H*W of the images before it); every level L (stride 2^L) has H>>L x W>>L pixels
+// starting at img_off[b] >> (2L) because H and W are multiples of 16.
+struct ImgGeom {
+    const int* img_off;   // [B+1]
+    const int* img_hw;    // [B][2]
+    int nimg;
+};
+
+TX_DEVINL int find_image(const int* off, int nimg, int level, int pix) {
+    // largest b with (off[b] >> 2L) <= pix
+    int lo = 0, hi = nimg - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if ((off[mid] >> (2 * level)) <= pix) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}

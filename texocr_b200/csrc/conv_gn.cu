@@ -1,0 +1,301 @@
+// Backbone pieces that are not GEMMs (model/resnet.py): the 7x7/s2 single-channel stem convolution,
+// GroupNorm(32) statistics + apply (+ residual + ReLU), the stem max-pool, patch im2col and the
+// cls / positional-embedding token assembly of model/encoder.py:128-143.
+// Activations are ragged NHWC pixel batches [sum_i h_i*w_i, C] (see ImgGeom in common.cuh).
+// All of these are HBM-bound: coalesced float4 rows, fp32 math, deterministic reductions.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+// ------------------------------------------------------------------ stem conv 7x7 stride 2, Cin = 1
+// model/resnet.py:219 + utils.py:98-123: SAME padding of an even extent with k=7,s=2 is (2,3).
+// One warp per run of output pixels; lane = output channel pair (lane, lane+32); the 2x49 filter taps
+// live in registers, the input window is a broadcast read.
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                        float* __restrict__ raw1, ImgGeom g, int total_p1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float w0[49], w1[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) {
+        w0[t] = w[t * 64 + lane];
+        w1[t] = w[t * 64 + lane + 32];
+    }
+    const int pix_per_warp = 16;
+    const int base = (blockIdx.x * 8 + warp) * pix_per_warp;
+    int b = -1, H = 0, W = 0, p_lo = 0, p_hi = 0;      // image of the current run of pixels
+    for (int i = 0; i < pix_per_warp; ++i) {
+        const int p = base + i;
+        if (p >= total_p1) return;
+        if (b < 0 || p >= p_hi) {
+            b = find_image(g.img_off, g.nimg, 1, p);
+            H = g.img_hw[2 * b]; W = g.img_hw[2 * b + 1];
+            p_lo = g.img_off[b] >> 2; p_hi = g.img_off[b + 1] >> 2;
+        }
+        const int w1d = W >> 1;
+        const int local = p - p_lo;
+        const int oy = local / w1d, ox = local - oy * w1d;
+        const float* im = img + g.img_off[b];
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+            const int iy = 2 * oy + ky - 2;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const int ix = 2 * ox + kx - 2;
+                if (ix < 0 || ix >= W) continue;
+                const float v = __ldg(im + (size_t)iy * W + ix);
+                a0 = fmaf(v, w0[ky * 7 + kx], a0);
+                a1 = fmaf(v, w1[ky * 7 + kx], a1);
+            }
+        }
+        raw1[(size_t)p * 64 + lane] = a0;
+        raw1[(size_t)p * 64 + lane + 32] = a1;
+    }
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics
+// partial[b][chunk][32][2] (double) then stats[b][32] = (mean, rstd).  Fixed summation order.
+template <int C>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ raw, const int* __restrict__ img_off,
+                                                       int level, int nchunk, double* __restrict__ partial) {
+    constexpr int C4 = C / 4;             // float4 columns
+    constexpr int RPP = 256 / C4;         // rows per pass
+    constexpr int CPG = C / 32;
+    __shared__ double s_sum[RPP * C];     // RPP*C == 1024
+    __shared__ double s_sq[RPP * C];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int p0 = img_off[b] >> (2 * level), p1 = img_off[b + 1] >> (2 * level);
+    const int npix = p1 - p0;
+    const int per = (npix + nchunk - 1) / nchunk;
+    const int lo = p0 + chunk * per, hi = min(p1, lo + per);
+    const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = lo + rl; p < hi; p += RPP) {
+        float4 v = ld4(raw + (size_t)p * C + c4 * 4);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s_sum[rl * C + c4 * 4 + i] = (double)s[i];
+        s_sq[rl * C + c4 * 4 + i] = (double)q[i];
+    }
+    __syncthreads();
+    // per-channel totals into row 0
+    for (int c = threadIdx.x; c < C; c += 256) {
+        double a = 0.0, bq = 0.0;
+        for (int r = 0; r < RPP; ++r) { a += s_sum[r * C + c]; bq += s_sq[r * C + c]; }
+        s_sum[c] = a; s_sq[c] = bq;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double a = 0.0, bq = 0.0;
+        for (int i = 0; i < CPG; ++i) { a += s_sum[threadIdx.x * CPG + i]; bq += s_sq[threadIdx.x * CPG + i]; }
+        double* out = partial + (((size_t)b * nchunk + chunk) * 32 + threadIdx.x) * 2;
+        out[0] = a; out[1] = bq;
+    }
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ partial, const int* __restrict__ img_off, int level,
+                                   int nchunk, int cpg, float* __restrict__ stats) {
+    const int b = blockIdx.x, g = threadIdx.x;
+    double a = 0.0, q = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+        const double* in = partial + (((size_t)b * nchunk + c) * 32 + g) * 2;
+        a += in[0]; q += in[1];
+    }
+    const double n = (double)((img_off[b + 1] >> (2 * level)) - (img_off[b] >> (2 * level))) * cpg;
+    const double mean = a / n;
+    double var = q / n - mean * mean;       // biased variance (F.group_norm)
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)b * 32 + g) * 2 + 0] = (float)mean;
+    stats[((size_t)b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+// ------------------------------------------------------------------ GroupNorm apply (+residual, +ReLU)
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, const int* __restrict__ img_off, int nchunk) {
+    const int C = a.C, C4 = C / 4, cpg = C / 32;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int p0 = img_off[b] >> (2 * a.level), p1 = img_off[b + 1] >> (2 * a.level);
+    const int per = (p1 - p0 + nchunk - 1) / nchunk;
+    const int lo = p0 + chunk * per, hi = min(p1, lo + per);
+    const int rpp = 256 / min(C4, 256);
+    const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;     // C4 <= 256
+    const int c = c4 * 4;
+    float mean[4], sc[4], be[4], mean2[4], sc2[4], be2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = (c + i) / cpg;
+        mean[i] = a.stats[((size_t)b * 32 + gi) * 2];
+        sc[i] = a.stats[((size_t)b * 32 + gi) * 2 + 1] * a.gamma[c + i];
+        be[i] = a.beta[c + i];
+        if (a.raw2) {
+            mean2[i] = a.stats2[((size_t)b * 32 + gi) * 2];
+            sc2[i] = a.stats2[((size_t)b * 32 + gi) * 2 + 1] * a.gamma2[c + i];
+            be2[i] = a.beta2[c + i];
+        } else { mean2[i] = sc2[i] = be2[i] = 0.f; }
+    }
+    for (int p = lo + rl; p < hi; p += rpp) {
+        const size_t o = (size_t)p * C + c;
+        float4 v = ld4(a.raw + o);
+        float r[4] = {(v.x - mean[0]) * sc[0] + be[0], (v.y - mean[1]) * sc[1] + be[1],
+                      (v.z - mean[2]) * sc[2] + be[2], (v.w - mean[3]) * sc[3] + be[3]};
+        if (a.raw2) {
+            float4 u = ld4(a.raw2 + o);
+            r[0] += (u.x - mean2[0]) * sc2[0] + be2[0]; r[1] += (u.y - mean2[1]) * sc2[1] + be2[1];
+            r[2] += (u.z - mean2[2]) * sc2[2] + be2[2]; r[3] += (u.w - mean2[3]) * sc2[3] + be2[3];
+        }
+        if (a.res) {
+            float4 u = ld4(a.res + o);
+            r[0] += u.x; r[1] += u.y; r[2] += u.z; r[3] += u.w;
+        }
+        if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[i] = fmaxf(r[i], 0.f);
+        }
+        st4(a.out + o, make_float4(r[0], r[1], r[2], r[3]));
+    }
+}
+
+// ------------------------------------------------------------------ stem: GN + ReLU + maxpool 3x3 s2
+// model/resnet.py:69-79: SAME pad (0,1) filled with -inf => out-of-range taps are skipped.
+__global__ void __launch_bounds__(256) gn_apply_maxpool_kernel(const float* __restrict__ raw1, const float* __restrict__ stats,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float* __restrict__ out2, ImgGeom g, int total_p2) {
+    const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;       // 16 float4 columns (C = 64), 16 pixels per block pass
+    const int p = blockIdx.x * 16 + rl;
+    if (p >= total_p2) return;
+    const int b = find_image(g.img_off, g.nimg, 2, p);
+    const int H1 = g.img_hw[2 * b] >> 1, W1 = g.img_hw[2 * b + 1] >> 1, W2 = W1 >> 1;
+    const int local = p - (g.img_off[b] >> 4);
+    const int oy = local / W2, ox = local - oy * W2;
+    const float* in = raw1 + (size_t)(g.img_off[b] >> 2) * 64;
+    const int c = c4 * 4;
+    float mean[4], sc[4], be[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = (c + i) >> 1;     // 64 channels / 32 groups
+        mean[i] = stats[((size_t)b * 32 + gi) * 2];
+        sc[i] = stats[((size_t)b * 32 + gi) * 2 + 1] * gamma[c + i];
+        be[i] = beta[c + i];
+    }
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy + ky;
+        if (iy >= H1) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = 2 * ox + kx;
+            if (ix >= W1) continue;
+            float4 v = ld4(in + ((size_t)iy * W1 + ix) * 64 + c);
+            m[0] = fmaxf(m[0], fmaxf((v.x - mean[0]) * sc[0] + be[0], 0.f));
+            m[1] = fmaxf(m[1], fmaxf((v.y - mean[1]) * sc[1] + be[1], 0.f));
+            m[2] = fmaxf(m[2], fmaxf((v.z - mean[2]) * sc[2] + be[2], 0.f));
+            m[3] = fmaxf(m[3], fmaxf((v.w - mean[3]) * sc[3] + be[3], 0.f));
+        }
+    }
+    st4(out2 + (size_t)p * 64 + c, make_float4(m[0], m[1], m[2], m[3]));
+}
+
+// ------------------------------------------------------------------ patch variant: 16x16/s16 im2col (model/encoder.py:22-27)
+__global__ void __launch_bounds__(256) im2col_patch_kernel(const float* __restrict__ img, float* __restrict__ cols, ImgGeom g,
+                                                           int total_p4) {
+    // one warp per patch pair... simple mapping: thread = (patch, float4 of the 256-element patch row)
+    const int p = blockIdx.x * 4 + (threadIdx.x >> 6);
+    const int q = threadIdx.x & 63;                // float4 index in [0,64): ky = q/4, kx4 = q%4
+    if (p >= total_p4) return;
+    const int b = find_image(g.img_off, g.nimg, 4, p);
+    const int W = g.img_hw[2 * b + 1], w4 = W >> 4;
+    const int local = p - (g.img_off[b] >> 8);
+    const int r = local / w4, cc = local - r * w4;
+    const int ky = q >> 2, kx = (q & 3) * 4;
+    float4 v = ld4(img + g.img_off[b] + (size_t)(r * 16 + ky) * W + cc * 16 + kx);
+    st4(cols + (size_t)p * 256 + q * 4, v);
+}
+
+// ------------------------------------------------------------------ cls + positional embedding (model/encoder.py:128-143)
+// x0[tok_off[b]] = cls + pos[0];  x0[tok_off[b] + 1 + r*w + c] = proj[pixel] + pos[r*63 + c + 1]
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ proj, const float* __restrict__ cls,
+                                                              const float* __restrict__ pos, float* __restrict__ x0, ImgGeom g,
+                                                              const int* __restrict__ tok_off, int total_tok) {
+    const int t = blockIdx.x * 4 + (threadIdx.x >> 6);
+    const int q = (threadIdx.x & 63) * 4;
+    if (t >= total_tok) return;
+    // tok_off[b] = (img_off[b] >> 8) + b  => find b by binary search on tok_off
+    int lo = 0, hi = g.nimg - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (tok_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int b = lo, local = t - tok_off[b];
+    float4 v, pe;
+    if (local == 0) {
+        v = ld4(cls + q);
+        pe = ld4(pos + q);
+    } else {
+        const int w4 = g.img_hw[2 * b + 1] >> 4;
+        const int r = (local - 1) / w4, c = (local - 1) - r * w4;
+        v = ld4(proj + ((size_t)(g.img_off[b] >> 8) + (local - 1)) * 256 + q);
+        pe = ld4(pos + (size_t)(r * 63 + c + 1) * 256 + q);
+    }
+    st4(x0 + (size_t)t * 256 + q, make_float4(v.x + pe.x, v.y + pe.y, v.z + pe.z, v.w + pe.w));
+}
+
+}  // namespace
+
+cudaError_t launch_stem_conv(const float* img, const float* w, float* raw1, const int* img_off, const int* img_hw,
+                             int nimg, int total_p1, cudaStream_t st) {
+    ImgGeom g{img_off, img_hw, nimg};
+    const int blocks = (total_p1 + 127) / 128;
+    stem_conv_kernel<<<blocks, 256, 0, st>>>(img, w, raw1, g, total_p1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_stats(const float* raw, int C, int level, const int* img_off, int nimg, int nchunk,
+                            double* partial, float* stats, cudaStream_t st) {
+    dim3 grid(nchunk, nimg);
+    switch (C) {
+        case 64: gn_stats_kernel<64><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 128: gn_stats_kernel<128><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 256: gn_stats_kernel<256><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 512: gn_stats_kernel<512><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 1024: gn_stats_kernel<1024><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    gn_finalize_kernel<<<nimg, 32, 0, st>>>(partial, img_off, level, nchunk, C / 32, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_apply(const GnApplyArgs& a, const int* img_off, int nimg, int nchunk, cudaStream_t st) {
+    if (a.C % 4 != 0 || a.C / 4 > 256) return cudaErrorInvalidValue;
+    dim3 grid(nchunk, nimg);
+    gn_apply_kernel<<<grid, 256, 0, st>>>(a, img_off, nchunk);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_apply_maxpool(const float* raw1, const float* stats, const float* gamma, const float* beta,
+                                    float* out2, const int* img_off, const int* img_hw, int nimg, int total_p2,
+                                    cudaStream_t st) {
+    ImgGeom g{img_off, img_hw, nimg};
+    gn_apply_maxpool_kernel<<<(total_p2 + 15) / 16, 256, 0, st>>>(raw1, stats, gamma, beta, out2, g, total_p2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_im2col_patch(const float* img, float* cols, const int* img_off, const int* img_hw, int nimg,
+                                int total_p4, cudaStream_t st) {
+    ImgGeom g{img_off, img_hw, nimg};
+    im2col_patch_kernel<<<(total_p4 + 3) / 4, 256, 0, st>>>(img, cols, g, total_p4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble_tokens(const float* proj, const float* cls, const float* pos, float* x0, const int* img_off,
+                                   const int* img_hw, const int* tok_off, int nimg, int total_tok, cudaStream_t st) {
+    ImgGeom g{img_off, img_hw, nimg};
+    assemble_tokens_kernel<<<(total_tok + 3) / 4, 256, 0, st>>>(proj, cls, pos, x0, g, tok_off, total_tok);
+    return cudaGetLastError();
+}

@@ -1,0 +1,1025 @@
+// Host-side engine + C-ABI of libtexocr_b200.so (include/texocr.h).
+//
+// What runs where (reference file:line in brackets):
+//   texocr_encode            ResNetV2 stem + bottlenecks [model/resnet.py:141-149,251-254] as NHWC implicit GEMMs with
+//                            GroupNorm statistics/apply kernels, 1x1 projection, cls/pos assembly
+//                            [model/encoder.py:128-143], ViT blocks with the shared double LayerNorm
+//                            [model/attention.py:237-259], final norm [model/encoder.py:148].
+//   texocr_decoder_logits    teacher-forced Transformer.forward [model/decoder.py:41-67].
+//   texocr_decoder_generate  KV-cached greedy loop, one CUDA graph per decode step, on-device EOS bookkeeping
+//                            [model/decoder.py:77-122]; cross-attention K/V of the memory projected once.
+// There is no CPU fallback anywhere: every entry point needs the sm_100 device the handle was created on.
+#include "engine.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "tc_gemm.h"
+
+static std::string g_create_error;
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, #expr, __LINE__);                         \
+    } while (0)
+
+static int fail(texocr_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+static int fail_cuda(texocr_handle* h, cudaError_t e, const char* what, int line) {
+    return fail(h, TEXOCR_ERR_CUDA, "CUDA error %s (%s) at engine.cu:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), line, what);
+}
+
+// ------------------------------------------------------------------------------------------------ profiling / launch accounting
+static const char* kclass_name[KC_COUNT] = {
+    "stem_conv", "gn_stats", "gn_apply", "conv_gemm", "enc_gemm", "enc_attn", "enc_rowwise", "crosskv_gemm",
+    "dec_gemm", "dec_attn_self", "dec_attn_cross", "dec_rowwise", "dec_argmax", "tf_gemm", "tf_attn", "tf_rowwise", "misc"};
+
+static cudaEvent_t get_event(texocr_handle* h) {
+    if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+#define LAUNCH(kc_, nkern, bytes_, flops_, expr)                                                   \
+    do {                                                                                           \
+        ProfRec pr__;                                                                              \
+        if (h->prof_on) { pr__.cls = (kc_); pr__.bytes = (bytes_); pr__.flops = (flops_);          \
+            pr__.e0 = get_event(h); pr__.e1 = get_event(h); cudaEventRecord(pr__.e0, st); }        \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, #expr, __LINE__);                         \
+        h->launches += (nkern);                                                                    \
+        if (h->prof_on) { cudaEventRecord(pr__.e1, st); h->prof.push_back(pr__); }                 \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ memory helpers
+static int ensure(texocr_handle* h, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return 0;
+    if (b.p) { CK(cudaDeviceSynchronize()); CK(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+    size_t want = std::max(bytes, (size_t)256);
+    want = (want + 255) & ~(size_t)255;
+    CK(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // pointers may have moved
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+    return 0;
+}
+#define ENSURE(buf, bytes) do { int r__ = ensure(h, (buf), (bytes)); if (r__) return r__; } while (0)
+
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Return a device pointer for `p` (bytes long): p itself if it is device memory, else a staged copy.
+static int to_device(texocr_handle* h, const void* p, size_t bytes, DevBuf& stage, const void** out, cudaStream_t st) {
+    if (is_device_ptr(p)) { *out = p; return 0; }
+    ENSURE(stage, bytes);
+    CK(cudaMemcpyAsync(stage.p, p, bytes, cudaMemcpyHostToDevice, st));
+    *out = stage.p;
+    return 0;
+}
+static int from_device(texocr_handle* h, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (dst == src) return 0;
+    CK(cudaMemcpyAsync(dst, src, bytes, is_device_ptr(dst) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+static int upload_ints(texocr_handle* h, const std::vector<int>& v, cudaStream_t st) {
+    const size_t bytes = v.size() * sizeof(int);
+    if (h->h_geom_cap < bytes) {
+        if (h->h_geom) { CK(cudaEventSynchronize(h->geom_ev)); CK(cudaFreeHost(h->h_geom)); }
+        h->h_geom_cap = std::max(bytes * 2, (size_t)4096);
+        CK(cudaMallocHost(&h->h_geom, h->h_geom_cap));
+    }
+    CK(cudaEventSynchronize(h->geom_ev));          // the previous upload has left the staging buffer
+    memcpy(h->h_geom, v.data(), bytes);
+    ENSURE(h->geom, bytes);
+    CK(cudaMemcpyAsync(h->geom.p, h->h_geom, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(h->geom_ev, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+template <typename T> static int dev_upload(texocr_handle* h, const std::vector<T>& v, void** out) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, std::max(v.size() * sizeof(T), (size_t)16)));
+    CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    h->weight_allocs.push_back(p);
+    *out = p;
+    return 0;
+}
+static uint16_t f2bf(float f) {     // round-to-nearest-even, like __float2bfloat16_rn
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static int upload_f32(texocr_handle* h, const std::vector<float>& v, float** out) { return dev_upload<float>(h, v, (void**)out); }
+static int upload_act(texocr_handle* h, const std::vector<float>& v, void** out) {      // in the GEMM operand type
+    if (h->dt == DT_F32) return dev_upload<float>(h, v, out);
+    std::vector<uint16_t> b(v.size());
+    for (size_t i = 0; i < v.size(); ++i) b[i] = f2bf(v[i]);
+    return dev_upload<uint16_t>(h, b, out);
+}
+
+static const HostTensor* find_w(texocr_handle* h, const std::string& key, std::initializer_list<int64_t> shape) {
+    auto it = h->sd.find(key);
+    if (it == h->sd.end()) { fail(h, TEXOCR_ERR_WEIGHT, "missing state_dict entry '%s'", key.c_str()); return nullptr; }
+    if (it->second.shape != std::vector<int64_t>(shape)) {
+        fail(h, TEXOCR_ERR_WEIGHT, "state_dict entry '%s' has the wrong shape", key.c_str());
+        return nullptr;
+    }
+    return &it->second;
+}
+#define GETW(var, key, ...) const HostTensor* var = find_w(h, (key), {__VA_ARGS__}); if (!var) return TEXOCR_ERR_WEIGHT
+
+// rows interleaved for the GLU / GeGLU epilogues: packed row 2j = W[j] (value), 2j+1 = W[half + j] (gate)
+static void interleave_rows(const std::vector<float>& w, int rows, int cols, std::vector<float>& out) {
+    const int half = rows / 2;
+    out.resize(w.size());
+    for (int j = 0; j < half; ++j) {
+        memcpy(&out[(size_t)(2 * j) * cols], &w[(size_t)j * cols], cols * sizeof(float));
+        memcpy(&out[(size_t)(2 * j + 1) * cols], &w[(size_t)(half + j) * cols], cols * sizeof(float));
+    }
+}
+
+static int pack_attn(texocr_handle* h, const std::string& p, bool cross, AttnW& out) {
+    GETW(q, p + ".q.weight", 512, 256);
+    GETW(k, p + ".k.weight", 512, 256);
+    GETW(v, p + ".v.weight", 512, 256);
+    GETW(wo, p + ".fc_out.0.weight", 512, 512);
+    GETW(bo, p + ".fc_out.0.bias", 512);
+    int r;
+    if (!cross) {
+        std::vector<float> qkv;
+        qkv.insert(qkv.end(), q->data.begin(), q->data.end());
+        qkv.insert(qkv.end(), k->data.begin(), k->data.end());
+        qkv.insert(qkv.end(), v->data.begin(), v->data.end());
+        if ((r = upload_act(h, qkv, &out.wqkv))) return r;
+    } else {
+        if ((r = upload_act(h, q->data, &out.wq))) return r;
+    }
+    std::vector<float> woi, boi;
+    interleave_rows(wo->data, 512, 512, woi);
+    interleave_rows(bo->data, 512, 1, boi);
+    if ((r = upload_act(h, woi, &out.wo))) return r;
+    return upload_f32(h, boi, &out.bo);
+}
+static int pack_mlp(texocr_handle* h, const std::string& p, MlpW& out) {
+    GETW(w1, p + ".fc_in.fc.weight", 2048, 256);
+    GETW(b1, p + ".fc_in.fc.bias", 2048);
+    GETW(w2, p + ".fc_out.weight", 256, 1024);
+    GETW(b2, p + ".fc_out.bias", 256);
+    std::vector<float> w1i, b1i;
+    interleave_rows(w1->data, 2048, 256, w1i);
+    interleave_rows(b1->data, 2048, 1, b1i);
+    int r;
+    if ((r = upload_act(h, w1i, &out.w1))) return r;
+    if ((r = upload_f32(h, b1i, &out.b1))) return r;
+    if ((r = upload_act(h, w2->data, &out.w2))) return r;
+    return upload_f32(h, b2->data, &out.b2);
+}
+
+// model/resnet.py:61-64: w_hat = (w - mean) / sqrt(biased var + 1e-6) per output channel; folded once here
+// (double accumulation), reordered [cout][cin][ky][kx] -> [cout][ky][kx][cin] for the NHWC implicit GEMM.
+static void standardise_reorder(const HostTensor& w, int cout, int cin, int k, std::vector<float>& out) {
+    const int n = cin * k * k;
+    out.resize((size_t)cout * n);
+    for (int o = 0; o < cout; ++o) {
+        const float* src = &w.data[(size_t)o * n];
+        double s = 0.0, q = 0.0;
+        for (int i = 0; i < n; ++i) s += src[i];
+        const double mean = s / n;
+        for (int i = 0; i < n; ++i) { const double d = src[i] - mean; q += d * d; }
+        const double rstd = 1.0 / sqrt(q / n + 1e-6);
+        for (int c = 0; c < cin; ++c)
+            for (int t = 0; t < k * k; ++t)
+                out[(size_t)o * n + (size_t)t * cin + c] = (float)((src[(size_t)c * k * k + t] - mean) * rstd);
+    }
+}
+
+static int finalize_weights(texocr_handle* h) {
+    const texocr_config& c = h->cfg;
+    int r;
+    const std::string E = "encoder.";
+    if (c.encoder_kind == TEXOCR_ENC_HYBRID) {
+        const std::string bb = E + "patch_embed.backbone_net.";
+        {   // stem: [64][1][7][7] -> standardised [tap][oc]
+            GETW(w, bb + "stem.0.weight", 64, 1, 7, 7);
+            std::vector<float> ws, wt(49 * 64);
+            standardise_reorder(*w, 64, 1, 7, ws);
+            for (int o = 0; o < 64; ++o) for (int t = 0; t < 49; ++t) wt[t * 64 + o] = ws[o * 49 + t];
+            if ((r = upload_f32(h, wt, &h->stem_w))) return r;
+            GETW(g, bb + "stem.1.weight", 64);
+            GETW(b, bb + "stem.1.bias", 64);
+            if ((r = upload_f32(h, g->data, &h->stem_g))) return r;
+            if ((r = upload_f32(h, b->data, &h->stem_b))) return r;
+        }
+        const int depths[3] = {2, 4, 6}, chans[3] = {256, 512, 1024};
+        int prev = 64;
+        for (int s = 0; s < 3; ++s) {
+            const int cout = chans[s], mid = cout / 4;
+            for (int b = 0; b < depths[s]; ++b) {
+                const int stride = (b == 0) ? (s == 0 ? 1 : 2) : 1;
+                const std::string p = bb + "stages." + std::to_string(s) + ".stage_blocks." + std::to_string(b);
+                struct Spec { std::string name, gn; int cin, cout, k, stride, act; };
+                std::vector<Spec> specs;
+                if (b == 0) specs.push_back({p + ".downsample.conv", p + ".downsample.norm", prev, cout, 1, stride, 0});
+                specs.push_back({p + ".block_list.0", p + ".block_list.1", prev, mid, 1, 1, 1});
+                specs.push_back({p + ".block_list.2", p + ".block_list.3", mid, mid, 3, stride, 1});
+                specs.push_back({p + ".block_list.4", p + ".block_list.5", mid, cout, 1, 1, 0});
+                for (auto& sp : specs) {
+                    GETW(w, sp.name + ".weight", sp.cout, sp.cin, sp.k, sp.k);
+                    GETW(g, sp.gn + ".weight", sp.cout);
+                    GETW(be, sp.gn + ".bias", sp.cout);
+                    ConvW cw;
+                    cw.name = sp.name; cw.gn = sp.gn; cw.cin = sp.cin; cw.cout = sp.cout; cw.k = sp.k; cw.stride = sp.stride; cw.act = sp.act;
+                    std::vector<float> ws;
+                    standardise_reorder(*w, sp.cout, sp.cin, sp.k, ws);
+                    if ((r = upload_f32(h, ws, &cw.w))) return r;
+                    if ((r = upload_f32(h, g->data, &cw.gamma))) return r;
+                    if ((r = upload_f32(h, be->data, &cw.beta))) return r;
+                    h->convs.push_back(cw);
+                }
+                prev = cout;
+            }
+        }
+        GETW(pw, E + "patch_embed.proj.weight", 256, 1024, 1, 1);
+        GETW(pb, E + "patch_embed.proj.bias", 256);
+        if ((r = upload_act(h, pw->data, &h->proj_w))) return r;
+        if ((r = upload_f32(h, pb->data, &h->proj_b))) return r;
+        h->proj_k = 1024;
+    } else {
+        GETW(pw, E + "patch_embed.proj.weight", 256, 1, 16, 16);
+        GETW(pb, E + "patch_embed.proj.bias", 256);
+        if ((r = upload_act(h, pw->data, &h->proj_w))) return r;      // [256][ky*16+kx] already K-major
+        if ((r = upload_f32(h, pb->data, &h->proj_b))) return r;
+        h->proj_k = 256;
+    }
+    const int64_t npos = (c.encoder_kind == TEXOCR_ENC_HYBRID ? 10 : 63) * 63 + 1;
+    GETW(cls, E + "cls_token", 1, 1, 256);
+    GETW(pos, E + "pos_embed", 1, npos, 256);
+    if ((r = upload_f32(h, cls->data, &h->cls))) return r;
+    if ((r = upload_f32(h, pos->data, &h->pos))) return r;
+    {
+        GETW(g, E + "attn_layers.layers.0.0.weight", 256);
+        GETW(b, E + "attn_layers.layers.0.0.bias", 256);
+        GETW(ng, E + "norm.weight", 256);
+        GETW(nb, E + "norm.bias", 256);
+        if ((r = upload_f32(h, g->data, &h->enc_ln_g))) return r;
+        if ((r = upload_f32(h, b->data, &h->enc_ln_b))) return r;
+        if ((r = upload_f32(h, ng->data, &h->enc_norm_g))) return r;
+        if ((r = upload_f32(h, nb->data, &h->enc_norm_b))) return r;
+    }
+    h->enc_attn.resize(c.enc_layers); h->enc_mlp.resize(c.enc_layers);
+    for (int l = 0; l < c.enc_layers; ++l) {
+        if ((r = pack_attn(h, E + "attn_layers.layers." + std::to_string(2 * l) + ".1", false, h->enc_attn[l]))) return r;
+        if ((r = pack_mlp(h, E + "attn_layers.layers." + std::to_string(2 * l + 1) + ".1", h->enc_mlp[l]))) return r;
+    }
+    const std::string Dn = "decoder.net.";
+    GETW(te, Dn + "token_embedding.weight", c.vocab_size, 256);
+    GETW(pe, Dn + "pos_embedding.embedding.weight", c.max_length, 256);
+    if ((r = upload_f32(h, te->data, &h->tok_emb))) return r;
+    if ((r = upload_f32(h, pe->data, &h->pos_emb))) return r;
+    {
+        GETW(g, Dn + "attn_layers.layers.0.0.weight", 256);
+        GETW(b, Dn + "attn_layers.layers.0.0.bias", 256);
+        GETW(ng, Dn + "norm.weight", 256);
+        GETW(nb, Dn + "norm.bias", 256);
+        if ((r = upload_f32(h, g->data, &h->dec_ln_g))) return r;
+        if ((r = upload_f32(h, b->data, &h->dec_ln_b))) return r;
+        if ((r = upload_f32(h, ng->data, &h->dec_norm_g))) return r;
+        if ((r = upload_f32(h, nb->data, &h->dec_norm_b))) return r;
+    }
+    h->dec_self.resize(c.dec_layers); h->dec_cross.resize(c.dec_layers); h->dec_mlp.resize(c.dec_layers);
+    std::vector<float> ckv;
+    for (int l = 0; l < c.dec_layers; ++l) {
+        const std::string base = Dn + "attn_layers.layers.";
+        if ((r = pack_attn(h, base + std::to_string(3 * l) + ".1", false, h->dec_self[l]))) return r;
+        if ((r = pack_attn(h, base + std::to_string(3 * l + 1) + ".1", true, h->dec_cross[l]))) return r;
+        if ((r = pack_mlp(h, base + std::to_string(3 * l + 2) + ".1", h->dec_mlp[l]))) return r;
+        GETW(k, base + std::to_string(3 * l + 1) + ".1.k.weight", 512, 256);
+        GETW(v, base + std::to_string(3 * l + 1) + ".1.v.weight", 512, 256);
+        ckv.insert(ckv.end(), k->data.begin(), k->data.end());
+        ckv.insert(ckv.end(), v->data.begin(), v->data.end());
+    }
+    if ((r = upload_act(h, ckv, &h->w_crosskv))) return r;
+    GETW(lw, Dn + "to_logits.weight", c.vocab_size, 256);
+    GETW(lb, Dn + "to_logits.bias", c.vocab_size);
+    if ((r = upload_act(h, lw->data, &h->w_logits))) return r;
+    if ((r = upload_f32(h, lb->data, &h->b_logits))) return r;
+    h->sd.clear();
+    h->finalized = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+// tcgen05 path for bf16 operands when the shape fits its tiles, FFMA path otherwise (and always in the fp32 tier).
+static cudaError_t run_gemm(texocr_handle* h, const GemmArgs& g, cudaStream_t st) {
+    if (h->use_tcgen05 && g.dt_a == DT_BF16 && !g.conv && tc_gemm_supported(g)) return launch_gemm_tc(g, st);
+    return launch_gemm_simt(g, st);
+}
+static GemmArgs mk_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epi,
+                        int dt_a, int dt_c, const float* bias, const float* res, int ldres) {
+    GemmArgs g{};
+    g.A = A; g.W = W; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldc = ldc;
+    g.bias = bias; g.res = res; g.ldres = ldres; g.dt_a = dt_a; g.dt_c = dt_c; g.epi = epi; g.conv = nullptr;
+    return g;
+}
+static double gemm_bytes(const GemmArgs& g, size_t esz) {
+    return (double)g.M * g.K * esz + (double)g.N * g.K * esz + (double)g.M * g.N * 4.0;
+}
+static double gemm_flops(const GemmArgs& g) { return 2.0 * g.M * (double)g.N * g.K; }
+
+// ------------------------------------------------------------------------------------------------ encoder
+struct EncGeom {
+    int B = 0;
+    std::vector<int> img_off, tok_off;
+    long P[5] = {0, 0, 0, 0, 0};
+    int ntok = 0, max_tok = 0;
+    const int* d_img_off = nullptr; const int* d_img_hw = nullptr; const int* d_tok_off = nullptr;
+};
+
+static int plan_geometry(texocr_handle* h, const int32_t* hw, int B, EncGeom& g, cudaStream_t st) {
+    if (B <= 0) return fail(h, TEXOCR_ERR_ARG, "batch must be positive");
+    g.B = B;
+    g.img_off.assign(B + 1, 0); g.tok_off.assign(B + 1, 0);
+    for (int b = 0; b < B; ++b) {
+        const int H = hw[2 * b], W = hw[2 * b + 1];
+        if (H <= 0 || W <= 0 || H % 16 || W % 16 || H > 160 || W > 1008)
+            return fail(h, TEXOCR_ERR_ARG, "image %d is %dx%d: height and width must be multiples of 16 with H <= 160 and "
+                        "W <= 1008 (10x63 position grid, model/encoder.py:137-143)", b, H, W);
+        const long next = (long)g.img_off[b] + (long)H * W;
+        if (next > 0x7fffffffL / 64) return fail(h, TEXOCR_ERR_ARG, "batch too large: more than 2^31 stem activations");
+        g.img_off[b + 1] = (int)next;
+        const int n = (H / 16) * (W / 16) + 1;
+        g.tok_off[b + 1] = g.tok_off[b] + n;
+        g.max_tok = std::max(g.max_tok, n);
+    }
+    for (int l = 0; l <= 4; ++l) g.P[l] = g.img_off[B] >> (2 * l);
+    g.ntok = g.tok_off[B];
+    std::vector<int> v;
+    v.insert(v.end(), g.img_off.begin(), g.img_off.end());
+    v.insert(v.end(), hw, hw + 2 * B);
+    v.insert(v.end(), g.tok_off.begin(), g.tok_off.end());
+    int r = upload_ints(h, v, st);
+    if (r) return r;
+    g.d_img_off = h->geom.as<int>();
+    g.d_img_hw = g.d_img_off + (B + 1);
+    g.d_tok_off = g.d_img_hw + 2 * B;
+    return 0;
+}
+
+static int nchunk_for(long pixels, int B) {
+    long avg = pixels / std::max(B, 1);
+    long n = (avg + 63) / 64;
+    return (int)std::min<long>(32, std::max<long>(1, n));
+}
+
+static int run_backbone(texocr_handle* h, const float* d_img, const EncGeom& g, cudaStream_t st, const float** feat_out) {
+    const int B = g.B;
+    ENSURE(h->raw1, (size_t)g.P[1] * 64 * 4);
+    ENSURE(h->act2, (size_t)g.P[2] * 64 * 4);
+    ENSURE(h->actA, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->actB, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->rawMid, (size_t)g.P[2] * 128 * 4);
+    ENSURE(h->actMid, (size_t)g.P[2] * 128 * 4);
+    ENSURE(h->rawMid2, (size_t)g.P[2] * 64 * 4);
+    ENSURE(h->actMid2, (size_t)g.P[2] * 64 * 4);
+    ENSURE(h->raw3, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->rawDs, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->gn_partial, (size_t)B * 32 * 32 * 2 * 8);
+    for (int i = 0; i < 4; ++i) ENSURE(h->gn_stats[i], (size_t)B * 32 * 2 * 4);
+    float* stats[4] = {h->gn_stats[0].as<float>(), h->gn_stats[1].as<float>(), h->gn_stats[2].as<float>(), h->gn_stats[3].as<float>()};
+    double* partial = h->gn_partial.as<double>();
+
+    // stem: conv 7x7/s2 -> GN+ReLU -> maxpool 3x3/s2  [model/resnet.py:218-222]
+    LAUNCH(KC_STEM, 1, (double)g.P[0] * 4 + (double)g.P[1] * 64 * 4, 2.0 * 49 * 64 * g.P[1],
+           launch_stem_conv(d_img, h->stem_w, h->raw1.as<float>(), g.d_img_off, g.d_img_hw, B, (int)g.P[1], st));
+    int nc = nchunk_for(g.P[1], B);
+    LAUNCH(KC_GN_STATS, 2, (double)g.P[1] * 64 * 4, 0.0,
+           launch_gn_stats(h->raw1.as<float>(), 64, 1, g.d_img_off, B, nc, partial, stats[0], st));
+    LAUNCH(KC_GN_APPLY, 1, (double)g.P[1] * 64 * 4 + (double)g.P[2] * 64 * 4, 0.0,
+           launch_gn_apply_maxpool(h->raw1.as<float>(), stats[0], h->stem_g, h->stem_b, h->act2.as<float>(), g.d_img_off,
+                                   g.d_img_hw, B, (int)g.P[2], st));
+
+    const float* x = h->act2.as<float>();
+    int Cx = 64, Lx = 2;
+    float* pingpong[2] = {h->actA.as<float>(), h->actB.as<float>()};
+    int pp = 0;
+    size_t ci = 0;
+    const int depths[3] = {2, 4, 6};
+    auto conv = [&](const ConvW& cw, const float* in, int lin, int lout, float* out) -> int {
+        const long M = g.P[lout];
+        GemmArgs ga = mk_gemm(in, cw.cin, cw.w, cw.k * cw.k * cw.cin, out, cw.cout, (int)M, cw.cout, cw.k * cw.k * cw.cin,
+                              EPI_STORE, DT_F32, DT_F32, nullptr, nullptr, 0);
+        ConvGather cg{g.d_img_off, g.d_img_hw, B, lin, lout, cw.k, cw.stride, (cw.k == 3 && cw.stride == 1) ? 1 : 0, cw.cin};
+        if (!(cw.k == 1 && cw.stride == 1)) ga.conv = &cg;       // 1x1/s1 is a plain GEMM over the pixel rows
+        LAUNCH(KC_CONV, 1, gemm_bytes(ga, 4), gemm_flops(ga), launch_gemm_simt(ga, st));
+        return 0;
+    };
+    auto gstats = [&](const float* raw, int C, int level, float* stt) -> int {
+        LAUNCH(KC_GN_STATS, 2, (double)g.P[level] * C * 4, 0.0,
+               launch_gn_stats(raw, C, level, g.d_img_off, B, nchunk_for(g.P[level], B), partial, stt, st));
+        return 0;
+    };
+    int r;
+    for (int s = 0; s < 3; ++s)
+        for (int b = 0; b < depths[s]; ++b) {
+            const ConvW* ds = nullptr;
+            if (b == 0) ds = &h->convs[ci++];
+            const ConvW& c1 = h->convs[ci++];
+            const ConvW& c2 = h->convs[ci++];
+            const ConvW& c3 = h->convs[ci++];
+            const int Lout = Lx + (c2.stride == 2 ? 1 : 0);
+            if (ds) {
+                if ((r = conv(*ds, x, Lx, Lout, h->rawDs.as<float>()))) return r;
+                if ((r = gstats(h->rawDs.as<float>(), ds->cout, Lout, stats[3]))) return r;
+            }
+            if ((r = conv(c1, x, Lx, Lx, h->rawMid.as<float>()))) return r;
+            if ((r = gstats(h->rawMid.as<float>(), c1.cout, Lx, stats[0]))) return r;
+            {
+                GnApplyArgs a{};
+                a.raw = h->rawMid.as<float>(); a.stats = stats[0]; a.gamma = c1.gamma; a.beta = c1.beta;
+                a.out = h->actMid.as<float>(); a.C = c1.cout; a.level = Lx; a.relu = 1;
+                LAUNCH(KC_GN_APPLY, 1, (double)g.P[Lx] * a.C * 8, 0.0, launch_gn_apply(a, g.d_img_off, B, nchunk_for(g.P[Lx], B), st));
+            }
+            if ((r = conv(c2, h->actMid.as<float>(), Lx, Lout, h->rawMid2.as<float>()))) return r;
+            if ((r = gstats(h->rawMid2.as<float>(), c2.cout, Lout, stats[1]))) return r;
+            {
+                GnApplyArgs a{};
+                a.raw = h->rawMid2.as<float>(); a.stats = stats[1]; a.gamma = c2.gamma; a.beta = c2.beta;
+                a.out = h->actMid2.as<float>(); a.C = c2.cout; a.level = Lout; a.relu = 1;
+                LAUNCH(KC_GN_APPLY, 1, (double)g.P[Lout] * a.C * 8, 0.0, launch_gn_apply(a, g.d_img_off, B, nchunk_for(g.P[Lout], B), st));
+            }
+            if ((r = conv(c3, h->actMid2.as<float>(), Lout, Lout, h->raw3.as<float>()))) return r;
+            if ((r = gstats(h->raw3.as<float>(), c3.cout, Lout, stats[2]))) return r;
+            {   // out = ReLU(GN3(y) + res)   [model/resnet.py:147-148]
+                GnApplyArgs a{};
+                a.raw = h->raw3.as<float>(); a.stats = stats[2]; a.gamma = c3.gamma; a.beta = c3.beta;
+                if (ds) { a.raw2 = h->rawDs.as<float>(); a.stats2 = stats[3]; a.gamma2 = ds->gamma; a.beta2 = ds->beta; }
+                else a.res = x;
+                a.out = pingpong[pp]; a.C = c3.cout; a.level = Lout; a.relu = 1;
+                LAUNCH(KC_GN_APPLY, 1, (double)g.P[Lout] * a.C * 12, 0.0, launch_gn_apply(a, g.d_img_off, B, nchunk_for(g.P[Lout], B), st));
+            }
+            x = pingpong[pp]; pp ^= 1; Cx = c3.cout; Lx = Lout;
+        }
+    (void)Cx;
+    h->last_backbone_pixels = (int)g.P[4];
+    *feat_out = x;
+    return 0;
+}
+
+// One (self-attention | cross-attention | MLP) sub-layer tail shared by encoder / decoder / decode step.
+struct RowCtx {
+    int rows; int kc_gemm, kc_row;
+    const float* ln_g; const float* ln_b;
+};
+
+static int sub_attn_out(texocr_handle* h, const RowCtx& rc, const AttnW& w, cudaStream_t st) {
+    // y = o.Wo^T + bo -> GLU -> + residual   [model/attention.py:96-99,180 ; 254]
+    GemmArgs ga = mk_gemm(h->o.p, 512, w.wo, 512, h->s.p, 256, rc.rows, 512, 512, EPI_GLU_RES, h->dt, DT_F32, w.bo, h->x.as<float>(), 256);
+    LAUNCH(rc.kc_gemm, 1, gemm_bytes(ga, h->esz), gemm_flops(ga), run_gemm(h, ga, st));
+    return 0;
+}
+static int sub_mlp(texocr_handle* h, const RowCtx& rc, const MlpW& w, cudaStream_t st) {
+    GemmArgs g1 = mk_gemm(h->xn.p, 256, w.w1, 256, h->hid.p, 1024, rc.rows, 2048, 256, EPI_GEGLU, h->dt, h->dt, w.b1, nullptr, 0);
+    LAUNCH(rc.kc_gemm, 1, gemm_bytes(g1, h->esz), gemm_flops(g1), run_gemm(h, g1, st));
+    GemmArgs g2 = mk_gemm(h->hid.p, 1024, w.w2, 1024, h->s.p, 256, rc.rows, 256, 1024, EPI_BIAS_RES, h->dt, DT_F32, w.b2, h->x.as<float>(), 256);
+    LAUNCH(rc.kc_gemm, 1, gemm_bytes(g2, h->esz), gemm_flops(g2), run_gemm(h, g2, st));
+    return 0;
+}
+// x = LN(s); xn = LN(x)  (shared LayerNorm twice, model/attention.py:242-259), or the stack's final norm.
+static int sub_norm(texocr_handle* h, const RowCtx& rc, bool last, const float* fin_g, const float* fin_b, float* fin_out_f,
+                    void* fin_out_a, cudaStream_t st) {
+    Ln2Args a{};
+    a.in = h->s.as<float>(); a.rows = rc.rows; a.dt_a = h->dt;
+    if (!last) { a.g1 = rc.ln_g; a.b1 = rc.ln_b; a.g2 = rc.ln_g; a.b2 = rc.ln_b; a.o1f = h->x.as<float>(); a.o2a = h->xn.p; }
+    else { a.g1 = fin_g; a.b1 = fin_b; a.o1f = fin_out_f; a.o1a = fin_out_a; }
+    LAUNCH(rc.kc_row, 1, (double)rc.rows * 256 * (4 + 4 + h->esz), 0.0, launch_ln2(a, st));
+    return 0;
+}
+
+static int ensure_rows(texocr_handle* h, long rows) {
+    ENSURE(h->x, (size_t)rows * 256 * 4);
+    ENSURE(h->s, (size_t)rows * 256 * 4);
+    ENSURE(h->xn, (size_t)rows * 256 * h->esz);
+    ENSURE(h->qkv, (size_t)rows * 1536 * h->esz);
+    ENSURE(h->o, (size_t)rows * 512 * h->esz);
+    ENSURE(h->hid, (size_t)rows * 1024 * h->esz);
+    return 0;
+}
+
+// images (device) -> h->enc_out (fp32) and h->enc_a (GEMM operand type)
+static int run_encoder(texocr_handle* h, const float* d_img, const EncGeom& g, cudaStream_t st) {
+    const texocr_config& c = h->cfg;
+    int r;
+    ENSURE(h->proj_out, (size_t)g.P[4] * 256 * 4);
+    if (c.encoder_kind == TEXOCR_ENC_HYBRID) {
+        const float* feat = nullptr;
+        if ((r = run_backbone(h, d_img, g, st, &feat))) return r;
+        const void* a_ptr = feat;
+        if (h->dt != DT_F32) {
+            ENSURE(h->backbone_a, (size_t)g.P[4] * 1024 * h->esz);
+            LAUNCH(KC_MISC, 1, (double)g.P[4] * 1024 * 6, 0.0, launch_cast_f32_to(feat, h->backbone_a.p, g.P[4] * 1024, h->dt, st));
+            a_ptr = h->backbone_a.p;
+        }
+        GemmArgs ga = mk_gemm(a_ptr, 1024, h->proj_w, 1024, h->proj_out.p, 256, (int)g.P[4], 256, 1024, EPI_STORE, h->dt, DT_F32, h->proj_b, nullptr, 0);
+        LAUNCH(KC_ENC_GEMM, 1, gemm_bytes(ga, h->esz), gemm_flops(ga), run_gemm(h, ga, st));
+    } else {
+        ENSURE(h->patch_cols, (size_t)g.P[4] * 256 * 4);
+        LAUNCH(KC_MISC, 1, (double)g.P[0] * 8, 0.0, launch_im2col_patch(d_img, h->patch_cols.as<float>(), g.d_img_off, g.d_img_hw, g.B, (int)g.P[4], st));
+        const void* a_ptr = h->patch_cols.p;
+        if (h->dt != DT_F32) {
+            ENSURE(h->backbone_a, (size_t)g.P[4] * 256 * h->esz);
+            LAUNCH(KC_MISC, 1, (double)g.P[4] * 256 * 6, 0.0, launch_cast_f32_to(h->patch_cols.as<float>(), h->backbone_a.p, g.P[4] * 256, h->dt, st));
+            a_ptr = h->backbone_a.p;
+        }
+        GemmArgs ga = mk_gemm(a_ptr, 256, h->proj_w, 256, h->proj_out.p, 256, (int)g.P[4], 256, 256, EPI_STORE, h->dt, DT_F32, h->proj_b, nullptr, 0);
+        LAUNCH(KC_ENC_GEMM, 1, gemm_bytes(ga, h->esz), gemm_flops(ga), run_gemm(h, ga, st));
+    }
+    const int R = g.ntok;
+    if ((r = ensure_rows(h, R))) return r;
+    ENSURE(h->enc_out, (size_t)R * 256 * 4);
+    ENSURE(h->enc_a, (size_t)R * 256 * h->esz);
+    LAUNCH(KC_ENC_ROW, 1, (double)R * 256 * 12, 0.0,
+           launch_assemble_tokens(h->proj_out.as<float>(), h->cls, h->pos, h->x.as<float>(), g.d_img_off, g.d_img_hw, g.d_tok_off, g.B, R, st));
+    RowCtx rc{R, KC_ENC_GEMM, KC_ENC_ROW, h->enc_ln_g, h->enc_ln_b};
+    {
+        Ln2Args a{};
+        a.in = h->x.as<float>(); a.rows = R; a.g2 = h->enc_ln_g; a.b2 = h->enc_ln_b; a.o2a = h->xn.p; a.dt_a = h->dt;
+        LAUNCH(KC_ENC_ROW, 1, (double)R * 256 * (4 + h->esz), 0.0, launch_ln2(a, st));
+    }
+    for (int l = 0; l < c.enc_layers; ++l) {
+        GemmArgs gq = mk_gemm(h->xn.p, 256, h->enc_attn[l].wqkv, 256, h->qkv.p, 1536, R, 1536, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+        LAUNCH(KC_ENC_GEMM, 1, gemm_bytes(gq, h->esz), gemm_flops(gq), run_gemm(h, gq, st));
+        AttnVarlenArgs av{};
+        const char* base = (const char*)h->qkv.p;
+        av.q = base; av.k = base + 512 * h->esz; av.v = base + 1024 * h->esz; av.ldq = av.ldk = av.ldv = 1536;
+        av.o = h->o.p; av.ldo = 512; av.q_off = g.d_tok_off; av.k_off = g.d_tok_off; av.batch = g.B; av.max_q = g.max_tok;
+        av.causal = 0; av.dt = h->dt;
+        double aflops = 0.0;
+        for (int b = 0; b < g.B; ++b) { const double n = g.tok_off[b + 1] - g.tok_off[b]; aflops += 4.0 * n * n * 512; }
+        LAUNCH(KC_ENC_ATTN, 1, (double)R * 2048 * h->esz, aflops, launch_attn_varlen(av, st));
+        if ((r = sub_attn_out(h, rc, h->enc_attn[l], st))) return r;
+        if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+        if ((r = sub_mlp(h, rc, h->enc_mlp[l], st))) return r;
+        const bool last = (l == c.enc_layers - 1);
+        if ((r = sub_norm(h, rc, last, h->enc_norm_g, h->enc_norm_b, h->enc_out.as<float>(), h->dt == DT_F32 ? nullptr : h->enc_a.p, st))) return r;
+    }
+    return 0;
+}
+
+// memory (device fp32 or already-typed copy) -> h->crosskv [ntok, L*1024]   (K/V of every cross-attention layer, once)
+static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_typed, int ntok, cudaStream_t st) {
+    const int L = h->cfg.dec_layers;
+    ENSURE(h->crosskv, (size_t)ntok * L * 1024 * h->esz);
+    const void* a_ptr = enc_f32;
+    if (h->dt != DT_F32) {
+        if (!enc_typed) {
+            ENSURE(h->enc_a, (size_t)ntok * 256 * h->esz);
+            LAUNCH(KC_MISC, 1, (double)ntok * 256 * 6, 0.0, launch_cast_f32_to(enc_f32, h->enc_a.p, (int64_t)ntok * 256, h->dt, st));
+            enc_typed = h->enc_a.p;
+        }
+        a_ptr = enc_typed;
+    }
+    GemmArgs ga = mk_gemm(a_ptr, 256, h->w_crosskv, 256, h->crosskv.p, L * 1024, ntok, L * 1024, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+    LAUNCH(KC_CROSSKV_GEMM, 1, gemm_bytes(ga, h->esz), gemm_flops(ga), run_gemm(h, ga, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decode step
+struct DecState {
+    int64_t* cur_tok; int* step; int* done_step; int* block_counter; int* seen;
+};
+static DecState dec_state(texocr_handle* h, int B) {
+    DecState d;
+    char* p = (char*)h->dec_state.p;
+    d.cur_tok = (int64_t*)p;
+    int* ip = (int*)(p + (size_t)B * 8);
+    d.step = ip; d.done_step = ip + 1; d.block_counter = ip + 2; d.seen = ip + 4;
+    return d;
+}
+
+// One greedy step for B rows.  `t_host` is only used for the profiler's byte accounting (-1: unknown).
+static int enqueue_decode_step(texocr_handle* h, int B, int tcap, int eos, const int* d_enc_off, int max_s, double sum_s,
+                               int t_host, cudaStream_t st) {
+    const texocr_config& c = h->cfg;
+    const int L = c.dec_layers;
+    DecState ds = dec_state(h, B);
+    RowCtx rc{B, KC_DEC_GEMM, KC_DEC_ROW, h->dec_ln_g, h->dec_ln_b};
+    int r;
+    LAUNCH(KC_DEC_ROW, 1, (double)B * 256 * (8 + 4 + h->esz), 0.0,
+           launch_embed_ln(ds.cur_tok, ds.step, 1, B, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b, h->x.as<float>(), h->xn.p, h->dt, st));
+    const double tkeys = t_host >= 0 ? (double)(t_host + 1) : 0.0;
+    for (int l = 0; l < L; ++l) {
+        // ---- causal self-attention over the KV cache
+        GemmArgs gq = mk_gemm(h->xn.p, 256, h->dec_self[l].wqkv, 256, h->qkv.p, 1536, B, 1536, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gq, h->esz), gemm_flops(gq), run_gemm(h, gq, st));
+        AttnDecodeArgs ad{};
+        char* qb = (char*)h->qkv.p;
+        char* kv = (char*)h->kvcache.p + (size_t)l * B * tcap * 1024 * h->esz;
+        ad.q = qb; ad.ldq = 1536; ad.knew = qb + 512 * h->esz; ad.vnew = qb + 1024 * h->esz; ad.ldnew = 1536;
+        ad.kcache = kv; ad.vcache = kv + 512 * h->esz; ad.ldkv = 1024; ad.batch_stride = (int64_t)tcap * 1024;
+        ad.step = ds.step; ad.o = h->o.p; ad.ldo = 512; ad.batch = B; ad.dt = h->dt;
+        LAUNCH(KC_DEC_ATTN_SELF, 1, (double)B * tkeys * 1024 * h->esz, 4.0 * B * tkeys * 512, launch_attn_decode(ad, tcap, st));
+        if ((r = sub_attn_out(h, rc, h->dec_self[l], st))) return r;
+        if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+        // ---- cross-attention over the (pre-projected) encoder memory
+        GemmArgs gc = mk_gemm(h->xn.p, 256, h->dec_cross[l].wq, 256, h->qkv.p, 512, B, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gc, h->esz), gemm_flops(gc), run_gemm(h, gc, st));
+        AttnDecodeArgs ac{};
+        char* ckv = (char*)h->crosskv.p + (size_t)l * 1024 * h->esz;
+        ac.q = h->qkv.p; ac.ldq = 512; ac.kcache = ckv; ac.vcache = ckv + 512 * h->esz; ac.ldkv = L * 1024;
+        ac.k_off = d_enc_off; ac.o = h->o.p; ac.ldo = 512; ac.batch = B; ac.dt = h->dt;
+        LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * 1024 * h->esz, 4.0 * sum_s * 512, launch_attn_decode(ac, max_s, st));
+        if ((r = sub_attn_out(h, rc, h->dec_cross[l], st))) return r;
+        if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+        // ---- GeGLU MLP
+        if ((r = sub_mlp(h, rc, h->dec_mlp[l], st))) return r;
+        if ((r = sub_norm(h, rc, l == L - 1, h->dec_norm_g, h->dec_norm_b, nullptr, h->xn.p, st))) return r;
+    }
+    GemmArgs gl = mk_gemm(h->xn.p, 256, h->w_logits, 256, h->logits.p, c.vocab_size, B, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
+    LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gl, h->esz), gemm_flops(gl), run_gemm(h, gl, st));
+    ArgmaxArgs aa{};
+    aa.logits = h->logits.as<float>(); aa.B = B; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>(); aa.out_ld = tcap;
+    aa.cur_tok = ds.cur_tok; aa.step = ds.step; aa.seen_eos = ds.seen; aa.done_step = ds.done_step; aa.block_counter = ds.block_counter;
+    aa.eos = eos;
+    LAUNCH(KC_DEC_ARGMAX, 1, (double)B * c.vocab_size * 4, 0.0, launch_argmax_step(aa, st));
+    return 0;
+}
+
+// enc memory must already be projected into h->crosskv; d_enc_off = per-row token offsets (device, B+1)
+static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const int* d_enc_off, int max_s, double sum_s, int B,
+                        int max_len, int64_t* out_ids, int32_t* n_steps, cudaStream_t st) {
+    const texocr_config& c = h->cfg;
+    if (max_len <= 0) return fail(h, TEXOCR_ERR_ARG, "max_len must be positive");
+    if (max_len > c.max_length)
+        return fail(h, TEXOCR_ERR_ARG, "max_len %d > config max_length %d: the KV cache is position-indexed; the reference's "
+                    "sliding-window regime (model/decoder.py:99-100) is not implemented", max_len, c.max_length);
+    const int tcap = max_len;
+    int r;
+    if ((r = ensure_rows(h, B))) return r;
+    ENSURE(h->logits, (size_t)B * c.vocab_size * 4);
+    ENSURE(h->kvcache, (size_t)c.dec_layers * B * tcap * 1024 * h->esz);
+    ENSURE(h->dec_state, (size_t)B * 8 + 16 + (size_t)B * 4);
+    ENSURE(h->out_ids, (size_t)B * tcap * 8);
+    if (!h->h_poll) CK(cudaMallocHost(&h->h_poll, 64));
+    DecState ds = dec_state(h, B);
+    CK(cudaMemsetAsync((char*)h->dec_state.p + (size_t)B * 8, 0, 16 + (size_t)B * 4, st));
+    CK(cudaMemcpyAsync(ds.cur_tok, d_start, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+
+    const bool graph_ok = h->use_graph && !h->prof_on;
+    if (graph_ok) {
+        const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
+                         h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv.p && h->gkey.x == h->x.p;
+        if (!hit) {
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+            const int64_t before = h->launches;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            r = enqueue_decode_step(h, B, tcap, eos, d_enc_off, max_s, sum_s, -1, st);
+            cudaError_t ce = cudaStreamEndCapture(st, &h->graph);
+            if (r) return r;
+            CK(ce);
+            CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+            h->gkey.kernels = (int)(h->launches - before);
+            h->launches = before;        // capture does not execute
+            h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s;
+            h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv.p; h->gkey.x = h->x.p;
+        }
+    }
+    // Host runs ahead of the device by at most 2*POLL steps; an early exit costs at most that many extra steps.
+    const int POLL = 16;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int issued = 0, polls = 0;
+    bool stop = false;
+    for (int t = 0; t < max_len && !stop; ++t) {
+        if (graph_ok) { CK(cudaGraphLaunch(h->graph_exec, st)); h->launches += h->gkey.kernels; }
+        else if ((r = enqueue_decode_step(h, B, tcap, eos, d_enc_off, max_s, sum_s, t, st))) return r;
+        ++issued;
+        if (eos >= 0 && issued % POLL == 0 && t + 1 < max_len) {
+            const int slot = polls & 1;
+            if (polls >= 1) {      // wait for the PREVIOUS poll (issued POLL steps ago), keeps the queue non-empty
+                CK(cudaEventSynchronize(ev[slot ^ 1]));
+                if (h->h_poll[slot ^ 1] > 0) stop = true;
+            }
+            CK(cudaMemcpyAsync(&h->h_poll[slot], ds.done_step, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ev[slot], st));
+            ++polls;
+        }
+    }
+    CK(cudaMemcpyAsync(&h->h_poll[2], ds.done_step, 4, cudaMemcpyDeviceToHost, st));
+    if ((r = from_device(h, out_ids, h->out_ids.p, (size_t)B * tcap * 8, st))) return r;
+    CK(cudaStreamSynchronize(st));
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    const int done = h->h_poll[2];
+    *n_steps = done > 0 ? done : max_len;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* texocr_last_error(const texocr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int texocr_create(const texocr_config* cfg, int device, texocr_handle** out) {
+    texocr_handle* h = nullptr;
+    if (!cfg || !out) return fail(h, TEXOCR_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != TEXOCR_ABI_VERSION) return fail(h, TEXOCR_ERR_ARG, "ABI version mismatch: header %d, library %d", cfg->abi_version, TEXOCR_ABI_VERSION);
+    if (cfg->vocab_size <= 0 || cfg->vocab_size % 4) return fail(h, TEXOCR_ERR_ARG, "vocab_size must be a positive multiple of 4");
+    if (cfg->max_length <= 0 || cfg->enc_layers <= 0 || cfg->dec_layers <= 0) return fail(h, TEXOCR_ERR_ARG, "bad layer counts / max_length");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(h, TEXOCR_ERR_NODEVICE, "no CUDA device: texocr_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(h, TEXOCR_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(h, TEXOCR_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    h = new texocr_handle();
+    h->cfg = *cfg; h->device = device;
+    h->dt = cfg->precision == TEXOCR_BF16 ? DT_BF16 : DT_F32;
+    h->esz = h->dt == DT_BF16 ? 2 : 4;
+    cudaError_t e = cudaEventCreateWithFlags(&h->geom_ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, TEXOCR_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return 0;
+}
+
+void texocr_destroy(texocr_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    for (void* p : h->weight_allocs) cudaFree(p);
+    DevBuf* bufs[] = {&h->geom, &h->img_stage, &h->raw1, &h->act2, &h->actA, &h->actB, &h->rawMid, &h->actMid, &h->rawMid2, &h->actMid2,
+                      &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
+                      &h->proj_out, &h->patch_cols, &h->backbone_a, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
+                      &h->enc_out, &h->enc_a, &h->crosskv, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
+                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (h->h_geom) cudaFreeHost(h->h_geom);
+    if (h->h_poll) cudaFreeHost(h->h_poll);
+    if (h->geom_ev) cudaEventDestroy(h->geom_ev);
+    for (auto& p : h->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    delete h;
+}
+
+int texocr_set_weight(texocr_handle* h, const char* name, const float* data, int32_t ndim, const int64_t* shape) {
+    if (!h || !name || !data || ndim < 0 || ndim > 8) return fail(h, TEXOCR_ERR_ARG, "bad argument to texocr_set_weight");
+    if (h->finalized) return fail(h, TEXOCR_ERR_STATE, "weights already finalised; create a new handle to load other weights");
+    CK(cudaSetDevice(h->device));
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    const int64_t n = t.numel();
+    if (n <= 0 || n > (int64_t)1 << 31) return fail(h, TEXOCR_ERR_ARG, "bad shape for '%s'", name);
+    t.data.resize((size_t)n);
+    if (is_device_ptr(data)) CK(cudaMemcpy(t.data.data(), data, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    else memcpy(t.data.data(), data, (size_t)n * 4);
+    h->sd[name] = std::move(t);
+    return 0;
+}
+
+int texocr_finalize_weights(texocr_handle* h) {
+    if (!h) return TEXOCR_ERR_ARG;
+    if (h->finalized) return fail(h, TEXOCR_ERR_STATE, "weights already finalised");
+    CK(cudaSetDevice(h->device));
+    return finalize_weights(h);
+}
+
+#define ENTRY_CHECKS()                                                                                     \
+    if (!h) return TEXOCR_ERR_ARG;                                                                         \
+    if (!h->finalized) return fail(h, TEXOCR_ERR_STATE, "weights not finalised (texocr_finalize_weights)"); \
+    CK(cudaSetDevice(h->device));                                                                          \
+    cudaStream_t st = (cudaStream_t)stream
+
+static long total_pixels(const int32_t* hw, int B) {
+    long n = 0;
+    for (int b = 0; b < B; ++b) n += (long)hw[2 * b] * hw[2 * b + 1];
+    return n;
+}
+
+int texocr_encode(texocr_handle* h, const float* images, const int32_t* hw, int32_t batch, float* enc_out, void* stream) {
+    ENTRY_CHECKS();
+    if (!images || !hw || !enc_out) return fail(h, TEXOCR_ERR_ARG, "null argument");
+    EncGeom g;
+    int r;
+    if ((r = plan_geometry(h, hw, batch, g, st))) return r;
+    const void* d_img = nullptr;
+    if ((r = to_device(h, images, (size_t)total_pixels(hw, batch) * 4, h->img_stage, &d_img, st))) return r;
+    if ((r = run_encoder(h, (const float*)d_img, g, st))) return r;
+    if ((r = from_device(h, enc_out, h->enc_out.p, (size_t)g.ntok * 256 * 4, st))) return r;
+    if (!is_device_ptr(enc_out)) CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int memory_offsets(texocr_handle* h, const int32_t* enc_len, int B, std::vector<int>& off, int* max_s) {
+    off.assign(B + 1, 0);
+    *max_s = 0;
+    for (int b = 0; b < B; ++b) {
+        if (enc_len[b] <= 0) return fail(h, TEXOCR_ERR_ARG, "enc_len[%d] must be positive", b);
+        off[b + 1] = off[b] + enc_len[b];
+        *max_s = std::max(*max_s, (int)enc_len[b]);
+    }
+    return 0;
+}
+
+int texocr_decoder_logits(texocr_handle* h, const int64_t* ids, const uint8_t* mask, const float* enc, const int32_t* enc_len,
+                          int32_t batch, int32_t T, float* logits_out, void* stream) {
+    ENTRY_CHECKS();
+    const texocr_config& c = h->cfg;
+    if (!ids || !enc || !enc_len || !logits_out || batch <= 0 || T <= 0) return fail(h, TEXOCR_ERR_ARG, "bad argument");
+    if (T > c.max_length) return fail(h, TEXOCR_ERR_ARG, "T %d exceeds the positional table (max_length %d)", T, c.max_length);
+    const int B = batch, L = c.dec_layers;
+    const long R = (long)B * T;
+    std::vector<int> enc_off;
+    int max_s, r;
+    if ((r = memory_offsets(h, enc_len, B, enc_off, &max_s))) return r;
+    const int ntok = enc_off[B];
+    std::vector<int> v;
+    for (int b = 0; b <= B; ++b) v.push_back(b * T);
+    v.insert(v.end(), enc_off.begin(), enc_off.end());
+    if ((r = upload_ints(h, v, st))) return r;
+    const int* d_row_off = h->geom.as<int>();
+    const int* d_enc_off = d_row_off + (B + 1);
+    const void *d_ids, *d_mask = nullptr, *d_enc;
+    if ((r = to_device(h, ids, (size_t)R * 8, h->ids_stage, &d_ids, st))) return r;
+    if (mask && (r = to_device(h, mask, (size_t)R, h->mask_stage, &d_mask, st))) return r;
+    if ((r = to_device(h, enc, (size_t)ntok * 256 * 4, h->enc_stage, &d_enc, st))) return r;
+    if ((r = ensure_rows(h, R))) return r;
+    float* d_logits = logits_out;
+    if (!is_device_ptr(logits_out)) { ENSURE(h->logits, (size_t)R * c.vocab_size * 4); d_logits = h->logits.as<float>(); }
+    if ((r = run_crosskv(h, (const float*)d_enc, nullptr, ntok, st))) return r;
+
+    RowCtx rc{(int)R, KC_TF_GEMM, KC_TF_ROW, h->dec_ln_g, h->dec_ln_b};
+    LAUNCH(KC_TF_ROW, 1, (double)R * 256 * 12, 0.0,
+           launch_embed_ln((const int64_t*)d_ids, nullptr, T, (int)R, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b,
+                           h->x.as<float>(), h->xn.p, h->dt, st));
+    for (int l = 0; l < L; ++l) {
+        GemmArgs gq = mk_gemm(h->xn.p, 256, h->dec_self[l].wqkv, 256, h->qkv.p, 1536, (int)R, 1536, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+        LAUNCH(KC_TF_GEMM, 1, gemm_bytes(gq, h->esz), gemm_flops(gq), run_gemm(h, gq, st));
+        AttnVarlenArgs av{};
+        const char* base = (const char*)h->qkv.p;
+        av.q = base; av.k = base + 512 * h->esz; av.v = base + 1024 * h->esz; av.ldq = av.ldk = av.ldv = 1536;
+        av.o = h->o.p; av.ldo = 512; av.q_off = d_row_off; av.k_off = d_row_off; av.batch = B; av.max_q = T; av.causal = 1; av.dt = h->dt;
+        av.q_mask = (const uint8_t*)d_mask; av.k_mask = (const uint8_t*)d_mask;
+        LAUNCH(KC_TF_ATTN, 1, (double)R * 2048 * h->esz, 2.0 * B * (double)T * T * 512, launch_attn_varlen(av, st));
+        if ((r = sub_attn_out(h, rc, h->dec_self[l], st))) return r;
+        if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+        GemmArgs gc = mk_gemm(h->xn.p, 256, h->dec_cross[l].wq, 256, h->qkv.p, 512, (int)R, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+        LAUNCH(KC_TF_GEMM, 1, gemm_bytes(gc, h->esz), gemm_flops(gc), run_gemm(h, gc, st));
+        AttnVarlenArgs ac{};
+        const char* ckv = (const char*)h->crosskv.p + (size_t)l * 1024 * h->esz;
+        ac.q = h->qkv.p; ac.ldq = 512; ac.k = ckv; ac.v = ckv + 512 * h->esz; ac.ldk = ac.ldv = L * 1024;
+        ac.o = h->o.p; ac.ldo = 512; ac.q_off = d_row_off; ac.k_off = d_enc_off; ac.batch = B; ac.max_q = T; ac.causal = 0; ac.dt = h->dt;
+        ac.q_mask = (const uint8_t*)d_mask;      // enc_mask is never passed by the reference: keys unmasked (model/attention.py:138-141)
+        LAUNCH(KC_TF_ATTN, 1, (double)R * 512 * h->esz + (double)ntok * 1024 * h->esz, 4.0 * T * (double)ntok * 512, launch_attn_varlen(ac, st));
+        if ((r = sub_attn_out(h, rc, h->dec_cross[l], st))) return r;
+        if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+        if ((r = sub_mlp(h, rc, h->dec_mlp[l], st))) return r;
+        if ((r = sub_norm(h, rc, l == L - 1, h->dec_norm_g, h->dec_norm_b, nullptr, h->xn.p, st))) return r;
+    }
+    GemmArgs gl = mk_gemm(h->xn.p, 256, h->w_logits, 256, d_logits, c.vocab_size, (int)R, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
+    LAUNCH(KC_TF_GEMM, 1, gemm_bytes(gl, h->esz), gemm_flops(gl), run_gemm(h, gl, st));
+    if (d_logits != logits_out) {
+        if ((r = from_device(h, logits_out, d_logits, (size_t)R * c.vocab_size * 4, st))) return r;
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int texocr_decoder_generate(texocr_handle* h, const int64_t* start_tokens, int32_t eos_tok, const float* enc, const int32_t* enc_len,
+                            int32_t batch, int32_t max_len, int64_t* out_ids, int32_t* n_steps, void* stream) {
+    ENTRY_CHECKS();
+    if (!start_tokens || !enc || !enc_len || !out_ids || !n_steps || batch <= 0) return fail(h, TEXOCR_ERR_ARG, "bad argument");
+    std::vector<int> enc_off;
+    int max_s, r;
+    if ((r = memory_offsets(h, enc_len, batch, enc_off, &max_s))) return r;
+    const int ntok = enc_off[batch];
+    if ((r = upload_ints(h, enc_off, st))) return r;
+    const void *d_enc, *d_start;
+    if ((r = to_device(h, enc, (size_t)ntok * 256 * 4, h->enc_stage, &d_enc, st))) return r;
+    if ((r = to_device(h, start_tokens, (size_t)batch * 8, h->ids_stage, &d_start, st))) return r;
+    if ((r = run_crosskv(h, (const float*)d_enc, nullptr, ntok, st))) return r;
+    return run_generate(h, (const int64_t*)d_start, eos_tok, h->geom.as<int>(), max_s, (double)ntok, batch, max_len, out_ids, n_steps, st);
+}
+
+int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, int32_t batch, int32_t max_len, int64_t* out_ids,
+                    int32_t* n_steps, void* stream) {
+    ENTRY_CHECKS();
+    if (!images || !hw || !out_ids || !n_steps) return fail(h, TEXOCR_ERR_ARG, "null argument");
+    EncGeom g;
+    int r;
+    if ((r = plan_geometry(h, hw, batch, g, st))) return r;
+    const void* d_img = nullptr;
+    if ((r = to_device(h, images, (size_t)total_pixels(hw, batch) * 4, h->img_stage, &d_img, st))) return r;
+    std::vector<int64_t> start((size_t)batch, (int64_t)h->cfg.bos_token);      // model/ocr_model.py:57
+    ENSURE(h->ids_stage, (size_t)batch * 8);
+    CK(cudaMemcpy(h->ids_stage.p, start.data(), (size_t)batch * 8, cudaMemcpyHostToDevice));
+    if ((r = run_encoder(h, (const float*)d_img, g, st))) return r;
+    if ((r = run_crosskv(h, h->enc_out.as<float>(), h->dt == DT_F32 ? nullptr : h->enc_a.p, g.ntok, st))) return r;
+    return run_generate(h, h->ids_stage.as<int64_t>(), h->cfg.eos_token, g.d_tok_off, g.max_tok, (double)g.ntok, batch, max_len, out_ids, n_steps, st);
+}
+
+int texocr_cross_entropy(texocr_handle* h, const float* logits, const int64_t* targets, int64_t rows, float* loss_out, void* stream) {
+    ENTRY_CHECKS();
+    if (!logits || !targets || !loss_out || rows <= 0) return fail(h, TEXOCR_ERR_ARG, "bad argument");
+    const int V = h->cfg.vocab_size;
+    int r;
+    const void *d_logits, *d_tgt;
+    if ((r = to_device(h, logits, (size_t)rows * V * 4, h->logits, &d_logits, st))) return r;
+    if ((r = to_device(h, targets, (size_t)rows * 8, h->tgt_stage, &d_tgt, st))) return r;
+    ENSURE(h->row_loss, (size_t)rows * 4);
+    ENSURE(h->scalars, 64);
+    float* d_loss = is_device_ptr(loss_out) ? loss_out : h->scalars.as<float>();
+    LAUNCH(KC_TF_ROW, 2, (double)rows * V * 4, 0.0, launch_cross_entropy((const float*)d_logits, (const int64_t*)d_tgt, rows, V, h->row_loss.as<float>(), d_loss, st));
+    if (d_loss != loss_out) {
+        CK(cudaMemcpyAsync(loss_out, d_loss, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int64_t texocr_kernel_launches(const texocr_handle* h) { return h ? h->launches : 0; }
+
+int texocr_profile_enable(texocr_handle* h, int32_t on) {
+    if (!h) return TEXOCR_ERR_ARG;
+    h->prof_on = on != 0;
+    return 0;
+}
+
+int texocr_profile_read(texocr_handle* h, texocr_profile_row* rows, int32_t cap) {
+    if (!h || !rows) return TEXOCR_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    for (auto& p : h->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            h->prof_ms[p.cls] += ms; h->prof_bytes[p.cls] += p.bytes; h->prof_flops[p.cls] += p.flops; h->prof_n[p.cls] += 1;
+        }
+        h->ev_pool.push_back(p.e0); h->ev_pool.push_back(p.e1);
+    }
+    h->prof.clear();
+    int n = 0;
+    for (int k = 0; k < KC_COUNT && n < cap; ++k) {
+        if (!h->prof_n[k]) continue;
+        memset(&rows[n], 0, sizeof rows[n]);
+        strncpy(rows[n].name, kclass_name[k], sizeof rows[n].name - 1);
+        rows[n].launches = h->prof_n[k]; rows[n].ms = h->prof_ms[k]; rows[n].bytes = h->prof_bytes[k]; rows[n].flops = h->prof_flops[k];
+        ++n;
+    }
+    for (int k = 0; k < KC_COUNT; ++k) { h->prof_ms[k] = h->prof_bytes[k] = h->prof_flops[k] = 0; h->prof_n[k] = 0; }
+    return n;
+}
+
+int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return TEXOCR_ERR_ARG;
+    if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
+    if (!strcmp(name, "tcgen05")) {
+        h->use_tcgen05 = value != 0;
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        return 0;
+    }
+    return fail(h, TEXOCR_ERR_ARG, "unknown option '%s'", name);
+}
+
+int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_t cap_elems) {
+    if (!h || !name || !out) return TEXOCR_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    if (!strcmp(name, "backbone")) {
+        const int64_t n = (int64_t)h->last_backbone_pixels * 1024;
+        if (n <= 0) return fail(h, TEXOCR_ERR_STATE, "no backbone activation recorded");
+        if (n > cap_elems) return fail(h, TEXOCR_ERR_ARG, "buffer too small: need %lld floats", (long long)n);
+        // the last block wrote into whichever ping-pong buffer is current: 12 blocks -> pingpong[1] (actB)
+        const float* src = h->actB.as<float>();
+        CK(cudaMemcpy(out, src, (size_t)n * 4, is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+        return n;
+    }
+    return fail(h, TEXOCR_ERR_ARG, "unknown debug tap '%s'", name);
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Engine state behind the C-ABI handle (include/texocr.h).  Host-side only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/texocr.h"
+#include "kernels.h"
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+    int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct DevBuf {          // grow-only device buffer
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ConvW {           // one weight-standardised convolution + its GroupNorm
+    std::string name, gn;
+    int cin, cout, k, stride, act;
+    float* w = nullptr;          // [cout][k*k*cin] fp32, (ky,kx,c) order, standardised
+    float* gamma = nullptr; float* beta = nullptr;
+};
+
+struct AttnW { void* wqkv = nullptr; void* wq = nullptr; void* wo = nullptr; float* bo = nullptr; };
+struct MlpW { void* w1 = nullptr; float* b1 = nullptr; void* w2 = nullptr; float* b2 = nullptr; };
+
+enum KClass {
+    KC_STEM = 0, KC_GN_STATS, KC_GN_APPLY, KC_CONV, KC_ENC_GEMM, KC_ENC_ATTN, KC_ENC_ROW, KC_CROSSKV_GEMM,
+    KC_DEC_GEMM, KC_DEC_ATTN_SELF, KC_DEC_ATTN_CROSS, KC_DEC_ROW, KC_DEC_ARGMAX, KC_TF_GEMM, KC_TF_ATTN, KC_TF_ROW,
+    KC_MISC, KC_COUNT
+};
+
+struct ProfRec { int cls; cudaEvent_t e0, e1; double bytes, flops; };
+
+struct texocr_handle {
+    texocr_config cfg{};
+    int device = 0;
+    int dt = DT_F32;                 // element type of transformer GEMM operands / KV cache
+    size_t esz = 4;
+    std::string err;
+    std::map<std::string, HostTensor> sd;
+    bool finalized = false;
+    std::vector<void*> weight_allocs;
+
+    // ---- packed weights
+    float* stem_w = nullptr; float* stem_g = nullptr; float* stem_b = nullptr;
+    std::vector<ConvW> convs;                 // the 39 non-stem convolutions in execution order
+    void* proj_w = nullptr; float* proj_b = nullptr; int proj_k = 0;
+    float* cls = nullptr; float* pos = nullptr;
+    float* enc_ln_g = nullptr; float* enc_ln_b = nullptr; float* enc_norm_g = nullptr; float* enc_norm_b = nullptr;
+    std::vector<AttnW> enc_attn; std::vector<MlpW> enc_mlp;
+    float* tok_emb = nullptr; float* pos_emb = nullptr;
+    float* dec_ln_g = nullptr; float* dec_ln_b = nullptr; float* dec_norm_g = nullptr; float* dec_norm_b = nullptr;
+    std::vector<AttnW> dec_self, dec_cross; std::vector<MlpW> dec_mlp;
+    void* w_crosskv = nullptr;                // [L*1024][256]: per layer K rows then V rows
+    void* w_logits = nullptr; float* b_logits = nullptr;
+
+    // ---- workspaces (grow-only)
+    DevBuf geom;                               // int32: img_off[B+1] | img_hw[2B] | tok_off[B+1] | row_off[B+1]
+    int* h_geom = nullptr; size_t h_geom_cap = 0;   // pinned staging for geom
+    cudaEvent_t geom_ev = nullptr;
+    DevBuf img_stage;                          // device copy of host images
+    DevBuf raw1, act2, actA, actB, rawMid, actMid, rawMid2, actMid2, raw3, rawDs;
+    DevBuf gn_partial, gn_stats[4];
+    DevBuf proj_out, patch_cols, backbone_a;
+    DevBuf x, s, xn, qkv, o, hid, logits;
+    DevBuf enc_out, enc_a, crosskv, kvcache;
+    DevBuf ids_stage, mask_stage, enc_stage, tgt_stage, row_loss, scalars;
+    DevBuf dec_state;                          // int64 cur_tok[B] | int32 step, done_step, block_counter, pad | int32 seen[B]
+    DevBuf out_ids;                            // int64 [B, max_len]
+    int* h_poll = nullptr;                     // pinned: done_step polls
+    int last_backbone_pixels = 0;
+
+    // ---- decode-step CUDA graph
+    bool use_graph = true;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; } gkey;
+
+    // ---- instrumentation
+    int64_t launches = 0;
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[KC_COUNT] = {0}; double prof_bytes[KC_COUNT] = {0}; double prof_flops[KC_COUNT] = {0};
+    int64_t prof_n[KC_COUNT] = {0};
+    bool use_tcgen05 = true;
+};

@@ -1,0 +1,113 @@
+// Launch wrappers of the TeXOCR kernels (host side).  Every wrapper enqueues on `st` and
+// returns the cudaError_t of the launch.  DT_* select the element type of a buffer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum { DT_F32 = 0, DT_BF16 = 1 };
+
+enum GemmEpi {
+    EPI_STORE = 0,      // C = A.W^T (+bias)                       out type = dt_c
+    EPI_GLU_RES = 1,    // pairs (2j,2j+1): (a+ba)*sigmoid(g+bg) + res    -> float [M, N/2]
+    EPI_GEGLU = 2,      // pairs (2j,2j+1): (a+ba)*gelu_erf(g+bg)         -> dt_a  [M, N/2]
+    EPI_BIAS_RES = 3    // acc + bias + res                                -> float [M, N]
+};
+
+struct ConvGather {      // implicit-GEMM view of a convolution over a ragged NHWC pixel batch
+    const int* img_off;  // [B+1] full-resolution pixel offsets
+    const int* img_hw;   // [B][2]
+    int nimg;
+    int lin, lout;       // input / output level (pixels are H>>L x W>>L)
+    int ksz, stride, pad, cin;
+};
+
+struct GemmArgs {
+    const void* A; const void* W; void* C;
+    int M, N, K;
+    int lda, ldw, ldc;
+    const float* bias;
+    const float* res; int ldres;
+    int dt_a;            // type of A and W
+    int dt_c;            // type of C for EPI_STORE
+    int epi;
+    const ConvGather* conv;   // non-null: A(m,k) gathered from NHWC input (fp32 only)
+};
+cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
+
+// ---- backbone pieces (conv_gn.cu)
+cudaError_t launch_stem_conv(const float* img, const float* w /*[49][64] std*/, float* raw1, const int* img_off,
+                             const int* img_hw, int nimg, int total_p1, cudaStream_t st);
+cudaError_t launch_gn_stats(const float* raw, int C, int level, const int* img_off, int nimg, int nchunk,
+                            double* partial, float* stats, cudaStream_t st);
+struct GnApplyArgs {
+    const float* raw; const float* stats; const float* gamma; const float* beta;       // main input
+    const float* raw2; const float* stats2; const float* gamma2; const float* beta2;   // optional normalised residual
+    const float* res;                                                                    // optional plain residual
+    float* out;
+    int C, level, relu;
+};
+cudaError_t launch_gn_apply(const GnApplyArgs& a, const int* img_off, int nimg, int nchunk, cudaStream_t st);
+cudaError_t launch_gn_apply_maxpool(const float* raw1, const float* stats, const float* gamma, const float* beta,
+                                    float* out2, const int* img_off, const int* img_hw, int nimg, int total_p2,
+                                    cudaStream_t st);
+cudaError_t launch_im2col_patch(const float* img, float* cols, const int* img_off, const int* img_hw, int nimg,
+                                int total_p4, cudaStream_t st);
+cudaError_t launch_assemble_tokens(const float* proj /*[P4,256]*/, const float* cls, const float* pos, float* x0,
+                                   const int* img_off, const int* img_hw, const int* tok_off, int nimg, int total_tok,
+                                   cudaStream_t st);
+
+// ---- row-wise kernels (rowwise.cu)
+struct Ln2Args {
+    const float* in; int rows;
+    const float* g1; const float* b1;      // nullable: first LN skipped (x1 = in)
+    const float* g2; const float* b2;      // nullable: second LN skipped
+    float* o1f; void* o1a;                 // x1 as fp32 and/or as activation type (nullable)
+    void* o2a;                             // x2 as activation type (nullable)
+    int dt_a;
+};
+cudaError_t launch_ln2(const Ln2Args& a, cudaStream_t st);
+// x[b] = tok_emb[id[b]] + pos_emb[pos]; xn = LN(x).  Decode step: ids = cur_tok [B], pos = *step.
+// Teacher-forced: ids = [B*T] row-major, pos = row % T (step == nullptr).
+cudaError_t launch_embed_ln(const int64_t* ids, const int* step, int T, int rows, const float* tok_emb,
+                            const float* pos_emb, int vocab, const float* g, const float* b, float* x, void* xn,
+                            int dt_a, cudaStream_t st);
+struct ArgmaxArgs {
+    const float* logits; int B, V;
+    int64_t* out_ids; int out_ld;        // out_ids[b*out_ld + step]
+    int64_t* cur_tok;                    // [B] next input token
+    int* step;                           // device step counter (incremented by the last block)
+    int* seen_eos;                       // [B]
+    int* done_step;                      // first step count at which all rows had an EOS (0 = not yet)
+    int* block_counter;                  // scratch, zero-initialised
+    int eos;
+};
+cudaError_t launch_argmax_step(const ArgmaxArgs& a, cudaStream_t st);
+cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_t rows, int V, float* row_loss,
+                                 float* loss, cudaStream_t st);
+cudaError_t launch_cast_f32_to(const float* in, void* out, int64_t n, int dt, cudaStream_t st);
+
+// ---- attention (attention.cu)
+struct AttnVarlenArgs {
+    const void* q; int ldq;            // row-major, head h at columns [h*64, h*64+64)
+    const void* k; int ldk;
+    const void* v; int ldv;
+    void* o; int ldo;
+    const int* q_off; const int* q_len;   // per batch row ranges (q_len may be null -> q_off[b+1]-q_off[b])
+    const int* k_off; const int* k_len;
+    const uint8_t* q_mask; const uint8_t* k_mask;   // per ROW (packed like q / k), nullable
+    int batch, max_q, causal, dt;
+};
+cudaError_t launch_attn_varlen(const AttnVarlenArgs& a, cudaStream_t st);
+struct AttnDecodeArgs {
+    const void* q; int ldq;            // [B, ldq], head h at q + h*64
+    const void* knew; const void* vnew; int ldnew;   // self: this step's k/v rows (appended at *step); null for cross
+    void* kcache; void* vcache;        // self: [B, t_max, 512]; cross: packed rows [sum S, ldkv]
+    int ldkv;                          // row stride in elements
+    int64_t batch_stride;              // self: t_max*ldkv; cross: unused
+    const int* k_off; const int* k_len;   // cross: per-row range; null for self
+    const int* step;                   // self: number of cached keys before this step = *step
+    void* o; int ldo;
+    int batch, dt;
+};
+// nk_cap >= the largest key count any row can have (sizes the per-head score buffer in shared memory)
+cudaError_t launch_attn_decode(const AttnDecodeArgs& a, int nk_cap, cudaStream_t st);

@@ -1,0 +1,194 @@
+// Row-wise HBM-bound kernels: the shared double LayerNorm of model/attention.py:242-259, the decoder
+// embedding (model/decoder.py:51-53), greedy argmax + EOS bookkeeping (model/decoder.py:103-116 in the
+// temp -> 0 limit) and the teacher-forcing cross-entropy (model/decoder.py:140).
+// One warp per 256-wide row, 8 elements per lane (two float4), fp32 statistics via warp shuffles.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int D = 256;
+constexpr float LN_EPS = 1e-5f;
+
+TX_DEVINL void layer_norm8(float* v, const float* __restrict__ g, const float* __restrict__ b, int col) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + LN_EPS);
+    float gg[8], bb[8];
+    ld8(g + col, gg);
+    ld8(b + col, bb);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+}
+
+template <typename T> TX_DEVINL void store8(T* p, const float* v) {
+    st4(p, make_float4(v[0], v[1], v[2], v[3]));
+    st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+template <typename TAct>
+__global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
+    if (row >= a.rows) return;
+    float v[8];
+    ld8(a.in + (size_t)row * D + col, v);
+    if (a.g1) layer_norm8(v, a.g1, a.b1, col);
+    if (a.o1f) store8(a.o1f + (size_t)row * D + col, v);
+    if (a.o1a) store8(reinterpret_cast<TAct*>(a.o1a) + (size_t)row * D + col, v);
+    if (a.g2) {
+        layer_norm8(v, a.g2, a.b2, col);
+        if (a.o2a) store8(reinterpret_cast<TAct*>(a.o2a) + (size_t)row * D + col, v);
+    }
+}
+
+template <typename TAct>
+__global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict__ ids, const int* __restrict__ step, int T, int rows,
+                                                       const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, int vocab,
+                                                       const float* __restrict__ g, const float* __restrict__ b,
+                                                       float* __restrict__ x, TAct* __restrict__ xn) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
+    if (row >= rows) return;
+    long id = (long)ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const int pos = step ? *step : (row % T);
+    float v[8], pe[8];
+    ld8(tok_emb + (size_t)id * D + col, v);
+    ld8(pos_emb + (size_t)pos * D + col, pe);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += pe[i];
+    store8(x + (size_t)row * D + col, v);
+    layer_norm8(v, g, b, col);
+    store8(xn + (size_t)row * D + col, v);
+}
+
+__global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
+    __shared__ int s_last;
+    const int t = *a.step;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row < a.B) {
+        const float* l = a.logits + (size_t)row * a.V;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < a.V; i += 32) {
+            const float v = l[i];
+            if (v > best) { best = v; bi = i; }       // ascending scan: first maximum wins (torch argmax)
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            if (bi == 0x7fffffff) bi = 0;
+            a.out_ids[(size_t)row * a.out_ld + t] = bi;
+            a.cur_tok[row] = bi;
+            if (a.eos >= 0 && bi == a.eos) a.seen_eos[row] = 1;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.block_counter, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        int all = 1;
+        for (int b = threadIdx.x; b < a.B; b += blockDim.x) all &= (*(volatile int*)(a.seen_eos + b) != 0);
+        all = __syncthreads_and(all);
+        if (threadIdx.x == 0) {
+            if (all && *a.done_step == 0) *a.done_step = t + 1;
+            *a.step = t + 1;
+            *a.block_counter = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ tgt, long rows,
+                                                      int V, float* __restrict__ row_loss) {
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* l = logits + (size_t)row * V;
+    float mx = -INFINITY;
+    for (int i = lane; i < V; i += 32) mx = fmaxf(mx, l[i]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int i = lane; i < V; i += 32) s += expf(l[i] - mx);
+    s = warp_sum(s);
+    if (lane == 0) {
+        long t = (long)tgt[row];
+        t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+        row_loss[row] = logf(s) + mx - l[t];
+    }
+}
+
+__global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v, long n, float* __restrict__ out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (long i = threadIdx.x; i < n; i += 1024) s += (double)v[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = (float)(sh[0] / (double)n);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, T* __restrict__ out, long n4) {
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n4) st4(out + i * 4, ld4(in + i * 4));
+}
+
+}  // namespace
+
+cudaError_t launch_ln2(const Ln2Args& a, cudaStream_t st) {
+    if (a.rows <= 0) return cudaSuccess;
+    const int blocks = (a.rows + 7) / 8;
+    if (a.dt_a == DT_F32) ln2_kernel<float><<<blocks, 256, 0, st>>>(a);
+    else ln2_kernel<bf16><<<blocks, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_embed_ln(const int64_t* ids, const int* step, int T, int rows, const float* tok_emb,
+                            const float* pos_emb, int vocab, const float* g, const float* b, float* x, void* xn,
+                            int dt_a, cudaStream_t st) {
+    if (rows <= 0) return cudaSuccess;
+    const int blocks = (rows + 7) / 8;
+    if (dt_a == DT_F32)
+        embed_ln_kernel<float><<<blocks, 256, 0, st>>>(ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (float*)xn);
+    else
+        embed_ln_kernel<bf16><<<blocks, 256, 0, st>>>(ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (bf16*)xn);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_argmax_step(const ArgmaxArgs& a, cudaStream_t st) {
+    argmax_step_kernel<<<(a.B + 7) / 8, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_t rows, int V, float* row_loss,
+                                 float* loss, cudaStream_t st) {
+    if (rows <= 0) return cudaErrorInvalidValue;
+    ce_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(logits, tgt, (long)rows, V, row_loss);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    mean_kernel<<<1, 1024, 0, st>>>(row_loss, (long)rows, loss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cast_f32_to(const float* in, void* out, int64_t n, int dt, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (n % 4 != 0) return cudaErrorInvalidValue;
+    const long n4 = n / 4;
+    const unsigned blocks = (unsigned)((n4 + 255) / 256);
+    if (dt == DT_F32) cast_kernel<float><<<blocks, 256, 0, st>>>(in, (float*)out, n4);
+    else cast_kernel<bf16><<<blocks, 256, 0, st>>>(in, (bf16*)out, n4);
+    return cudaGetLastError();
+}
