@@ -55,6 +55,9 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     }
 }
 
+// chunks an image of `npix` pixels is split into: depends on the image alone (batch-composition independent)
+TX_DEVINL int image_chunks(int npix, int nchunk) { return max(1, min(nchunk, (npix + 63) / 64)); }
+
 // ------------------------------------------------------------------ GroupNorm statistics
 // partial[b][chunk][32][2] (double) then stats[b][32] = (mean, rstd).  Fixed summation order.
 template <int C>
@@ -68,7 +71,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int p0 = img_off[b] >> (2 * level), p1 = img_off[b + 1] >> (2 * level);
     const int npix = p1 - p0;
-    const int per = (npix + nchunk - 1) / nchunk;
+    const int used = image_chunks(npix, nchunk);
+    if (chunk >= used) return;
+    const int per = (npix + used - 1) / used;
     const int lo = p0 + chunk * per, hi = min(p1, lo + per);
     const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -102,7 +107,8 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partial, const int
                                    int nchunk, int cpg, float* __restrict__ stats) {
     const int b = blockIdx.x, g = threadIdx.x;
     double a = 0.0, q = 0.0;
-    for (int c = 0; c < nchunk; ++c) {
+    const int used = image_chunks((img_off[b + 1] >> (2 * level)) - (img_off[b] >> (2 * level)), nchunk);
+    for (int c = 0; c < used; ++c) {
         const double* in = partial + (((size_t)b * nchunk + c) * 32 + g) * 2;
         a += in[0]; q += in[1];
     }
@@ -119,7 +125,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, const int*
     const int C = a.C, C4 = C / 4, cpg = C / 32;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int p0 = img_off[b] >> (2 * a.level), p1 = img_off[b + 1] >> (2 * a.level);
-    const int per = (p1 - p0 + nchunk - 1) / nchunk;
+    const int used = image_chunks(p1 - p0, nchunk);
+    if (chunk >= used) return;
+    const int per = (p1 - p0 + used - 1) / used;
     const int lo = p0 + chunk * per, hi = min(p1, lo + per);
     const int rpp = 256 / min(C4, 256);
     const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;     // C4 <= 256

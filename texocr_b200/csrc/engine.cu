@@ -385,11 +385,10 @@ static int plan_geometry(texocr_handle* h, const int32_t* hw, int B, EncGeom& g,
     return 0;
 }
 
-static int nchunk_for(long pixels, int B) {
-    long avg = pixels / std::max(B, 1);
-    long n = (avg + 63) / 64;
-    return (int)std::min<long>(32, std::max<long>(1, n));
-}
+// GroupNorm work is split into per-image pixel chunks.  The grid always offers GN_MAX_CHUNKS chunks per image and each
+// image uses min(GN_MAX_CHUNKS, ceil(pixels/64)) of them, a function of its OWN size only: the summation order of
+// an image's statistics -- hence every bit of its result -- does not depend on what else is in the batch.
+static int nchunk_for(long, int) { return 32; }
 
 static int run_backbone(texocr_handle* h, const float* d_img, const EncGeom& g, cudaStream_t st, const float** feat_out) {
     const int B = g.B;
@@ -762,7 +761,10 @@ int texocr_create(const texocr_config* cfg, int device, texocr_handle** out) {
     h->dt = cfg->precision == TEXOCR_BF16 ? DT_BF16 : DT_F32;
     h->esz = h->dt == DT_BF16 ? 2 : 4;
     cudaError_t e = cudaEventCreateWithFlags(&h->geom_ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) { delete h; return fail(nullptr, TEXOCR_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->hop_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->hop_out, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(nullptr, TEXOCR_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
     *out = h;
     return 0;
 }
@@ -783,6 +785,9 @@ void texocr_destroy(texocr_handle* h) {
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);
     if (h->geom_ev) cudaEventDestroy(h->geom_ev);
+    if (h->hop_in) cudaEventDestroy(h->hop_in);
+    if (h->hop_out) cudaEventDestroy(h->hop_out);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (auto& p : h->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     delete h;
@@ -810,11 +815,33 @@ int texocr_finalize_weights(texocr_handle* h) {
     return finalize_weights(h);
 }
 
+// The legacy / per-thread default streams cannot be captured into a CUDA graph, so work submitted on them hops to
+// the handle's own non-blocking stream: it waits for everything already queued on the caller's stream, and the
+// caller's stream waits for it on exit -- stream-ordering as seen by the caller is unchanged.
+struct StreamHop {
+    texocr_handle* h; cudaStream_t user, work; bool hop;
+    StreamHop(texocr_handle* h_, void* stream) : h(h_), user((cudaStream_t)stream), work((cudaStream_t)stream), hop(false) {
+        if (user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread) {
+            hop = true;
+            work = h->own_stream;
+            cudaEventRecord(h->hop_in, user);
+            cudaStreamWaitEvent(work, h->hop_in, 0);
+        }
+    }
+    ~StreamHop() {
+        if (hop) {
+            cudaEventRecord(h->hop_out, work);
+            cudaStreamWaitEvent(user, h->hop_out, 0);
+        }
+    }
+};
+
 #define ENTRY_CHECKS()                                                                                     \
     if (!h) return TEXOCR_ERR_ARG;                                                                         \
     if (!h->finalized) return fail(h, TEXOCR_ERR_STATE, "weights not finalised (texocr_finalize_weights)"); \
     CK(cudaSetDevice(h->device));                                                                          \
-    cudaStream_t st = (cudaStream_t)stream
+    StreamHop hop__(h, stream);                                                                            \
+    cudaStream_t st = hop__.work
 
 static long total_pixels(const int32_t* hw, int B) {
     long n = 0;

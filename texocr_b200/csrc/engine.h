@@ -66,7 +66,8 @@ struct texocr_handle {
     // ---- workspaces (grow-only)
     DevBuf geom;                               // int32: img_off[B+1] | img_hw[2B] | tok_off[B+1] | row_off[B+1]
     int* h_geom = nullptr; size_t h_geom_cap = 0;   // pinned staging for geom
-    cudaEvent_t geom_ev = nullptr;
+    cudaEvent_t geom_ev = nullptr, hop_in = nullptr, hop_out = nullptr;
+    cudaStream_t own_stream = nullptr;
     DevBuf img_stage;                          // device copy of host images
     DevBuf raw1, act2, actA, actB, rawMid, actMid, rawMid2, actMid2, raw3, rawDs;
     DevBuf gn_partial, gn_stats[4];
