@@ -133,6 +133,13 @@ TEXOCR_API int texocr_set_option(texocr_handle* h, const char* name, int64_t val
  * name = "backbone" -> float32 [sum h_i*w_i, 1024] (NHWC pixels).  Returns element count or <0. */
 TEXOCR_API int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_t cap_elems);
 
+/* Test hook: run one GEMM  C[M,N] = epi(A[M,K] . W[N,K]^T)  on device buffers through the engine's own kernels.
+ * dt_a: 0 = fp32 operands (FFMA kernel), 1 = bf16 operands; use_tc != 0 selects the tcgen05 kernel (bf16 only);
+ * A2/W2 non-NULL select the bf16x3 split mode (low-order parts).  epi / dt_c as in csrc/kernels.h (GemmEpi, DT_*). */
+TEXOCR_API int texocr_debug_gemm(texocr_handle* h, const void* A, const void* W, void* C, int32_t M, int32_t N, int32_t K,
+                      int32_t lda, int32_t ldw, int32_t ldc, int32_t epi, int32_t dt_a, int32_t dt_c, const float* bias,
+                      const float* res, int32_t ldres, int32_t use_tc, const void* A2, const void* W2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ EXPORTS = (
     "texocr_create", "texocr_destroy", "texocr_last_error", "texocr_set_weight", "texocr_finalize_weights",
     "texocr_encode", "texocr_decoder_logits", "texocr_decoder_generate", "texocr_generate", "texocr_cross_entropy",
     "texocr_kernel_launches", "texocr_profile_enable", "texocr_profile_read", "texocr_set_option", "texocr_debug_read",
+    "texocr_debug_gemm",
 )
 
 
@@ -70,6 +71,7 @@ def load_library() -> C.CDLL:
     lib.texocr_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.texocr_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
     lib.texocr_debug_read.restype = i64
+    lib.texocr_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib
@@ -222,6 +224,18 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.texocr_set_option(self.h, name.encode(), int(value)))
+
+    def debug_gemm(self, A, W, C, epi=0, bias=None, res=None, use_tc=True, A2=None, W2=None):
+        """Test hook: C = epi(A @ W.T) through the engine's GEMM kernels (tensors on the device, row-major)."""
+        M, K = A.shape
+        N = W.shape[0]
+        dt_a = 1 if A.dtype == torch.bfloat16 else 0
+        dt_c = 1 if C.dtype == torch.bfloat16 else 0
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self._check(self.lib.texocr_debug_gemm(self.h, A.data_ptr(), W.data_ptr(), C.data_ptr(), M, N, K, A.stride(0), W.stride(0),
+                                               C.stride(0), epi, dt_a, dt_c, ptr(bias), ptr(res), 0 if res is None else res.stride(0),
+                                               1 if use_tc else 0, ptr(A2), ptr(W2), self._stream()))
+        return C
 
     def debug_read(self, name: str, numel: int) -> torch.Tensor:
         out = torch.empty(numel, dtype=torch.float32, device=self.device)

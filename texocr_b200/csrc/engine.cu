@@ -1049,4 +1049,22 @@ int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_
     return fail(h, TEXOCR_ERR_ARG, "unknown debug tap '%s'", name);
 }
 
+int texocr_debug_gemm(texocr_handle* h, const void* A, const void* W, void* C, int32_t M, int32_t N, int32_t K, int32_t lda,
+                      int32_t ldw, int32_t ldc, int32_t epi, int32_t dt_a, int32_t dt_c, const float* bias, const float* res,
+                      int32_t ldres, int32_t use_tc, const void* A2, const void* W2, void* stream) {
+    if (!h) return TEXOCR_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    StreamHop hop__(h, stream);
+    cudaStream_t st = hop__.work;
+    GemmArgs g = mk_gemm(A, lda, W, ldw, C, ldc, M, N, K, epi, dt_a, dt_c, bias, res, ldres);
+    g.A2 = A2; g.W2 = W2;
+    if (use_tc) {
+        if (!tc_gemm_supported(g)) return fail(h, TEXOCR_ERR_ARG, "shape not supported by the tcgen05 GEMM");
+        LAUNCH(KC_MISC, 1, gemm_bytes(g, 2), gemm_flops(g), launch_gemm_tc(g, st));
+    } else {
+        LAUNCH(KC_MISC, 1, gemm_bytes(g, dt_a == DT_BF16 ? 2 : 4), gemm_flops(g), launch_gemm_simt(g, st));
+    }
+    return 0;
+}
+
 }  // extern "C"

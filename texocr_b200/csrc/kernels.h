@@ -31,6 +31,7 @@ struct GemmArgs {
     int dt_c;            // type of C for EPI_STORE
     int epi;
     const ConvGather* conv;   // non-null: A(m,k) gathered from NHWC input (fp32 only)
+    const void* A2; const void* W2;   // tcgen05 bf16x3 mode: low-order bf16 parts of A and W (same shapes / strides)
 };
 cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 

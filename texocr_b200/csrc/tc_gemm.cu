@@ -1,5 +1,356 @@
-// Placeholder until the tcgen05 kernel lands: reports "unsupported" so the engine uses the FFMA path.
+// tcgen05 GEMM for sm_100a:  C[M,N] = epi(A[M,K] . W[N,K]^T), bf16 operands (both K-major), fp32 accumulation in TMEM.
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring (STAGES x {A 128x64, W BNx64})
+//   -> tcgen05.mma.cta_group::1.kind::f16 issued by one thread, accumulator 128 lanes x BN columns in TMEM
+//   -> tcgen05.ld (32x32b) by four epilogue warps, one accumulator row per thread, fused epilogue
+//      (bias / GLU+residual / GeGLU / bias+residual), vectorised row-segment stores.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (warp w may only touch TMEM lanes 32*(w%4)..+31, so four consecutive warps cover the 128 rows).
+//
+// SPLIT = 3 is the "bf16x3" mode used for the ill-conditioned ResNet backbone: both operands are
+// given as hi + lo bf16 pairs and every k-slice issues hi.hi + hi.lo + lo.hi into the same accumulator, which
+// carries ~16 mantissa bits per operand through the tensor cores.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
 #include "tc_gemm.h"
 
-bool tc_gemm_supported(const GemmArgs&) { return false; }
-cudaError_t launch_gemm_tc(const GemmArgs&, cudaStream_t) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+
+struct TcParams {
+    void* C; int M, N, K, ldc;
+    const float* bias; const float* res; int ldres;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+TX_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+TX_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+TX_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+TX_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+TX_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+TX_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+TX_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+TX_DEVINL void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+TX_DEVINL void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), LBO unused (=1).
+// Bit layout: cute::UMMA::SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+TX_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;       // SWIZZLE_128B
+    return d;
+}
+// cute::UMMA::InstrDescriptor: c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+
+template <int BN, int SPLIT> struct Smem {
+    static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+    static constexpr int NOPS = SPLIT == 3 ? 2 : 1;                 // hi (+ lo) copies per operand
+    static constexpr int STAGE = NOPS * (A_BYTES + W_BYTES);
+    static constexpr int STAGES = (STAGE * 4 <= 160 * 1024) ? 4 : (STAGE * 3 <= 200 * 1024 ? 3 : 2);
+    static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI, typename TC, int SPLIT>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
+    using S = Smem<BN, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
+    uint64_t* empty = full + S::STAGES;
+    uint64_t* tmem_full = empty + S::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nkb = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % S::STAGES, ph = (kb / S::STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * S::STAGE;
+                mbar_expect_tx(&full[s], S::STAGE);
+                tma_load_2d(&tmA, &full[s], st, kb * BK, m0);
+                tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, kb * BK, n0);
+                if (SPLIT == 3) {
+                    tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, kb * BK, m0);
+                    tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % S::STAGES, ph = (kb / S::STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tcgen05_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::STAGE);
+                const uint32_t w_hi = a_hi + S::NOPS * S::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t koff = k * UMMA_K * 2;
+                    umma_bf16(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, (kb | k) != 0);
+                    if (SPLIT == 3) {
+                        umma_bf16(tmem_base, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + S::W_BYTES + koff), idesc, 1);
+                        umma_bf16(tmem_base, make_smem_desc(a_hi + S::A_BYTES + koff), make_smem_desc(w_hi + koff), idesc, 1);
+                    }
+                }
+                umma_commit(&empty[s]);        // frees the smem slot once these MMAs have read it
+            }
+            umma_commit(tmem_full);            // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: thread = accumulator row (TMEM lane), 32 columns per tcgen05.ld
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < p.M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+            const int n = n0 + c0;
+            if (!row_ok || n >= p.N) continue;
+            const int nvalid = min(32, p.N - n);            // multiple of 8
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+            if (p.bias) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nvalid) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
+                }
+            }
+            if (EPI == EPI_STORE) {
+                TC* out = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc + n;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (i < nvalid) {
+                        st4(out + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                        st4(out + i + 4, make_float4(v[i + 4], v[i + 5], v[i + 6], v[i + 7]));
+                    }
+                }
+            } else if (EPI == EPI_BIAS_RES) {
+                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + n;
+                const float* rs = p.res + (size_t)m * p.ldres + n;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nvalid) {
+                        const float4 r = ld4(rs + i);
+                        st4(out + i, make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w));
+                    }
+                }
+            } else if (EPI == EPI_GLU_RES) {
+                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + (n >> 1);
+                const float* rs = p.res + (size_t)m * p.ldres + (n >> 1);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (i < nvalid) {
+                        const float4 r = ld4(rs + (i >> 1));
+                        st4(out + (i >> 1), make_float4(v[i] * sigmoidf_(v[i + 1]) + r.x, v[i + 2] * sigmoidf_(v[i + 3]) + r.y,
+                                                        v[i + 4] * sigmoidf_(v[i + 5]) + r.z, v[i + 6] * sigmoidf_(v[i + 7]) + r.w));
+                    }
+                }
+            } else {    // EPI_GEGLU -> bf16
+                bf16* out = reinterpret_cast<bf16*>(p.C) + (size_t)m * p.ldc + (n >> 1);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (i < nvalid)
+                        st4(out + (i >> 1), make_float4(v[i] * gelu_erf(v[i + 1]), v[i + 2] * gelu_erf(v[i + 3]),
+                                                        v[i + 4] * gelu_erf(v[i + 5]), v[i + 6] * gelu_erf(v[i + 7])));
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::mutex g_mu;
+std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
+
+cudaError_t get_encode() {
+    if (g_encode) return cudaSuccess;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    g_encode = (EncodeTiledFn)fn;
+    return cudaSuccess;
+}
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = box_rows x 64 columns, 128B swizzle, zero OOB fill.
+cudaError_t get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return cudaSuccess; }
+    cudaError_t e = get_encode();
+    if (e != cudaSuccess) return e;
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = m;
+    *out = m;
+    return cudaSuccess;
+}
+
+template <int BN, int EPI, typename TC, int SPLIT>
+cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                       cudaStream_t st) {
+    using S = Smem<BN, SPLIT>;
+    static bool attr_set = false;
+    auto kern = tc_gemm_kernel<BN, EPI, TC, SPLIT>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+    kern<<<grid, 192, S::TOTAL, st>>>(a, w, a2, w2, p);
+    return cudaGetLastError();
+}
+
+template <int BN, int SPLIT>
+cudaError_t launch_epi(const GemmArgs& g, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2,
+                       const TcParams& p, cudaStream_t st) {
+    switch (g.epi) {
+        case EPI_STORE:
+            if (g.dt_c == DT_F32) return launch_cfg<BN, EPI_STORE, float, SPLIT>(a, w, a2, w2, p, st);
+            return launch_cfg<BN, EPI_STORE, bf16, SPLIT>(a, w, a2, w2, p, st);
+        case EPI_GLU_RES: return launch_cfg<BN, EPI_GLU_RES, float, SPLIT>(a, w, a2, w2, p, st);
+        case EPI_GEGLU: return launch_cfg<BN, EPI_GEGLU, bf16, SPLIT>(a, w, a2, w2, p, st);
+        case EPI_BIAS_RES: return launch_cfg<BN, EPI_BIAS_RES, float, SPLIT>(a, w, a2, w2, p, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool tc_gemm_supported(const GemmArgs& g) {
+    if (g.dt_a != DT_BF16 || g.conv) return false;
+    if (g.K % BK != 0 || g.N % 8 != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0) return false;
+    if (((uintptr_t)g.A | (uintptr_t)g.W) & 15) return false;
+    if (g.epi == EPI_STORE) { if (g.ldc % 8 != 0) return false; }
+    else if (g.ldc % 4 != 0) return false;
+    if ((g.epi == EPI_GLU_RES || g.epi == EPI_BIAS_RES) && (!g.res || g.ldres % 4 != 0)) return false;
+    return true;
+}
+
+cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+    if (g.M <= 0) return cudaSuccess;
+    // tile width: keep >= ~1 wave of CTAs when M is small (decode steps), 128 otherwise
+    const long mt = (g.M + BM - 1) / BM;
+    int bn = 128;
+    if (mt * ((g.N + 127) / 128) < 120) bn = 64;
+    if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
+    const bool split = g.A2 != nullptr;
+    if (split) bn = 128;
+    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres};
+    CUtensorMap a, w, a2, w2;
+    cudaError_t e;
+    if ((e = get_map(g.A, g.M, g.K, g.lda, BM, &a)) != cudaSuccess) return e;
+    if ((e = get_map(g.W, g.N, g.K, g.ldw, bn, &w)) != cudaSuccess) return e;
+    a2 = a; w2 = w;
+    if (split) {
+        if ((e = get_map(g.A2, g.M, g.K, g.lda, BM, &a2)) != cudaSuccess) return e;
+        if ((e = get_map(g.W2, g.N, g.K, g.ldw, bn, &w2)) != cudaSuccess) return e;
+        return launch_epi<128, 3>(g, a, w, a2, w2, p, st);
+    }
+    if (bn == 128) return launch_epi<128, 1>(g, a, w, a2, w2, p, st);
+    if (bn == 64) return launch_epi<64, 1>(g, a, w, a2, w2, p, st);
+    return launch_epi<32, 1>(g, a, w, a2, w2, p, st);
+}
