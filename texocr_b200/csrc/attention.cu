@@ -142,6 +142,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) attn_decode_kernel(AttnDecodeArgs a, int nk_cap) {
     extern __shared__ float s_scores[];
     __shared__ __align__(16) float s_q[NH][HD];
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* ps = s_scores + (size_t)h * nk_cap;
     const T* __restrict__ Q = reinterpret_cast<const T*>(a.q) + (size_t)b * a.ldq + h * HD;
@@ -243,7 +245,6 @@ cudaError_t launch_attn_decode(const AttnDecodeArgs& a, int nk_cap, cudaStream_t
         if (e != cudaSuccess) return e;
         g_decode_smem_set[ti] = (int)smem;
     }
-    if (a.dt == DT_F32) attn_decode_kernel<float><<<a.batch, 256, smem, st>>>(a, nk_cap);
-    else attn_decode_kernel<bf16><<<a.batch, 256, smem, st>>>(a, nk_cap);
-    return cudaGetLastError();
+    if (a.dt == DT_F32) return launch_pdl(attn_decode_kernel<float>, dim3(a.batch), dim3(256), smem, st, a, nk_cap);
+    return launch_pdl(attn_decode_kernel<bf16>, dim3(a.batch), dim3(256), smem, st, a, nk_cap);
 }

@@ -66,6 +66,13 @@ TX_DEVINL float warp_max(float v) {
 TX_DEVINL float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)); }
 TX_DEVINL float sigmoidf_(float g) { return 1.0f / (1.0f + expf(-g)); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor drains.  pdl_launch_dependents() lets the successor be scheduled early; pdl_wait() blocks until
+// the predecessor grid has completed and its memory is visible.  Both are no-ops for ordinary launches.  Every kernel
+// on the decode path calls them first thing, before touching global memory.
+TX_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+TX_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Ragged image batch geometry.  img_off[b] = pixel offset of image b at full resolution
 // (sum of H*W of the images before it); every level L (stride 2^L) has H>>L x W>>L pixels
 // starting at img_off[b] >> (2L) because H and W are multiples of 16.

@@ -55,6 +55,15 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     }
 }
 
+// v = hi + lo with hi = bf16(v), lo = bf16(v - hi): ~16 mantissa bits through two bf16 tensor-core operands
+TX_DEVINL void store_split4(bf16* hi, bf16* lo, const float* r) {
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = __bfloat162float(__float2bfloat16_rn(r[i])); l[i] = r[i] - h[i]; }
+    st4(hi, make_float4(h[0], h[1], h[2], h[3]));
+    st4(lo, make_float4(l[0], l[1], l[2], l[3]));
+}
+
 // chunks an image of `npix` pixels is split into: depends on the image alone (batch-composition independent)
 TX_DEVINL int image_chunks(int npix, int nchunk) { return max(1, min(nchunk, (npix + 63) / 64)); }
 
@@ -159,11 +168,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, const int*
             float4 u = ld4(a.res + o);
             r[0] += u.x; r[1] += u.y; r[2] += u.z; r[3] += u.w;
         }
+        if (a.res_hi) {
+            float4 u = ld4(reinterpret_cast<const bf16*>(a.res_hi) + o), w = ld4(reinterpret_cast<const bf16*>(a.res_lo) + o);
+            r[0] += u.x + w.x; r[1] += u.y + w.y; r[2] += u.z + w.z; r[3] += u.w + w.w;
+        }
         if (a.relu) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) r[i] = fmaxf(r[i], 0.f);
         }
-        st4(a.out + o, make_float4(r[0], r[1], r[2], r[3]));
+        if (a.out) st4(a.out + o, make_float4(r[0], r[1], r[2], r[3]));
+        else store_split4(reinterpret_cast<bf16*>(a.out_hi) + o, reinterpret_cast<bf16*>(a.out_lo) + o, r);
     }
 }
 
@@ -171,7 +185,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, const int*
 // model/resnet.py:69-79: SAME pad (0,1) filled with -inf => out-of-range taps are skipped.
 __global__ void __launch_bounds__(256) gn_apply_maxpool_kernel(const float* __restrict__ raw1, const float* __restrict__ stats,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               float* __restrict__ out2, ImgGeom g, int total_p2) {
+                                                               float* __restrict__ out2, bf16* __restrict__ out_hi,
+                                                               bf16* __restrict__ out_lo, ImgGeom g, int total_p2) {
     const int c4 = threadIdx.x & 15, rl = threadIdx.x >> 4;       // 16 float4 columns (C = 64), 16 pixels per block pass
     const int p = blockIdx.x * 16 + rl;
     if (p >= total_p2) return;
@@ -205,7 +220,37 @@ __global__ void __launch_bounds__(256) gn_apply_maxpool_kernel(const float* __re
             m[3] = fmaxf(m[3], fmaxf((v.w - mean[3]) * sc[3] + be[3], 0.f));
         }
     }
-    st4(out2 + (size_t)p * 64 + c, make_float4(m[0], m[1], m[2], m[3]));
+    if (out2) st4(out2 + (size_t)p * 64 + c, make_float4(m[0], m[1], m[2], m[3]));
+    else store_split4(out_hi + (size_t)p * 64 + c, out_lo + (size_t)p * 64 + c, m);
+}
+
+// ------------------------------------------------------------------ explicit im2col for the tcgen05 (bf16x3) conv path
+// thread = 8 channels (16 B) of one tap of one output pixel; both halves of the split pair are copied.
+__global__ void __launch_bounds__(256) im2col_split_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
+                                                           bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, ConvGather cg,
+                                                           long total_items, int c8, int taps) {
+    const long item = (long)blockIdx.x * 256 + threadIdx.x;
+    if (item >= total_items) return;
+    const int cc = (int)(item % c8);
+    const long rest = item / c8;
+    const int tap = (int)(rest % taps);
+    const long m = rest / taps;
+    const int b = find_image(cg.img_off, cg.nimg, cg.lout, (int)m);
+    const int H = cg.img_hw[2 * b], W = cg.img_hw[2 * b + 1];
+    const int wo = W >> cg.lout, hin = H >> cg.lin, win = W >> cg.lin;
+    const int local = (int)m - (cg.img_off[b] >> (2 * cg.lout));
+    const int oy = local / wo, ox = local - oy * wo;
+    const int ky = tap / cg.ksz, kx = tap - ky * cg.ksz;
+    const int iy = oy * cg.stride + ky - cg.pad, ix = ox * cg.stride + kx - cg.pad;
+    uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < hin && ix >= 0 && ix < win) {
+        const size_t src = ((size_t)(cg.img_off[b] >> (2 * cg.lin)) + (size_t)iy * win + ix) * cg.cin + cc * 8;
+        vh = *reinterpret_cast<const uint4*>(in_hi + src);
+        vl = *reinterpret_cast<const uint4*>(in_lo + src);
+    }
+    const size_t dst = ((size_t)m * taps + tap) * cg.cin + cc * 8;
+    *reinterpret_cast<uint4*>(out_hi + dst) = vh;
+    *reinterpret_cast<uint4*>(out_lo + dst) = vl;
 }
 
 // ------------------------------------------------------------------ patch variant: 16x16/s16 im2col (model/encoder.py:22-27)
@@ -287,10 +332,23 @@ cudaError_t launch_gn_apply(const GnApplyArgs& a, const int* img_off, int nimg, 
 }
 
 cudaError_t launch_gn_apply_maxpool(const float* raw1, const float* stats, const float* gamma, const float* beta,
-                                    float* out2, const int* img_off, const int* img_hw, int nimg, int total_p2,
-                                    cudaStream_t st) {
+                                    float* out2, void* out_hi, void* out_lo, const int* img_off, const int* img_hw, int nimg,
+                                    int total_p2, cudaStream_t st) {
     ImgGeom g{img_off, img_hw, nimg};
-    gn_apply_maxpool_kernel<<<(total_p2 + 15) / 16, 256, 0, st>>>(raw1, stats, gamma, beta, out2, g, total_p2);
+    gn_apply_maxpool_kernel<<<(total_p2 + 15) / 16, 256, 0, st>>>(raw1, stats, gamma, beta, out2, (bf16*)out_hi, (bf16*)out_lo, g, total_p2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_im2col_split(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, const ConvGather& cg,
+                                long total_out_pixels, cudaStream_t st) {
+    if (cg.cin % 8 != 0) return cudaErrorInvalidValue;
+    const int c8 = cg.cin / 8, taps = cg.ksz * cg.ksz;
+    const long items = total_out_pixels * taps * c8;
+    if (items <= 0) return cudaSuccess;
+    const long blocks = (items + 255) / 256;
+    if (blocks > 0x7fffffffL) return cudaErrorInvalidValue;
+    im2col_split_kernel<<<(unsigned)blocks, 256, 0, st>>>((const bf16*)in_hi, (const bf16*)in_lo, (bf16*)out_hi, (bf16*)out_lo, cg,
+                                                         items, c8, taps);
     return cudaGetLastError();
 }
 

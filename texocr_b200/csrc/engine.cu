@@ -21,6 +21,7 @@
 #include "tc_gemm.h"
 
 static std::string g_create_error;
+int g_texocr_pdl = 1;
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -135,6 +136,16 @@ static int upload_act(texocr_handle* h, const std::vector<float>& v, void** out)
     std::vector<uint16_t> b(v.size());
     for (size_t i = 0; i < v.size(); ++i) b[i] = f2bf(v[i]);
     return dev_upload<uint16_t>(h, b, out);
+}
+
+// v -> (bf16(v), bf16(v - bf16(v))): the operand pair of the tcgen05 bf16x3 mode
+static float bf2f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+static int upload_split(texocr_handle* h, const std::vector<float>& v, void** hi, void** lo) {
+    std::vector<uint16_t> a(v.size()), b(v.size());
+    for (size_t i = 0; i < v.size(); ++i) { a[i] = f2bf(v[i]); b[i] = f2bf(v[i] - bf2f(a[i])); }
+    int r = dev_upload<uint16_t>(h, a, hi);
+    if (r) return r;
+    return dev_upload<uint16_t>(h, b, lo);
 }
 
 static const HostTensor* find_w(texocr_handle* h, const std::string& key, std::initializer_list<int64_t> shape) {
@@ -252,6 +263,7 @@ static int finalize_weights(texocr_handle* h) {
                     std::vector<float> ws;
                     standardise_reorder(*w, sp.cout, sp.cin, sp.k, ws);
                     if ((r = upload_f32(h, ws, &cw.w))) return r;
+                    if (h->dt == DT_BF16 && (r = upload_split(h, ws, &cw.w_hi, &cw.w_lo))) return r;
                     if ((r = upload_f32(h, g->data, &cw.gamma))) return r;
                     if ((r = upload_f32(h, be->data, &cw.beta))) return r;
                     h->convs.push_back(cw);
@@ -261,7 +273,8 @@ static int finalize_weights(texocr_handle* h) {
         }
         GETW(pw, E + "patch_embed.proj.weight", 256, 1024, 1, 1);
         GETW(pb, E + "patch_embed.proj.bias", 256);
-        if ((r = upload_act(h, pw->data, &h->proj_w))) return r;
+        if (h->dt == DT_BF16) { if ((r = upload_split(h, pw->data, &h->proj_w, &h->proj_w_lo))) return r; }
+        else if ((r = upload_act(h, pw->data, &h->proj_w))) return r;
         if ((r = upload_f32(h, pb->data, &h->proj_b))) return r;
         h->proj_k = 1024;
     } else {
@@ -414,8 +427,8 @@ static int run_backbone(texocr_handle* h, const float* d_img, const EncGeom& g, 
     LAUNCH(KC_GN_STATS, 2, (double)g.P[1] * 64 * 4, 0.0,
            launch_gn_stats(h->raw1.as<float>(), 64, 1, g.d_img_off, B, nc, partial, stats[0], st));
     LAUNCH(KC_GN_APPLY, 1, (double)g.P[1] * 64 * 4 + (double)g.P[2] * 64 * 4, 0.0,
-           launch_gn_apply_maxpool(h->raw1.as<float>(), stats[0], h->stem_g, h->stem_b, h->act2.as<float>(), g.d_img_off,
-                                   g.d_img_hw, B, (int)g.P[2], st));
+           launch_gn_apply_maxpool(h->raw1.as<float>(), stats[0], h->stem_g, h->stem_b, h->act2.as<float>(), nullptr, nullptr,
+                                   g.d_img_off, g.d_img_hw, B, (int)g.P[2], st));
 
     const float* x = h->act2.as<float>();
     int Cx = 64, Lx = 2;
@@ -484,22 +497,135 @@ static int run_backbone(texocr_handle* h, const float* d_img, const EncGeom& g, 
     return 0;
 }
 
+// bf16 tier: the same backbone with every convolution on the tensor cores in bf16x3 mode (tc_gemm.cu, SPLIT=3).
+// Activations live as split-bf16 pairs (hi | lo halves of one buffer); 1x1/s1 convs are plain GEMMs over pixel rows,
+// 3x3 and stride-2 convs go through an explicit im2col of the pair.  Raw conv outputs and all statistics stay fp32.
+static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& g, cudaStream_t st, const void** feat_hi,
+                           const void** feat_lo) {
+    const int B = g.B;
+    ENSURE(h->raw1, (size_t)g.P[1] * 64 * 4);
+    ENSURE(h->act2, (size_t)g.P[2] * 64 * 4);
+    ENSURE(h->actA, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->actB, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->rawMid, (size_t)g.P[2] * 128 * 4);
+    ENSURE(h->actMid, (size_t)g.P[2] * 128 * 4);
+    ENSURE(h->rawMid2, (size_t)g.P[2] * 64 * 4);
+    ENSURE(h->actMid2, (size_t)g.P[2] * 64 * 4);
+    ENSURE(h->raw3, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->rawDs, (size_t)g.P[2] * 256 * 4);
+    ENSURE(h->col, (size_t)g.P[2] * 576 * 4);
+    ENSURE(h->gn_partial, (size_t)B * 32 * 32 * 2 * 8);
+    for (int i = 0; i < 4; ++i) ENSURE(h->gn_stats[i], (size_t)B * 32 * 2 * 4);
+    float* stats[4] = {h->gn_stats[0].as<float>(), h->gn_stats[1].as<float>(), h->gn_stats[2].as<float>(), h->gn_stats[3].as<float>()};
+    double* partial = h->gn_partial.as<double>();
+    struct Pair { char* hi; char* lo; };
+    auto pair_of = [](DevBuf& b, size_t elems) { Pair p; p.hi = (char*)b.p; p.lo = (char*)b.p + elems * 2; return p; };
+
+    LAUNCH(KC_STEM, 1, (double)g.P[0] * 4 + (double)g.P[1] * 64 * 4, 2.0 * 49 * 64 * g.P[1],
+           launch_stem_conv(d_img, h->stem_w, h->raw1.as<float>(), g.d_img_off, g.d_img_hw, B, (int)g.P[1], st));
+    LAUNCH(KC_GN_STATS, 2, (double)g.P[1] * 64 * 4, 0.0,
+           launch_gn_stats(h->raw1.as<float>(), 64, 1, g.d_img_off, B, nchunk_for(g.P[1], B), partial, stats[0], st));
+    Pair x = pair_of(h->act2, (size_t)g.P[2] * 64);
+    LAUNCH(KC_GN_APPLY, 1, (double)g.P[1] * 64 * 4 + (double)g.P[2] * 64 * 4, 0.0,
+           launch_gn_apply_maxpool(h->raw1.as<float>(), stats[0], h->stem_g, h->stem_b, nullptr, x.hi, x.lo, g.d_img_off,
+                                   g.d_img_hw, B, (int)g.P[2], st));
+    int Lx = 2;
+    DevBuf* pingpong[2] = {&h->actA, &h->actB};
+    int pp = 0;
+    size_t ci = 0;
+    const int depths[3] = {2, 4, 6};
+    // conv: split GEMM, through im2col unless 1x1/s1
+    auto conv = [&](const ConvW& cw, Pair in, int lin, int lout, float* out) -> int {
+        const long M = g.P[lout];
+        const int K = cw.k * cw.k * cw.cin;
+        const void *a_hi = in.hi, *a_lo = in.lo;
+        if (!(cw.k == 1 && cw.stride == 1)) {
+            ConvGather cg{g.d_img_off, g.d_img_hw, B, lin, lout, cw.k, cw.stride, (cw.k == 3 && cw.stride == 1) ? 1 : 0, cw.cin};
+            Pair c = pair_of(h->col, (size_t)M * K);
+            LAUNCH(KC_GN_APPLY, 1, (double)M * K * 8, 0.0, launch_im2col_split(in.hi, in.lo, c.hi, c.lo, cg, M, st));
+            a_hi = c.hi; a_lo = c.lo;
+        }
+        GemmArgs ga = mk_gemm(a_hi, K, cw.w_hi, K, out, cw.cout, (int)M, cw.cout, K, EPI_STORE, DT_BF16, DT_F32, nullptr, nullptr, 0);
+        ga.A2 = a_lo; ga.W2 = cw.w_lo;
+        if (!tc_gemm_supported(ga)) return fail(h, TEXOCR_ERR_ARG, "backbone conv %s not supported by the tcgen05 GEMM", cw.name.c_str());
+        LAUNCH(KC_CONV, 1, gemm_bytes(ga, 4), gemm_flops(ga), launch_gemm_tc(ga, st));
+        return 0;
+    };
+    auto gstats = [&](const float* raw, int C, int level, float* stt) -> int {
+        LAUNCH(KC_GN_STATS, 2, (double)g.P[level] * C * 4, 0.0,
+               launch_gn_stats(raw, C, level, g.d_img_off, B, nchunk_for(g.P[level], B), partial, stt, st));
+        return 0;
+    };
+    auto gapply = [&](GnApplyArgs& a, Pair out, int level, double bytes_per) -> int {
+        a.out = nullptr; a.out_hi = out.hi; a.out_lo = out.lo; a.level = level;
+        LAUNCH(KC_GN_APPLY, 1, (double)g.P[level] * a.C * bytes_per, 0.0, launch_gn_apply(a, g.d_img_off, B, nchunk_for(g.P[level], B), st));
+        return 0;
+    };
+    int r;
+    for (int s = 0; s < 3; ++s)
+        for (int b = 0; b < depths[s]; ++b) {
+            const ConvW* ds = nullptr;
+            if (b == 0) ds = &h->convs[ci++];
+            const ConvW& c1 = h->convs[ci++];
+            const ConvW& c2 = h->convs[ci++];
+            const ConvW& c3 = h->convs[ci++];
+            const int Lout = Lx + (c2.stride == 2 ? 1 : 0);
+            if (ds) {
+                if ((r = conv(*ds, x, Lx, Lout, h->rawDs.as<float>()))) return r;
+                if ((r = gstats(h->rawDs.as<float>(), ds->cout, Lout, stats[3]))) return r;
+            }
+            if ((r = conv(c1, x, Lx, Lx, h->rawMid.as<float>()))) return r;
+            if ((r = gstats(h->rawMid.as<float>(), c1.cout, Lx, stats[0]))) return r;
+            Pair m1 = pair_of(h->actMid, (size_t)g.P[Lx] * c1.cout);
+            {
+                GnApplyArgs a{};
+                a.raw = h->rawMid.as<float>(); a.stats = stats[0]; a.gamma = c1.gamma; a.beta = c1.beta; a.C = c1.cout; a.relu = 1;
+                if ((r = gapply(a, m1, Lx, 8))) return r;
+            }
+            if ((r = conv(c2, m1, Lx, Lout, h->rawMid2.as<float>()))) return r;
+            if ((r = gstats(h->rawMid2.as<float>(), c2.cout, Lout, stats[1]))) return r;
+            Pair m2 = pair_of(h->actMid2, (size_t)g.P[Lout] * c2.cout);
+            {
+                GnApplyArgs a{};
+                a.raw = h->rawMid2.as<float>(); a.stats = stats[1]; a.gamma = c2.gamma; a.beta = c2.beta; a.C = c2.cout; a.relu = 1;
+                if ((r = gapply(a, m2, Lout, 8))) return r;
+            }
+            if ((r = conv(c3, m2, Lout, Lout, h->raw3.as<float>()))) return r;
+            if ((r = gstats(h->raw3.as<float>(), c3.cout, Lout, stats[2]))) return r;
+            Pair out = pair_of(*pingpong[pp], (size_t)g.P[Lout] * c3.cout);
+            {
+                GnApplyArgs a{};
+                a.raw = h->raw3.as<float>(); a.stats = stats[2]; a.gamma = c3.gamma; a.beta = c3.beta; a.C = c3.cout; a.relu = 1;
+                if (ds) { a.raw2 = h->rawDs.as<float>(); a.stats2 = stats[3]; a.gamma2 = ds->gamma; a.beta2 = ds->beta; }
+                else { a.res_hi = x.hi; a.res_lo = x.lo; }
+                if ((r = gapply(a, out, Lout, 12))) return r;
+            }
+            x = out; pp ^= 1; Lx = Lout;
+        }
+    h->last_backbone_pixels = 0;     // the fp32 tap is only kept by the fp32 tier
+    *feat_hi = x.hi; *feat_lo = x.lo;
+    return 0;
+}
+
 // One (self-attention | cross-attention | MLP) sub-layer tail shared by encoder / decoder / decode step.
 struct RowCtx {
     int rows; int kc_gemm, kc_row;
     const float* ln_g; const float* ln_b;
+    int row0 = 0;        // first row of this sub-batch inside the row workspaces
 };
+static inline float* rowf(const DevBuf& b, const RowCtx& rc, int width) { return b.as<float>() + (size_t)rc.row0 * width; }
+static inline void* rowa(texocr_handle* h, const DevBuf& b, const RowCtx& rc, int width) { return (char*)b.p + (size_t)rc.row0 * width * h->esz; }
 
 static int sub_attn_out(texocr_handle* h, const RowCtx& rc, const AttnW& w, cudaStream_t st) {
     // y = o.Wo^T + bo -> GLU -> + residual   [model/attention.py:96-99,180 ; 254]
-    GemmArgs ga = mk_gemm(h->o.p, 512, w.wo, 512, h->s.p, 256, rc.rows, 512, 512, EPI_GLU_RES, h->dt, DT_F32, w.bo, h->x.as<float>(), 256);
+    GemmArgs ga = mk_gemm(rowa(h, h->o, rc, 512), 512, w.wo, 512, rowf(h->s, rc, 256), 256, rc.rows, 512, 512, EPI_GLU_RES, h->dt, DT_F32, w.bo, rowf(h->x, rc, 256), 256);
     LAUNCH(rc.kc_gemm, 1, gemm_bytes(ga, h->esz), gemm_flops(ga), run_gemm(h, ga, st));
     return 0;
 }
 static int sub_mlp(texocr_handle* h, const RowCtx& rc, const MlpW& w, cudaStream_t st) {
-    GemmArgs g1 = mk_gemm(h->xn.p, 256, w.w1, 256, h->hid.p, 1024, rc.rows, 2048, 256, EPI_GEGLU, h->dt, h->dt, w.b1, nullptr, 0);
+    GemmArgs g1 = mk_gemm(rowa(h, h->xn, rc, 256), 256, w.w1, 256, rowa(h, h->hid, rc, 1024), 1024, rc.rows, 2048, 256, EPI_GEGLU, h->dt, h->dt, w.b1, nullptr, 0);
     LAUNCH(rc.kc_gemm, 1, gemm_bytes(g1, h->esz), gemm_flops(g1), run_gemm(h, g1, st));
-    GemmArgs g2 = mk_gemm(h->hid.p, 1024, w.w2, 1024, h->s.p, 256, rc.rows, 256, 1024, EPI_BIAS_RES, h->dt, DT_F32, w.b2, h->x.as<float>(), 256);
+    GemmArgs g2 = mk_gemm(rowa(h, h->hid, rc, 1024), 1024, w.w2, 1024, rowf(h->s, rc, 256), 256, rc.rows, 256, 1024, EPI_BIAS_RES, h->dt, DT_F32, w.b2, rowf(h->x, rc, 256), 256);
     LAUNCH(rc.kc_gemm, 1, gemm_bytes(g2, h->esz), gemm_flops(g2), run_gemm(h, g2, st));
     return 0;
 }
@@ -507,8 +633,8 @@ static int sub_mlp(texocr_handle* h, const RowCtx& rc, const MlpW& w, cudaStream
 static int sub_norm(texocr_handle* h, const RowCtx& rc, bool last, const float* fin_g, const float* fin_b, float* fin_out_f,
                     void* fin_out_a, cudaStream_t st) {
     Ln2Args a{};
-    a.in = h->s.as<float>(); a.rows = rc.rows; a.dt_a = h->dt;
-    if (!last) { a.g1 = rc.ln_g; a.b1 = rc.ln_b; a.g2 = rc.ln_g; a.b2 = rc.ln_b; a.o1f = h->x.as<float>(); a.o2a = h->xn.p; }
+    a.in = rowf(h->s, rc, 256); a.rows = rc.rows; a.dt_a = h->dt;
+    if (!last) { a.g1 = rc.ln_g; a.b1 = rc.ln_b; a.g2 = rc.ln_g; a.b2 = rc.ln_b; a.o1f = rowf(h->x, rc, 256); a.o2a = rowa(h, h->xn, rc, 256); }
     else { a.g1 = fin_g; a.b1 = fin_b; a.o1f = fin_out_f; a.o1a = fin_out_a; }
     LAUNCH(rc.kc_row, 1, (double)rc.rows * 256 * (4 + 4 + h->esz), 0.0, launch_ln2(a, st));
     return 0;
@@ -529,7 +655,13 @@ static int run_encoder(texocr_handle* h, const float* d_img, const EncGeom& g, c
     const texocr_config& c = h->cfg;
     int r;
     ENSURE(h->proj_out, (size_t)g.P[4] * 256 * 4);
-    if (c.encoder_kind == TEXOCR_ENC_HYBRID) {
+    if (c.encoder_kind == TEXOCR_ENC_HYBRID && h->dt == DT_BF16 && h->use_tcgen05) {
+        const void *fh = nullptr, *fl = nullptr;
+        if ((r = run_backbone_tc(h, d_img, g, st, &fh, &fl))) return r;
+        GemmArgs ga = mk_gemm(fh, 1024, h->proj_w, 1024, h->proj_out.p, 256, (int)g.P[4], 256, 1024, EPI_STORE, DT_BF16, DT_F32, h->proj_b, nullptr, 0);
+        ga.A2 = fl; ga.W2 = h->proj_w_lo;
+        LAUNCH(KC_ENC_GEMM, 1, gemm_bytes(ga, 4), gemm_flops(ga), launch_gemm_tc(ga, st));
+    } else if (c.encoder_kind == TEXOCR_ENC_HYBRID) {
         const float* feat = nullptr;
         if ((r = run_backbone(h, d_img, g, st, &feat))) return r;
         const void* a_ptr = feat;
@@ -588,6 +720,7 @@ static int run_encoder(texocr_handle* h, const float* d_img, const EncGeom& g, c
 static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_typed, int ntok, cudaStream_t st) {
     const int L = h->cfg.dec_layers;
     ENSURE(h->crosskv, (size_t)ntok * L * 1024 * h->esz);
+    h->crosskv_rows = ntok;
     const void* a_ptr = enc_f32;
     if (h->dt != DT_F32) {
         if (!enc_typed) {
@@ -603,63 +736,111 @@ static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_t
 }
 
 // ------------------------------------------------------------------------------------------------ decode step
+constexpr int MAX_BRANCH = 8;
 struct DecState {
-    int64_t* cur_tok; int* step; int* done_step; int* block_counter; int* seen;
+    int64_t* cur_tok; int* step; int* done_step; int* block_counter; int* seen;     // step/done/counter: [MAX_BRANCH]
 };
+static size_t dec_state_bytes(int B) { return (size_t)B * 8 + 3 * MAX_BRANCH * 4 + (size_t)B * 4; }
 static DecState dec_state(texocr_handle* h, int B) {
     DecState d;
     char* p = (char*)h->dec_state.p;
     d.cur_tok = (int64_t*)p;
     int* ip = (int*)(p + (size_t)B * 8);
-    d.step = ip; d.done_step = ip + 1; d.block_counter = ip + 2; d.seen = ip + 4;
+    d.step = ip; d.done_step = ip + MAX_BRANCH; d.block_counter = ip + 2 * MAX_BRANCH; d.seen = ip + 3 * MAX_BRANCH;
     return d;
 }
 
-// One greedy step for B rows.  `t_host` is only used for the profiler's byte accounting (-1: unknown).
-static int enqueue_decode_step(texocr_handle* h, int B, int tcap, int eos, const int* d_enc_off, int max_s, double sum_s,
-                               int t_host, cudaStream_t st) {
+// One greedy step for rows [row0, row0+rows) of a batch of B (a "branch": every row is independent, so the batch is cut
+// into sub-batches whose step graphs run concurrently and hide each other's launch / dependency latency).
+// `t_host` is only used for the profiler's byte accounting (-1: unknown).
+static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int branch, int tcap, int eos, const int* d_enc_off,
+                               int max_s, double sum_s, int t_host, cudaStream_t st) {
     const texocr_config& c = h->cfg;
     const int L = c.dec_layers;
     DecState ds = dec_state(h, B);
-    RowCtx rc{B, KC_DEC_GEMM, KC_DEC_ROW, h->dec_ln_g, h->dec_ln_b};
+    RowCtx rc{rows, KC_DEC_GEMM, KC_DEC_ROW, h->dec_ln_g, h->dec_ln_b, row0};
+    int* step = ds.step + branch;
+    const size_t e = h->esz;
     int r;
-    LAUNCH(KC_DEC_ROW, 1, (double)B * 256 * (8 + 4 + h->esz), 0.0,
-           launch_embed_ln(ds.cur_tok, ds.step, 1, B, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b, h->x.as<float>(), h->xn.p, h->dt, st));
+    LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4 + e), 0.0,
+           launch_embed_ln(ds.cur_tok + row0, step, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b,
+                           rowf(h->x, rc, 256), rowa(h, h->xn, rc, 256), h->dt, st));
     const double tkeys = t_host >= 0 ? (double)(t_host + 1) : 0.0;
+    char* qb = (char*)rowa(h, h->qkv, rc, 1536);
     for (int l = 0; l < L; ++l) {
         // ---- causal self-attention over the KV cache
-        GemmArgs gq = mk_gemm(h->xn.p, 256, h->dec_self[l].wqkv, 256, h->qkv.p, 1536, B, 1536, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
-        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gq, h->esz), gemm_flops(gq), run_gemm(h, gq, st));
+        GemmArgs gq = mk_gemm(rowa(h, h->xn, rc, 256), 256, h->dec_self[l].wqkv, 256, qb, 1536, rows, 1536, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gq, e), gemm_flops(gq), run_gemm(h, gq, st));
         AttnDecodeArgs ad{};
-        char* qb = (char*)h->qkv.p;
-        char* kv = (char*)h->kvcache.p + (size_t)l * B * tcap * 1024 * h->esz;
-        ad.q = qb; ad.ldq = 1536; ad.knew = qb + 512 * h->esz; ad.vnew = qb + 1024 * h->esz; ad.ldnew = 1536;
-        ad.kcache = kv; ad.vcache = kv + 512 * h->esz; ad.ldkv = 1024; ad.batch_stride = (int64_t)tcap * 1024;
-        ad.step = ds.step; ad.o = h->o.p; ad.ldo = 512; ad.batch = B; ad.dt = h->dt;
-        LAUNCH(KC_DEC_ATTN_SELF, 1, (double)B * tkeys * 1024 * h->esz, 4.0 * B * tkeys * 512, launch_attn_decode(ad, tcap, st));
+        char* kv = (char*)h->kvcache.p + ((size_t)l * B + row0) * tcap * 1024 * e;
+        ad.q = qb; ad.ldq = 1536; ad.knew = qb + 512 * e; ad.vnew = qb + 1024 * e; ad.ldnew = 1536;
+        ad.kcache = kv; ad.vcache = kv + 512 * e; ad.ldkv = 1024; ad.batch_stride = (int64_t)tcap * 1024;
+        ad.step = step; ad.o = rowa(h, h->o, rc, 512); ad.ldo = 512; ad.batch = rows; ad.dt = h->dt;
+        if (h->use_tma_attn && attn_decode_tma_supported(ad))
+            LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512,
+                   launch_attn_decode_tma(ad, kv, (long)rows * tcap, 1024, 0, tcap, h->num_sms, st));
+        else
+            LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512, launch_attn_decode(ad, tcap, st));
         if ((r = sub_attn_out(h, rc, h->dec_self[l], st))) return r;
         if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
-        // ---- cross-attention over the (pre-projected) encoder memory
-        GemmArgs gc = mk_gemm(h->xn.p, 256, h->dec_cross[l].wq, 256, h->qkv.p, 512, B, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
-        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gc, h->esz), gemm_flops(gc), run_gemm(h, gc, st));
+        // ---- cross-attention over the (pre-projected) encoder memory; q goes to the first 512 columns of this branch's qkv rows
+        GemmArgs gc = mk_gemm(rowa(h, h->xn, rc, 256), 256, h->dec_cross[l].wq, 256, qb, 512, rows, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gc, e), gemm_flops(gc), run_gemm(h, gc, st));
         AttnDecodeArgs ac{};
-        char* ckv = (char*)h->crosskv.p + (size_t)l * 1024 * h->esz;
-        ac.q = h->qkv.p; ac.ldq = 512; ac.kcache = ckv; ac.vcache = ckv + 512 * h->esz; ac.ldkv = L * 1024;
-        ac.k_off = d_enc_off; ac.o = h->o.p; ac.ldo = 512; ac.batch = B; ac.dt = h->dt;
-        LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * 1024 * h->esz, 4.0 * sum_s * 512, launch_attn_decode(ac, max_s, st));
+        char* ckv = (char*)h->crosskv.p + (size_t)l * 1024 * e;
+        ac.q = qb; ac.ldq = 512; ac.kcache = ckv; ac.vcache = ckv + 512 * e; ac.ldkv = L * 1024;
+        ac.k_off = d_enc_off + row0; ac.o = rowa(h, h->o, rc, 512); ac.ldo = 512; ac.batch = rows; ac.dt = h->dt;
+        if (h->use_tma_attn && attn_decode_tma_supported(ac))
+            LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512,
+                   launch_attn_decode_tma(ac, h->crosskv.p, (long)h->crosskv_rows, L * 1024, l * 1024, 0, h->num_sms, st));
+        else
+            LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512, launch_attn_decode(ac, max_s, st));
         if ((r = sub_attn_out(h, rc, h->dec_cross[l], st))) return r;
         if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
         // ---- GeGLU MLP
         if ((r = sub_mlp(h, rc, h->dec_mlp[l], st))) return r;
-        if ((r = sub_norm(h, rc, l == L - 1, h->dec_norm_g, h->dec_norm_b, nullptr, h->xn.p, st))) return r;
+        if ((r = sub_norm(h, rc, l == L - 1, h->dec_norm_g, h->dec_norm_b, nullptr, rowa(h, h->xn, rc, 256), st))) return r;
     }
-    GemmArgs gl = mk_gemm(h->xn.p, 256, h->w_logits, 256, h->logits.p, c.vocab_size, B, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
-    LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gl, h->esz), gemm_flops(gl), run_gemm(h, gl, st));
+    float* lg = h->logits.as<float>() + (size_t)row0 * c.vocab_size;
+    GemmArgs gl = mk_gemm(rowa(h, h->xn, rc, 256), 256, h->w_logits, 256, lg, c.vocab_size, rows, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
+    LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gl, e), gemm_flops(gl), run_gemm(h, gl, st));
     ArgmaxArgs aa{};
-    aa.logits = h->logits.as<float>(); aa.B = B; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>(); aa.out_ld = tcap;
-    aa.cur_tok = ds.cur_tok; aa.step = ds.step; aa.seen_eos = ds.seen; aa.done_step = ds.done_step; aa.block_counter = ds.block_counter;
-    aa.eos = eos;
-    LAUNCH(KC_DEC_ARGMAX, 1, (double)B * c.vocab_size * 4, 0.0, launch_argmax_step(aa, st));
+    aa.logits = lg; aa.B = rows; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>() + (size_t)row0 * tcap; aa.out_ld = tcap;
+    aa.cur_tok = ds.cur_tok + row0; aa.step = step; aa.seen_eos = ds.seen + row0; aa.done_step = ds.done_step + branch;
+    aa.block_counter = ds.block_counter + branch; aa.eos = eos;
+    LAUNCH(KC_DEC_ARGMAX, 1, (double)rows * c.vocab_size * 4, 0.0, launch_argmax_step(aa, st));
+    return 0;
+}
+
+struct BranchPlan { int n; int row0[MAX_BRANCH]; int rows[MAX_BRANCH]; };
+static BranchPlan plan_branches(texocr_handle* h, int B) {
+    int n = h->decode_branches > 0 ? h->decode_branches : (B >= 256 ? 4 : (B >= 64 ? 2 : 1));
+    n = std::max(1, std::min(std::min(n, MAX_BRANCH), B));
+    BranchPlan p;
+    p.n = n;
+    const int per = (B + n - 1) / n;
+    for (int i = 0; i < n; ++i) { p.row0[i] = std::min(B, i * per); p.rows[i] = std::min(B, (i + 1) * per) - p.row0[i]; }
+    while (p.n > 1 && p.rows[p.n - 1] <= 0) --p.n;
+    return p;
+}
+
+// all branches of one decode step: sequentially on `st` (eager / profiling) or forked onto the branch streams (graph capture)
+static int enqueue_all_branches(texocr_handle* h, const BranchPlan& bp, bool fork, int B, int tcap, int eos, const int* d_enc_off,
+                                int max_s, double sum_s, int t_host, cudaStream_t st) {
+    int r;
+    if (!fork || bp.n == 1) {
+        for (int i = 0; i < bp.n; ++i)
+            if ((r = enqueue_decode_step(h, B, bp.row0[i], bp.rows[i], i, tcap, eos, d_enc_off, max_s, sum_s, t_host, st))) return r;
+        return 0;
+    }
+    CK(cudaEventRecord(h->fork_ev, st));
+    for (int i = 1; i < bp.n; ++i) {
+        CK(cudaStreamWaitEvent(h->branch_stream[i], h->fork_ev, 0));
+        if ((r = enqueue_decode_step(h, B, bp.row0[i], bp.rows[i], i, tcap, eos, d_enc_off, max_s, sum_s, t_host, h->branch_stream[i]))) return r;
+        CK(cudaEventRecord(h->join_ev[i], h->branch_stream[i]));
+    }
+    if ((r = enqueue_decode_step(h, B, bp.row0[0], bp.rows[0], 0, tcap, eos, d_enc_off, max_s, sum_s, t_host, st))) return r;
+    for (int i = 1; i < bp.n; ++i) CK(cudaStreamWaitEvent(st, h->join_ev[i], 0));
     return 0;
 }
 
@@ -676,30 +857,38 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     if ((r = ensure_rows(h, B))) return r;
     ENSURE(h->logits, (size_t)B * c.vocab_size * 4);
     ENSURE(h->kvcache, (size_t)c.dec_layers * B * tcap * 1024 * h->esz);
-    ENSURE(h->dec_state, (size_t)B * 8 + 16 + (size_t)B * 4);
+    ENSURE(h->dec_state, dec_state_bytes(B));
     ENSURE(h->out_ids, (size_t)B * tcap * 8);
-    if (!h->h_poll) CK(cudaMallocHost(&h->h_poll, 64));
+    if (!h->h_poll) CK(cudaMallocHost(&h->h_poll, 4 * MAX_BRANCH * 4));
     DecState ds = dec_state(h, B);
-    CK(cudaMemsetAsync((char*)h->dec_state.p + (size_t)B * 8, 0, 16 + (size_t)B * 4, st));
+    CK(cudaMemsetAsync((char*)h->dec_state.p + (size_t)B * 8, 0, dec_state_bytes(B) - (size_t)B * 8, st));
     CK(cudaMemcpyAsync(ds.cur_tok, d_start, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+    const BranchPlan bp = plan_branches(h, B);
+    for (int i = 1; i < bp.n; ++i) {
+        if (!h->branch_stream[i]) {
+            CK(cudaStreamCreateWithFlags(&h->branch_stream[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+        }
+    }
+    if (!h->fork_ev) CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
 
     const bool graph_ok = h->use_graph && !h->prof_on;
     if (graph_ok) {
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
-                         h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv.p && h->gkey.x == h->x.p;
+                         h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
             if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
             if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
             const int64_t before = h->launches;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            r = enqueue_decode_step(h, B, tcap, eos, d_enc_off, max_s, sum_s, -1, st);
+            r = enqueue_all_branches(h, bp, true, B, tcap, eos, d_enc_off, max_s, sum_s, -1, st);
             cudaError_t ce = cudaStreamEndCapture(st, &h->graph);
             if (r) return r;
             CK(ce);
             CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
             h->gkey.kernels = (int)(h->launches - before);
             h->launches = before;        // capture does not execute
-            h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s;
+            h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
             h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv.p; h->gkey.x = h->x.p;
         }
     }
@@ -712,25 +901,34 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     bool stop = false;
     for (int t = 0; t < max_len && !stop; ++t) {
         if (graph_ok) { CK(cudaGraphLaunch(h->graph_exec, st)); h->launches += h->gkey.kernels; }
-        else if ((r = enqueue_decode_step(h, B, tcap, eos, d_enc_off, max_s, sum_s, t, st))) return r;
+        else if ((r = enqueue_all_branches(h, bp, false, B, tcap, eos, d_enc_off, max_s, sum_s, t, st))) return r;
         ++issued;
         if (eos >= 0 && issued % POLL == 0 && t + 1 < max_len) {
             const int slot = polls & 1;
             if (polls >= 1) {      // wait for the PREVIOUS poll (issued POLL steps ago), keeps the queue non-empty
                 CK(cudaEventSynchronize(ev[slot ^ 1]));
-                if (h->h_poll[slot ^ 1] > 0) stop = true;
+                bool all = true;
+                for (int i = 0; i < bp.n; ++i) all = all && h->h_poll[(slot ^ 1) * MAX_BRANCH + i] > 0;
+                if (all) stop = true;
             }
-            CK(cudaMemcpyAsync(&h->h_poll[slot], ds.done_step, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&h->h_poll[slot * MAX_BRANCH], ds.done_step, MAX_BRANCH * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(ev[slot], st));
             ++polls;
         }
     }
-    CK(cudaMemcpyAsync(&h->h_poll[2], ds.done_step, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h->h_poll[2 * MAX_BRANCH], ds.done_step, MAX_BRANCH * 4, cudaMemcpyDeviceToHost, st));
     if ((r = from_device(h, out_ids, h->out_ids.p, (size_t)B * tcap * 8, st))) return r;
     CK(cudaStreamSynchronize(st));
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
-    const int done = h->h_poll[2];
-    *n_steps = done > 0 ? done : max_len;
+    // every row holds an EOS once every branch has seen one in all of its rows: the LAST branch to finish decides
+    int done = 0;
+    bool all_done = true;
+    for (int i = 0; i < bp.n; ++i) {
+        const int d = h->h_poll[2 * MAX_BRANCH + i];
+        all_done = all_done && d > 0;
+        done = std::max(done, d);
+    }
+    *n_steps = all_done ? done : max_len;
     return 0;
 }
 
@@ -757,6 +955,7 @@ int texocr_create(const texocr_config* cfg, int device, texocr_handle** out) {
     if (prop.major != 10) return fail(h, TEXOCR_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     CK(cudaSetDevice(device));
     h = new texocr_handle();
+    h->num_sms = prop.multiProcessorCount;
     h->cfg = *cfg; h->device = device;
     h->dt = cfg->precision == TEXOCR_BF16 ? DT_BF16 : DT_F32;
     h->esz = h->dt == DT_BF16 ? 2 : 4;
@@ -778,7 +977,7 @@ void texocr_destroy(texocr_handle* h) {
     for (void* p : h->weight_allocs) cudaFree(p);
     DevBuf* bufs[] = {&h->geom, &h->img_stage, &h->raw1, &h->act2, &h->actA, &h->actB, &h->rawMid, &h->actMid, &h->rawMid2, &h->actMid2,
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
-                      &h->proj_out, &h->patch_cols, &h->backbone_a, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
+                      &h->proj_out, &h->patch_cols, &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
                       &h->enc_out, &h->enc_a, &h->crosskv, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
                       &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -788,6 +987,11 @@ void texocr_destroy(texocr_handle* h) {
     if (h->hop_in) cudaEventDestroy(h->hop_in);
     if (h->hop_out) cudaEventDestroy(h->hop_out);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int i = 0; i < 8; ++i) {
+        if (h->branch_stream[i]) cudaStreamDestroy(h->branch_stream[i]);
+        if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]);
+    }
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     for (auto& p : h->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     delete h;
@@ -1025,6 +1229,21 @@ int texocr_profile_read(texocr_handle* h, texocr_profile_row* rows, int32_t cap)
 int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
+    if (!strcmp(name, "pdl")) {
+        g_texocr_pdl = value != 0;
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        return 0;
+    }
+    if (!strcmp(name, "tma_attention")) {
+        h->use_tma_attn = value != 0;
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        return 0;
+    }
+    if (!strcmp(name, "decode_branches")) {
+        if (value < 0 || value > MAX_BRANCH) return fail(h, TEXOCR_ERR_ARG, "decode_branches must be in [0, %d] (0 = automatic)", MAX_BRANCH);
+        h->decode_branches = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "tcgen05")) {
         h->use_tcgen05 = value != 0;
         if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }

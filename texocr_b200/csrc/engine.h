@@ -26,6 +26,7 @@ struct ConvW {           // one weight-standardised convolution + its GroupNorm
     std::string name, gn;
     int cin, cout, k, stride, act;
     float* w = nullptr;          // [cout][k*k*cin] fp32, (ky,kx,c) order, standardised
+    void* w_hi = nullptr; void* w_lo = nullptr;   // bf16 tier: split-bf16 pair of the same matrix (tcgen05 bf16x3 path)
     float* gamma = nullptr; float* beta = nullptr;
 };
 
@@ -53,7 +54,7 @@ struct texocr_handle {
     // ---- packed weights
     float* stem_w = nullptr; float* stem_g = nullptr; float* stem_b = nullptr;
     std::vector<ConvW> convs;                 // the 39 non-stem convolutions in execution order
-    void* proj_w = nullptr; float* proj_b = nullptr; int proj_k = 0;
+    void* proj_w = nullptr; void* proj_w_lo = nullptr; float* proj_b = nullptr; int proj_k = 0;
     float* cls = nullptr; float* pos = nullptr;
     float* enc_ln_g = nullptr; float* enc_ln_b = nullptr; float* enc_norm_g = nullptr; float* enc_norm_b = nullptr;
     std::vector<AttnW> enc_attn; std::vector<MlpW> enc_mlp;
@@ -68,10 +69,12 @@ struct texocr_handle {
     int* h_geom = nullptr; size_t h_geom_cap = 0;   // pinned staging for geom
     cudaEvent_t geom_ev = nullptr, hop_in = nullptr, hop_out = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t branch_stream[8] = {nullptr}; cudaEvent_t join_ev[8] = {nullptr}; cudaEvent_t fork_ev = nullptr;
+    int decode_branches = 0;                   // 0 = automatic (4 for B >= 256, 2 for B >= 64)
     DevBuf img_stage;                          // device copy of host images
     DevBuf raw1, act2, actA, actB, rawMid, actMid, rawMid2, actMid2, raw3, rawDs;
     DevBuf gn_partial, gn_stats[4];
-    DevBuf proj_out, patch_cols, backbone_a;
+    DevBuf proj_out, patch_cols, backbone_a, col;
     DevBuf x, s, xn, qkv, o, hid, logits;
     DevBuf enc_out, enc_a, crosskv, kvcache;
     DevBuf ids_stage, mask_stage, enc_stage, tgt_stage, row_loss, scalars;
@@ -79,11 +82,12 @@ struct texocr_handle {
     DevBuf out_ids;                            // int64 [B, max_len]
     int* h_poll = nullptr;                     // pinned: done_step polls
     int last_backbone_pixels = 0;
+    int crosskv_rows = 0;
 
     // ---- decode-step CUDA graph
     bool use_graph = true;
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
-    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; } gkey;
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; } gkey;
 
     // ---- instrumentation
     int64_t launches = 0;
@@ -93,4 +97,6 @@ struct texocr_handle {
     double prof_ms[KC_COUNT] = {0}; double prof_bytes[KC_COUNT] = {0}; double prof_flops[KC_COUNT] = {0};
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
+    bool use_tma_attn = true;
+    int num_sms = 148;
 };

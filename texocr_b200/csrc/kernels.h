@@ -6,6 +6,21 @@
 
 enum { DT_F32 = 0, DT_BF16 = 1 };
 
+// Launch with programmatic dependent launch enabled (kernels call pdl_wait() before reading their inputs).
+extern int g_texocr_pdl;      // 1 = launch decode-path kernels with programmatic dependent launch (engine.cu)
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_texocr_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 enum GemmEpi {
     EPI_STORE = 0,      // C = A.W^T (+bias)                       out type = dt_c
     EPI_GLU_RES = 1,    // pairs (2j,2j+1): (a+ba)*sigmoid(g+bg) + res    -> float [M, N/2]
@@ -43,14 +58,21 @@ cudaError_t launch_gn_stats(const float* raw, int C, int level, const int* img_o
 struct GnApplyArgs {
     const float* raw; const float* stats; const float* gamma; const float* beta;       // main input
     const float* raw2; const float* stats2; const float* gamma2; const float* beta2;   // optional normalised residual
-    const float* res;                                                                    // optional plain residual
-    float* out;
+    const float* res;                                                                    // optional plain residual (fp32)
+    const void* res_hi; const void* res_lo;                                              // ... or as a split-bf16 pair
+    float* out;                                                                          // fp32 output, or
+    void* out_hi; void* out_lo;                                                          // split-bf16 pair: v = hi + lo
     int C, level, relu;
 };
 cudaError_t launch_gn_apply(const GnApplyArgs& a, const int* img_off, int nimg, int nchunk, cudaStream_t st);
+// out2 (fp32) or the split-bf16 pair (out_hi, out_lo)
 cudaError_t launch_gn_apply_maxpool(const float* raw1, const float* stats, const float* gamma, const float* beta,
-                                    float* out2, const int* img_off, const int* img_hw, int nimg, int total_p2,
-                                    cudaStream_t st);
+                                    float* out2, void* out_hi, void* out_lo, const int* img_off, const int* img_hw, int nimg,
+                                    int total_p2, cudaStream_t st);
+// Explicit im2col of a split-bf16 NHWC activation: out[m][(ky*k+kx)*C + c] for output pixel m (level lout) of a
+// k x k / stride convolution with TF-SAME padding `pad` before (utils.py:93-123); zero where the tap is out of range.
+cudaError_t launch_im2col_split(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, const ConvGather& cg,
+                                long total_out_pixels, cudaStream_t st);
 cudaError_t launch_im2col_patch(const float* img, float* cols, const int* img_off, const int* img_hw, int nimg,
                                 int total_p4, cudaStream_t st);
 cudaError_t launch_assemble_tokens(const float* proj /*[P4,256]*/, const float* cls, const float* pos, float* x0,
@@ -112,3 +134,10 @@ struct AttnDecodeArgs {
 };
 // nk_cap >= the largest key count any row can have (sizes the per-head score buffer in shared memory)
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, int nk_cap, cudaStream_t st);
+
+// bf16 tier: persistent TMA-fed streaming version of the decode attention (attn_decode_tma.cu).
+// map_base / map_rows / map_cols describe the 2-D K|V matrix the rows live in (row stride a.ldkv); col0 = column of
+// head 0's K inside a row; tcap = cache rows per sequence (self-attention).
+bool attn_decode_tma_supported(const AttnDecodeArgs& a);
+cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base, long map_rows, int map_cols, int col0, int tcap,
+                                   int num_sms, cudaStream_t st);

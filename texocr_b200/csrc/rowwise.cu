@@ -33,6 +33,8 @@ template <typename T> TX_DEVINL void store8(T* p, const float* v) {
 
 template <typename TAct>
 __global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
     if (row >= a.rows) return;
     float v[8];
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict
                                                        const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, int vocab,
                                                        const float* __restrict__ g, const float* __restrict__ b,
                                                        float* __restrict__ x, TAct* __restrict__ xn) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
     if (row >= rows) return;
     long id = (long)ids[row];
@@ -68,6 +72,8 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict
 
 __global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
     __shared__ int s_last;
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = *a.step;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row < a.B) {
@@ -151,9 +157,8 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 cudaError_t launch_ln2(const Ln2Args& a, cudaStream_t st) {
     if (a.rows <= 0) return cudaSuccess;
     const int blocks = (a.rows + 7) / 8;
-    if (a.dt_a == DT_F32) ln2_kernel<float><<<blocks, 256, 0, st>>>(a);
-    else ln2_kernel<bf16><<<blocks, 256, 0, st>>>(a);
-    return cudaGetLastError();
+    if (a.dt_a == DT_F32) return launch_pdl(ln2_kernel<float>, dim3(blocks), dim3(256), 0, st, a);
+    return launch_pdl(ln2_kernel<bf16>, dim3(blocks), dim3(256), 0, st, a);
 }
 
 cudaError_t launch_embed_ln(const int64_t* ids, const int* step, int T, int rows, const float* tok_emb,
@@ -162,15 +167,12 @@ cudaError_t launch_embed_ln(const int64_t* ids, const int* step, int T, int rows
     if (rows <= 0) return cudaSuccess;
     const int blocks = (rows + 7) / 8;
     if (dt_a == DT_F32)
-        embed_ln_kernel<float><<<blocks, 256, 0, st>>>(ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (float*)xn);
-    else
-        embed_ln_kernel<bf16><<<blocks, 256, 0, st>>>(ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (bf16*)xn);
-    return cudaGetLastError();
+        return launch_pdl(embed_ln_kernel<float>, dim3(blocks), dim3(256), 0, st, ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (float*)xn);
+    return launch_pdl(embed_ln_kernel<bf16>, dim3(blocks), dim3(256), 0, st, ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (bf16*)xn);
 }
 
 cudaError_t launch_argmax_step(const ArgmaxArgs& a, cudaStream_t st) {
-    argmax_step_kernel<<<(a.B + 7) / 8, 256, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(argmax_step_kernel, dim3((a.B + 7) / 8), dim3(256), 0, st, a);
 }
 
 cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_t rows, int V, float* row_loss,

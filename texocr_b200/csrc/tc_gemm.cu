@@ -118,6 +118,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int nkb = p.K / BK;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -133,6 +134,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();        // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -252,7 +254,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 std::mutex g_mu;
-std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> g_maps;
+std::map<std::tuple<const void*, long, int, long, int, int, int>, CUtensorMap> g_maps;
 
 cudaError_t get_encode() {
     if (g_encode) return cudaSuccess;
@@ -265,10 +267,18 @@ cudaError_t get_encode() {
     return cudaSuccess;
 }
 
-// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = box_rows x 64 columns, 128B swizzle, zero OOB fill.
+// GEMM operand map: box = box_rows x 64 columns, 128B swizzle
 cudaError_t get_map(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+    return tma_map_2d_bf16(ptr, rows, cols, ld, box_rows, BK, 1, out);
+}
+
+}  // namespace
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); zero OOB fill; cached per (ptr, shape, box).
+cudaError_t tma_map_2d_bf16(const void* ptr, long rows, int cols, long ld, int box_rows, int box_cols, int swizzle128,
+                            CUtensorMap* out) {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+    auto key = std::make_tuple(ptr, rows, cols, ld, box_rows, box_cols, swizzle128);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return cudaSuccess; }
     cudaError_t e = get_encode();
@@ -276,17 +286,19 @@ cudaError_t get_map(const void* ptr, int rows, int cols, int ld, int box_rows, C
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps[key] = m;
     *out = m;
     return cudaSuccess;
 }
+
+namespace {
 
 template <int BN, int EPI, typename TC, int SPLIT>
 cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
@@ -300,8 +312,7 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
         attr_set = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    kern<<<grid, 192, S::TOTAL, st>>>(a, w, a2, w2, p);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid, dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
 }
 
 template <int BN, int SPLIT>
@@ -338,7 +349,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (mt * ((g.N + 127) / 128) < 120) bn = 64;
     if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
     const bool split = g.A2 != nullptr;
-    if (split) bn = 128;
+    if (split) bn = g.N <= 64 ? 64 : 128;
     TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres};
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
@@ -348,6 +359,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (split) {
         if ((e = get_map(g.A2, g.M, g.K, g.lda, BM, &a2)) != cudaSuccess) return e;
         if ((e = get_map(g.W2, g.N, g.K, g.ldw, bn, &w2)) != cudaSuccess) return e;
+        if (bn == 64) return launch_epi<64, 3>(g, a, w, a2, w2, p, st);
         return launch_epi<128, 3>(g, a, w, a2, w2, p, st);
     }
     if (bn == 128) return launch_epi<128, 1>(g, a, w, a2, w2, p, st);

@@ -1,8 +1,15 @@
 // tcgen05 / TMEM / TMA GEMM for bf16 operands (sm_100a).  See tc_gemm.cu.
 #pragma once
+#include <cuda.h>
+
 #include "kernels.h"
 
 // true when launch_gemm_tc can take this problem (shape / alignment / epilogue); the engine falls back to the
 // FFMA kernel otherwise.
 bool tc_gemm_supported(const GemmArgs& g);
 cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+
+// Shared TMA helper (driver entry point resolved through the runtime; no libcuda link): cached tensor map of a 2-D bf16
+// matrix [rows, cols] (row stride ld elements), box = box_rows x box_cols, optional 128-byte swizzle, zero OOB fill.
+cudaError_t tma_map_2d_bf16(const void* ptr, long rows, int cols, long ld, int box_rows, int box_cols, int swizzle128,
+                            CUtensorMap* out);
