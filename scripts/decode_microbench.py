@@ -37,16 +37,15 @@ def decode_us(label):
     print(f"{label}: generate(256) {t256:.1f} ms, generate(64) {t64:.1f} ms -> decode {(t256 - t64) / 192 * 1000:.0f} us/step (t in 64..256)")
 
 
-for tma in (1, 0):
-    for pdl in (1, 0):
-        for nb in (1, 2, 4):
-            eng.set_option("tma_attention", tma)
-            eng.set_option("pdl", pdl)
-            eng.set_option("decode_branches", nb)
-            decode_us(f"tma_attn={tma} pdl={pdl} branches={nb}")
-eng.set_option("tma_attention", 1)
-eng.set_option("pdl", 1)
+for cps in (3, 2):
+    eng.set_option("attn_ctas_per_sm", cps)
+    for nb, stag in ((1, 0), (2, 100), (4, 0), (4, 50), (8, 25)):
+        eng.set_option("decode_branches", nb)
+        eng.set_option("stagger_us", stag)
+        decode_us(f"attn_ctas/sm={cps} branches={nb} stagger={stag}us")
 eng.set_option("decode_branches", 1)
-for B in (64, 128, 256):
-    sub = img[:B]
-    print(f"B={B} (1 branch): generate(256) {timeit(lambda: m.generate(sub, 256)):.1f} ms")
+eng.set_option("attn_ctas_per_sm", 3)
+for skip, label in ((3, "no attention"), (12, "attention only")):
+    eng.set_option("dbg_skip", skip)
+    decode_us(f"branches=1 {label}")
+eng.set_option("dbg_skip", 0)

@@ -176,6 +176,16 @@ def test_decode_branches_do_not_change_tokens(m16, golden):
     eng.set_option("decode_branches", 0)
     for o in outs[1:]:
         assert torch.equal(outs[0], o)
+    # early exit across independent branches: same n_steps and tokens as a single branch
+    enc = m16.encoder(img)
+    start = torch.full((96, 1), m16.dims.bos, dtype=torch.long, device="cuda")
+    eos = int(outs[0][0, 20])
+    res = []
+    for nb in (1, 4):
+        eng.set_option("decode_branches", nb)
+        res.append(m16.decoder.generate(start_tokens=start, eos_tok=eos, max_len=48, enc=enc))
+    eng.set_option("decode_branches", 0)
+    assert res[0].shape == res[1].shape and torch.equal(res[0], res[1])
 
 
 def test_tma_attention_matches_simple_kernel(m16):

@@ -62,18 +62,24 @@ TX_DEVINL void unpack8(const uint4& r, float* o) {
     for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
 }
 
-template <bool SELF>
-__global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_constant__ CUtensorMap tm, const Args a) {
+// WPH = consumer warps per head: the 16 keys of a stage are dealt to them in groups of 4, each keeps its own online-softmax
+// state and the partial states are merged once per unit (more independent dependency chains per SM: the per-warp chain
+// LDS -> FMA -> 3 shuffles -> max -> exp -> FMA is latency-bound).
+template <bool SELF, int WPH>
+__global__ void __launch_bounds__(32 * (1 + 2 * WPH)) attn_decode_tma_kernel(const __grid_constant__ CUtensorMap tm,
+                                                                           const __grid_constant__ CUtensorMap tm4, const Args a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + NS * STAGE);
     uint64_t* empty = full + NS;
+    float* scratch = reinterpret_cast<float*>(empty + NS);          // [2 parity][2 heads][WPH][8 dg][10]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     pdl_launch_dependents();
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm4) : "memory");
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * WPH); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -95,35 +101,46 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
                 for (int c = 0; c < nchunk; ++c, ++it) {
                     const int s = it % NS, ph = (it / NS) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], STAGE);
-                    tma_load_2d(&tm, &full[s], ring + s * STAGE, a.col0 + hp * 128, row0 + c * CH);
-                    tma_load_2d(&tm, &full[s], ring + s * STAGE + TILE, a.col0 + 512 + hp * 128, row0 + c * CH);
+                    uint8_t* kt = ring + s * STAGE;
+                    const int left = nk - c * CH;
+                    const int kc = a.col0 + hp * 128, r = row0 + c * CH;
+                    if (left >= CH) {
+                        mbar_expect_tx(&full[s], STAGE);
+                        tma_load_2d(&tm, &full[s], kt, kc, r);
+                        tma_load_2d(&tm, &full[s], kt + TILE, kc + 512, r);
+                    } else {               // tail: 4-row boxes, at most 3 rows fetched beyond the sequence
+                        const int n4 = (left + 3) >> 2;
+                        mbar_expect_tx(&full[s], n4 * 2 * 1024);
+                        for (int j = 0; j < n4; ++j) {
+                            tma_load_2d(&tm4, &full[s], kt + j * 1024, kc, r + 4 * j);
+                            tma_load_2d(&tm4, &full[s], kt + TILE + j * 1024, kc + 512, r + 4 * j);
+                        }
+                    }
                 }
             }
         }
         return;
     }
-    // ---------------------------------------------------------------- consumers: warp 1 -> head 2*hp, warp 2 -> head 2*hp+1
-    const int hd = warp - 1;
+    // ---------------------------------------------------------------- consumers
+    const int w = warp - 1, hd = w / WPH, part = w % WPH;
     const int kg = lane >> 3, dg = lane & 7;
-    int it = 0;
-    // header of the first unit
+    constexpr int ITER = 4 / WPH;          // key groups of 4 per warp per stage
+    int it = 0, parity = 0;
     uint4 q_raw = make_uint4(0, 0, 0, 0), kn_raw = make_uint4(0, 0, 0, 0), vn_raw = make_uint4(0, 0, 0, 0);
     auto load_header = [&](int u) {
         const int b = u >> 2, h = (u & 3) * 2 + hd;
         q_raw = *reinterpret_cast<const uint4*>(a.q + (size_t)b * a.ldq + h * 64 + dg * 8);
-        if (SELF) {
+        if (SELF && part == 0) {
             kn_raw = *reinterpret_cast<const uint4*>(a.knew + (size_t)b * a.ldnew + h * 64 + dg * 8);
             vn_raw = *reinterpret_cast<const uint4*>(a.vnew + (size_t)b * a.ldnew + h * 64 + dg * 8);
         }
     };
     if ((int)blockIdx.x < units) load_header(blockIdx.x);
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = blockIdx.x; u < units; u += gridDim.x, parity ^= 1) {
         const int b = u >> 2, h = (u & 3) * 2 + hd;
-        float q8[8], kn8[8], vn8[8];
+        float q8[8];
         unpack8(q_raw, q8);
         const uint4 kn_keep = kn_raw, vn_keep = vn_raw;
-        if (SELF) { unpack8(kn_raw, kn8); unpack8(vn_raw, vn8); }
         const int un = u + gridDim.x;
         if (un < units) load_header(un);          // prefetch the next unit's q / new k,v while this one streams
         int nk;
@@ -137,10 +154,12 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
             mbar_wait(&full[s], ph);
             const uint8_t* kt = ring + s * STAGE + hd * 128 + dg * 16;
             const uint8_t* vt = kt + TILE;
-            float sc[CH / 4];
+            float sc[ITER];
+            bool ok[ITER];
 #pragma unroll
-            for (int i = 0; i < CH / 4; ++i) {
-                const int kl = kg + 4 * i;
+            for (int i = 0; i < ITER; ++i) {
+                const int kl = kg + 4 * (i * WPH + part);
+                ok[i] = c * CH + kl < nk;
                 float k8[8];
                 unpack8(*reinterpret_cast<const uint4*>(kt + kl * 256), k8);
                 float d = 0.f;
@@ -149,33 +168,71 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
                 d += __shfl_xor_sync(0xffffffffu, d, 1);
                 d += __shfl_xor_sync(0xffffffffu, d, 2);
                 d += __shfl_xor_sync(0xffffffffu, d, 4);
-                sc[i] = (c * CH + kl < nk) ? d * SCALE : -INFINITY;
+                sc[i] = ok[i] ? d * SCALE : -INFINITY;       // rows past the sequence may hold anything (even NaN): never used
             }
             float cm = sc[0];
 #pragma unroll
-            for (int i = 1; i < CH / 4; ++i) cm = fmaxf(cm, sc[i]);
+            for (int i = 1; i < ITER; ++i) cm = fmaxf(cm, sc[i]);
             cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
             cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
-            const float mn = fmaxf(m, cm);          // finite: every chunk holds at least one valid key
-            const float corr = __expf(m - mn);
-            l *= corr;
+            const float mn = fmaxf(m, cm);
+            if (mn != -INFINITY) {                            // this warp's share of a tail stage may be empty
+                const float corr = __expf(m - mn);
+                l *= corr;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] *= corr;
+                for (int e = 0; e < 8; ++e) acc[e] *= corr;
 #pragma unroll
-            for (int i = 0; i < CH / 4; ++i) {
-                const float p = __expf(sc[i] - mn);
-                l += p;
-                float v8[8];
-                unpack8(*reinterpret_cast<const uint4*>(vt + (kg + 4 * i) * 256), v8);
+                for (int i = 0; i < ITER; ++i) {
+                    if (ok[i]) {
+                        const float p = __expf(sc[i] - mn);
+                        l += p;
+                        float v8[8];
+                        unpack8(*reinterpret_cast<const uint4*>(vt + (kg + 4 * (i * WPH + part)) * 256), v8);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, v8[e], acc[e]);
+                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, v8[e], acc[e]);
+                    }
+                }
+                m = mn;
             }
-            m = mn;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
+        // fold the 4 key groups of this warp
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+        }
+        if (WPH > 1) {
+            float* slot = scratch + ((((parity * 2 + hd) * WPH + part) * 8 + dg) * 10);
+            if (part != 0 && kg == 0) {
+                slot[0] = m; slot[1] = l;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) slot[2 + e] = acc[e];
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + hd), "r"(32 * WPH) : "memory");
+            if (part != 0) continue;
+#pragma unroll
+            for (int p2 = 1; p2 < WPH; ++p2) {
+                const float* o2 = scratch + ((((parity * 2 + hd) * WPH + p2) * 8 + dg) * 10);
+                const float m2 = o2[0];
+                const float mn = fmaxf(m, m2);
+                if (mn != -INFINITY) {
+                    const float c1 = __expf(m - mn), c2 = __expf(m2 - mn);
+                    l = l * c1 + o2[1] * c2;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] = acc[e] * c1 + o2[2 + e] * c2;
+                    m = mn;
+                }
+            }
+        }
         if (SELF) {
-            // this step's own key / value: score on every lane, accumulated by key group 0 only
+            // this step's own key / value (from the QKV GEMM output); also appended to the cache for the next steps
+            float kn8[8], vn8[8];
+            unpack8(kn_keep, kn8);
+            unpack8(vn_keep, vn8);
             float d = 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) d = fmaf(q8[e], kn8[e], d);
@@ -184,24 +241,15 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
             d += __shfl_xor_sync(0xffffffffu, d, 4);
             d *= SCALE;
             const float mn = fmaxf(m, d);
-            const float corr = __expf(m - mn);
-            const float p = (kg == 0) ? __expf(d - mn) : 0.f;
+            const float corr = __expf(m - mn), p = __expf(d - mn);
             l = l * corr + p;
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vn8[e], acc[e] * corr);
-            m = mn;
-            if (kg == 0) {      // append to the cache (row t of sequence b): K at column h*64, V at 512 + h*64
+            if (kg == 0) {      // row t of sequence b: K at column h*64, V at 512 + h*64
                 bf16* row = a.cache + ((size_t)b * a.tcap + t) * 1024 + h * 64 + dg * 8;
                 *reinterpret_cast<uint4*>(row) = kn_keep;
                 *reinterpret_cast<uint4*>(row + 512) = vn_keep;
             }
-        }
-        l += __shfl_xor_sync(0xffffffffu, l, 8);
-        l += __shfl_xor_sync(0xffffffffu, l, 16);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
         }
         if (kg == 0) {
             const float inv = 1.0f / l;
@@ -225,15 +273,17 @@ bool attn_decode_tma_supported(const AttnDecodeArgs& a) {
 // map_rows: number of rows of the K/V matrix the tensor map covers (self: B*tcap of this layer; cross: total tokens);
 // map_base: its first row (column 0); col0: column of head 0's K inside a row (cross: layer*1024).
 cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base, long map_rows, int map_cols, int col0, int tcap,
-                                   int num_sms, cudaStream_t st) {
+                                   int max_ctas, cudaStream_t st) {
     if (a.batch <= 0) return cudaSuccess;
-    CUtensorMap tm;
+    CUtensorMap tm, tm4;
     cudaError_t e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, CH, 128, 0, &tm);
     if (e != cudaSuccess) return e;
-    const size_t smem = (size_t)NS * STAGE + 128 + 2 * NS * 8 + 64;
+    if ((e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, 4, 128, 0, &tm4)) != cudaSuccess) return e;
+    constexpr int WPH = 2;
+    const size_t smem = (size_t)NS * STAGE + 128 + 2 * NS * 8 + 2 * 2 * WPH * 8 * 10 * 4 + 64;
     if (!g_smem_set) {
-        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<true, WPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<false, WPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         g_smem_set = 1;
     }
     Args k{};
@@ -241,7 +291,8 @@ cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base
     k.cache = (bf16*)a.kcache; k.tcap = tcap; k.k_off = a.k_off; k.step = a.step; k.o = (bf16*)a.o; k.ldo = a.ldo;
     k.batch = a.batch; k.col0 = col0;
     const int units = a.batch * 4;
-    const int grid = units < num_sms * 3 ? units : num_sms * 3;
-    if (a.knew) return launch_pdl(attn_decode_tma_kernel<true>, dim3(grid), dim3(96), smem, st, tm, k);
-    return launch_pdl(attn_decode_tma_kernel<false>, dim3(grid), dim3(96), smem, st, tm, k);
+    const int grid = units < max_ctas ? units : max_ctas;
+    const dim3 block(32 * (1 + 2 * WPH));
+    if (a.knew) return launch_pdl(attn_decode_tma_kernel<true, WPH>, dim3(grid), block, smem, st, tm, tm4, k);
+    return launch_pdl(attn_decode_tma_kernel<false, WPH>, dim3(grid), block, smem, st, tm, tm4, k);
 }

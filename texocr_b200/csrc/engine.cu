@@ -66,6 +66,14 @@ static cudaEvent_t get_event(texocr_handle* h) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------ memory helpers
+static void drop_graphs(texocr_handle* h) {
+    for (int i = 0; i < 8; ++i) {
+        if (h->bgraph_exec[i]) { cudaGraphExecDestroy(h->bgraph_exec[i]); h->bgraph_exec[i] = nullptr; }
+        if (h->bgraph[i]) { cudaGraphDestroy(h->bgraph[i]); h->bgraph[i] = nullptr; }
+    }
+    h->graph_exec = nullptr; h->graph = nullptr;
+}
+
 static int ensure(texocr_handle* h, DevBuf& b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return 0;
     if (b.p) { CK(cudaDeviceSynchronize()); CK(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
@@ -73,8 +81,7 @@ static int ensure(texocr_handle* h, DevBuf& b, size_t bytes) {
     want = (want + 255) & ~(size_t)255;
     CK(cudaMalloc(&b.p, want));
     b.bytes = want;
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // pointers may have moved
-    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+    drop_graphs(h);      // pointers may have moved
     return 0;
 }
 #define ENSURE(buf, bytes) do { int r__ = ensure(h, (buf), (bytes)); if (r__) return r__; } while (0)
@@ -344,6 +351,7 @@ static int finalize_weights(texocr_handle* h) {
 // ------------------------------------------------------------------------------------------------ GEMM dispatch
 // tcgen05 path for bf16 operands when the shape fits its tiles, FFMA path otherwise (and always in the fp32 tier).
 static cudaError_t run_gemm(texocr_handle* h, const GemmArgs& g, cudaStream_t st) {
+    if ((h->dbg_skip & 8) && g.M <= 512) return cudaSuccess;
     if (h->use_tcgen05 && g.dt_a == DT_BF16 && !g.conv && tc_gemm_supported(g)) return launch_gemm_tc(g, st);
     return launch_gemm_simt(g, st);
 }
@@ -632,6 +640,7 @@ static int sub_mlp(texocr_handle* h, const RowCtx& rc, const MlpW& w, cudaStream
 // x = LN(s); xn = LN(x)  (shared LayerNorm twice, model/attention.py:242-259), or the stack's final norm.
 static int sub_norm(texocr_handle* h, const RowCtx& rc, bool last, const float* fin_g, const float* fin_b, float* fin_out_f,
                     void* fin_out_a, cudaStream_t st) {
+    if ((h->dbg_skip & 4) && rc.kc_row == KC_DEC_ROW) return 0;
     Ln2Args a{};
     a.in = rowf(h->s, rc, 256); a.rows = rc.rows; a.dt_a = h->dt;
     if (!last) { a.g1 = rc.ln_g; a.b1 = rc.ln_b; a.g2 = rc.ln_g; a.b2 = rc.ln_b; a.o1f = rowf(h->x, rc, 256); a.o2a = rowa(h, h->xn, rc, 256); }
@@ -776,9 +785,10 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
         ad.q = qb; ad.ldq = 1536; ad.knew = qb + 512 * e; ad.vnew = qb + 1024 * e; ad.ldnew = 1536;
         ad.kcache = kv; ad.vcache = kv + 512 * e; ad.ldkv = 1024; ad.batch_stride = (int64_t)tcap * 1024;
         ad.step = step; ad.o = rowa(h, h->o, rc, 512); ad.ldo = 512; ad.batch = rows; ad.dt = h->dt;
-        if (h->use_tma_attn && attn_decode_tma_supported(ad))
+        if (h->dbg_skip & 1) {}
+        else if (h->use_tma_attn && attn_decode_tma_supported(ad))
             LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512,
-                   launch_attn_decode_tma(ad, kv, (long)rows * tcap, 1024, 0, tcap, h->num_sms, st));
+                   launch_attn_decode_tma(ad, kv, (long)rows * tcap, 1024, 0, tcap, h->num_sms * h->attn_ctas_per_sm, st));
         else
             LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512, launch_attn_decode(ad, tcap, st));
         if ((r = sub_attn_out(h, rc, h->dec_self[l], st))) return r;
@@ -790,9 +800,10 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
         char* ckv = (char*)h->crosskv.p + (size_t)l * 1024 * e;
         ac.q = qb; ac.ldq = 512; ac.kcache = ckv; ac.vcache = ckv + 512 * e; ac.ldkv = L * 1024;
         ac.k_off = d_enc_off + row0; ac.o = rowa(h, h->o, rc, 512); ac.ldo = 512; ac.batch = rows; ac.dt = h->dt;
-        if (h->use_tma_attn && attn_decode_tma_supported(ac))
+        if (h->dbg_skip & 2) {}
+        else if (h->use_tma_attn && attn_decode_tma_supported(ac))
             LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512,
-                   launch_attn_decode_tma(ac, h->crosskv.p, (long)h->crosskv_rows, L * 1024, l * 1024, 0, h->num_sms, st));
+                   launch_attn_decode_tma(ac, h->crosskv.p, (long)h->crosskv_rows, L * 1024, l * 1024, 0, h->num_sms * h->attn_ctas_per_sm, st));
         else
             LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512, launch_attn_decode(ac, max_s, st));
         if ((r = sub_attn_out(h, rc, h->dec_cross[l], st))) return r;
@@ -864,62 +875,86 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     CK(cudaMemsetAsync((char*)h->dec_state.p + (size_t)B * 8, 0, dec_state_bytes(B) - (size_t)B * 8, st));
     CK(cudaMemcpyAsync(ds.cur_tok, d_start, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
     const BranchPlan bp = plan_branches(h, B);
-    for (int i = 1; i < bp.n; ++i) {
+    for (int i = 0; i < bp.n; ++i) {
         if (!h->branch_stream[i]) {
             CK(cudaStreamCreateWithFlags(&h->branch_stream[i], cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
         }
     }
+    h->own_stream2 = h->branch_stream[0];
     if (!h->fork_ev) CK(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
 
     const bool graph_ok = h->use_graph && !h->prof_on;
+    // Stream of branch i: its own non-blocking stream (branch 0 included when there are several branches), so the
+    // branches run as independent, phase-shifted pipelines that only meet again at the end of the call.
+    cudaStream_t bst[MAX_BRANCH];
+    for (int i = 0; i < bp.n; ++i) bst[i] = (bp.n == 1 || !graph_ok) ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
     if (graph_ok) {
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
                          h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
-            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-            if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+            drop_graphs(h);
             const int64_t before = h->launches;
-            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-            r = enqueue_all_branches(h, bp, true, B, tcap, eos, d_enc_off, max_s, sum_s, -1, st);
-            cudaError_t ce = cudaStreamEndCapture(st, &h->graph);
-            if (r) return r;
-            CK(ce);
-            CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
-            h->gkey.kernels = (int)(h->launches - before);
+            for (int i = 0; i < bp.n; ++i) {
+                CK(cudaStreamBeginCapture(bst[i], cudaStreamCaptureModeRelaxed));
+                r = enqueue_decode_step(h, B, bp.row0[i], bp.rows[i], i, tcap, eos, d_enc_off, max_s, sum_s, -1, bst[i]);
+                cudaError_t ce = cudaStreamEndCapture(bst[i], &h->bgraph[i]);
+                if (r) return r;
+                CK(ce);
+                CK(cudaGraphInstantiate(&h->bgraph_exec[i], h->bgraph[i], 0));
+            }
+            h->graph = h->bgraph[0]; h->graph_exec = h->bgraph_exec[0];
+            h->gkey.kernels = (int)(h->launches - before) / bp.n;
             h->launches = before;        // capture does not execute
             h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
             h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv.p; h->gkey.x = h->x.p;
         }
+        if (bp.n > 1) {      // fork: every branch stream waits for the work already queued on st, then starts with its phase shift
+            CK(cudaEventRecord(h->fork_ev, st));
+            for (int i = 0; i < bp.n; ++i) {
+                CK(cudaStreamWaitEvent(bst[i], h->fork_ev, 0));
+                if (i > 0 && h->stagger_us > 0) CK(launch_delay((long)i * h->stagger_us * 1000L, bst[i]));
+            }
+        }
     }
+    for (int s2 = 0; s2 < 2; ++s2)
+        for (int i = 0; i < bp.n; ++i)
+            if (!h->poll_ev[s2][i]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][i], cudaEventDisableTiming));
     // Host runs ahead of the device by at most 2*POLL steps; an early exit costs at most that many extra steps.
     const int POLL = 16;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
     int issued = 0, polls = 0;
     bool stop = false;
     for (int t = 0; t < max_len && !stop; ++t) {
-        if (graph_ok) { CK(cudaGraphLaunch(h->graph_exec, st)); h->launches += h->gkey.kernels; }
-        else if ((r = enqueue_all_branches(h, bp, false, B, tcap, eos, d_enc_off, max_s, sum_s, t, st))) return r;
+        if (graph_ok) {
+            for (int i = 0; i < bp.n; ++i) { CK(cudaGraphLaunch(h->bgraph_exec[i], bst[i])); h->launches += h->gkey.kernels; }
+        } else if ((r = enqueue_all_branches(h, bp, false, B, tcap, eos, d_enc_off, max_s, sum_s, t, st))) return r;
         ++issued;
         if (eos >= 0 && issued % POLL == 0 && t + 1 < max_len) {
             const int slot = polls & 1;
-            if (polls >= 1) {      // wait for the PREVIOUS poll (issued POLL steps ago), keeps the queue non-empty
-                CK(cudaEventSynchronize(ev[slot ^ 1]));
+            if (polls >= 1) {      // wait for the PREVIOUS poll (issued POLL steps ago), keeps the queues non-empty
                 bool all = true;
-                for (int i = 0; i < bp.n; ++i) all = all && h->h_poll[(slot ^ 1) * MAX_BRANCH + i] > 0;
+                for (int i = 0; i < bp.n; ++i) {
+                    CK(cudaEventSynchronize(h->poll_ev[slot ^ 1][i]));
+                    all = all && h->h_poll[(slot ^ 1) * MAX_BRANCH + i] > 0;
+                }
                 if (all) stop = true;
             }
-            CK(cudaMemcpyAsync(&h->h_poll[slot * MAX_BRANCH], ds.done_step, MAX_BRANCH * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(ev[slot], st));
+            for (int i = 0; i < bp.n; ++i) {
+                CK(cudaMemcpyAsync(&h->h_poll[slot * MAX_BRANCH + i], ds.done_step + i, 4, cudaMemcpyDeviceToHost, bst[i]));
+                CK(cudaEventRecord(h->poll_ev[slot][i], bst[i]));
+            }
             ++polls;
+        }
+    }
+    if (graph_ok && bp.n > 1) {      // join
+        for (int i = 0; i < bp.n; ++i) {
+            CK(cudaEventRecord(h->join_ev[i], bst[i]));
+            CK(cudaStreamWaitEvent(st, h->join_ev[i], 0));
         }
     }
     CK(cudaMemcpyAsync(&h->h_poll[2 * MAX_BRANCH], ds.done_step, MAX_BRANCH * 4, cudaMemcpyDeviceToHost, st));
     if ((r = from_device(h, out_ids, h->out_ids.p, (size_t)B * tcap * 8, st))) return r;
     CK(cudaStreamSynchronize(st));
-    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
     // every row holds an EOS once every branch has seen one in all of its rows: the LAST branch to finish decides
     int done = 0;
     bool all_done = true;
@@ -972,8 +1007,8 @@ void texocr_destroy(texocr_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
-    if (h->graph) cudaGraphDestroy(h->graph);
+    drop_graphs(h);
+    for (int s2 = 0; s2 < 2; ++s2) for (int i = 0; i < 8; ++i) if (h->poll_ev[s2][i]) cudaEventDestroy(h->poll_ev[s2][i]);
     for (void* p : h->weight_allocs) cudaFree(p);
     DevBuf* bufs[] = {&h->geom, &h->img_stage, &h->raw1, &h->act2, &h->actA, &h->actB, &h->rawMid, &h->actMid, &h->rawMid2, &h->actMid2,
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
@@ -1229,14 +1264,17 @@ int texocr_profile_read(texocr_handle* h, texocr_profile_row* rows, int32_t cap)
 int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
+    if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(3, value)); drop_graphs(h); return 0; }
+    if (!strcmp(name, "dbg_skip")) { h->dbg_skip = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "pdl")) {
         g_texocr_pdl = value != 0;
-        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        drop_graphs(h);
         return 0;
     }
     if (!strcmp(name, "tma_attention")) {
         h->use_tma_attn = value != 0;
-        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        drop_graphs(h);
         return 0;
     }
     if (!strcmp(name, "decode_branches")) {
@@ -1246,7 +1284,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     }
     if (!strcmp(name, "tcgen05")) {
         h->use_tcgen05 = value != 0;
-        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        drop_graphs(h);
         return 0;
     }
     return fail(h, TEXOCR_ERR_ARG, "unknown option '%s'", name);

@@ -68,7 +68,7 @@ struct texocr_handle {
     DevBuf geom;                               // int32: img_off[B+1] | img_hw[2B] | tok_off[B+1] | row_off[B+1]
     int* h_geom = nullptr; size_t h_geom_cap = 0;   // pinned staging for geom
     cudaEvent_t geom_ev = nullptr, hop_in = nullptr, hop_out = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaStream_t branch_stream[8] = {nullptr}; cudaEvent_t join_ev[8] = {nullptr}; cudaEvent_t fork_ev = nullptr;
     int decode_branches = 0;                   // 0 = automatic (4 for B >= 256, 2 for B >= 64)
     DevBuf img_stage;                          // device copy of host images
@@ -86,7 +86,10 @@ struct texocr_handle {
 
     // ---- decode-step CUDA graph
     bool use_graph = true;
-    cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;        // branch 0 (kept under these names)
+    cudaGraph_t bgraph[8] = {nullptr}; cudaGraphExec_t bgraph_exec[8] = {nullptr};   // one single-step graph per branch
+    cudaEvent_t poll_ev[2][8] = {{nullptr}};
+    int stagger_us = 60;                        // start offset between consecutive branches
     struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; } gkey;
 
     // ---- instrumentation
@@ -98,5 +101,7 @@ struct texocr_handle {
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
     bool use_tma_attn = true;
+    int dbg_skip = 0;        // timing experiments only: 1 self-attn, 2 cross-attn, 4 LayerNorms, 8 GEMMs (results are garbage)
     int num_sms = 148;
+    int attn_ctas_per_sm = 2;     // persistent decode-attention CTAs per SM (64 KB ring each); leaves room for the GEMM CTAs of other branches
 };

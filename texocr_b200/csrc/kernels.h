@@ -107,6 +107,8 @@ struct ArgmaxArgs {
 cudaError_t launch_argmax_step(const ArgmaxArgs& a, cudaStream_t st);
 cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_t rows, int V, float* row_loss,
                                  float* loss, cudaStream_t st);
+// busy-wait for `ns` nanoseconds on the stream (used to phase-shift the concurrent decode branches)
+cudaError_t launch_delay(long ns, cudaStream_t st);
 cudaError_t launch_cast_f32_to(const float* in, void* out, int64_t n, int dt, cudaStream_t st);
 
 // ---- attention (attention.cu)
@@ -140,4 +142,4 @@ cudaError_t launch_attn_decode(const AttnDecodeArgs& a, int nk_cap, cudaStream_t
 // head 0's K inside a row; tcap = cache rows per sequence (self-attention).
 bool attn_decode_tma_supported(const AttnDecodeArgs& a);
 cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base, long map_rows, int map_cols, int col0, int tcap,
-                                   int num_sms, cudaStream_t st);
+                                   int max_ctas, cudaStream_t st);

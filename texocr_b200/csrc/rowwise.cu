@@ -146,6 +146,15 @@ __global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ v,
     if (threadIdx.x == 0) *out = (float)(sh[0] / (double)n);
 }
 
+__global__ void delay_kernel(long ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(500);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while ((long)(t1 - t0) < ns);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, T* __restrict__ out, long n4) {
     const long i = (long)blockIdx.x * 256 + threadIdx.x;
@@ -182,6 +191,12 @@ cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     mean_kernel<<<1, 1024, 0, st>>>(row_loss, (long)rows, loss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_delay(long ns, cudaStream_t st) {
+    if (ns <= 0) return cudaSuccess;
+    delay_kernel<<<1, 1, 0, st>>>(ns);
     return cudaGetLastError();
 }
 
