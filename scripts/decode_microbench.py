@@ -49,3 +49,11 @@ for skip, label in ((3, "no attention"), (12, "attention only")):
     eng.set_option("dbg_skip", skip)
     decode_us(f"branches=1 {label}")
 eng.set_option("dbg_skip", 0)
+eng.set_option("decode_branches", 0)
+eng.set_option("stagger_us", 60)
+for pdl in (0x3f, 0x3f | 512, 0x3f | 768, 0x3f | 256, 0):
+    eng.set_option("pdl", pdl)
+    decode_us(f"pdl mask {pdl:#x} (auto branches)")
+    eng.set_option("decode_branches", 1)
+    decode_us(f"pdl mask {pdl:#x} (1 branch)")
+    eng.set_option("decode_branches", 0)

@@ -1,0 +1,67 @@
+"""GPU tier: the decode-step attention kernels (persistent TMA + mma.sync kernel, simple per-sequence kernel) against a
+plain PyTorch fp32 reference of the same op: softmax(q.K^T * 0.125).V over the cached keys (+ this step's key)."""
+import pytest
+import torch
+
+from texocr_b200 import spec, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(sd):
+    import texocr_b200
+    cfg = spec.default_config()
+    cfg["device"] = "cuda:0"
+    m = texocr_b200.create_model(cfg, precision="bf16")
+    m.load_state_dict(sd)
+    return m.engine()
+
+
+def _ref(q, K, V):
+    """q [8,64]; K, V [n, 8, 64] (fp32) -> [512]"""
+    s = torch.einsum("hd,nhd->hn", q, K) * 0.125
+    return torch.einsum("hn,nhd->hd", torch.softmax(s, dim=-1), V).reshape(-1)
+
+
+@pytest.mark.parametrize("use_tma", [True, False])
+@pytest.mark.parametrize("B", [37, 300])
+@pytest.mark.parametrize("t", [0, 1, 3, 4, 5, 12, 15, 16, 17, 31, 33, 100, 255])
+def test_self_attention_decode(eng, t, use_tma, B):
+    tcap = 256
+    g = torch.Generator(device="cuda").manual_seed(t + 1)
+    cache = torch.randn(B * tcap, 1024, device="cuda", generator=g).to(torch.bfloat16)
+    cache.view(B, tcap, 1024)[:, t:] = float("nan")           # rows not yet written must never matter
+    qkv = torch.randn(B, 1536, device="cuda", generator=g).to(torch.bfloat16)
+    step = torch.tensor([t], dtype=torch.int32, device="cuda")
+    out = eng.debug_attn_decode(True, qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:], cache, 0, tcap, None, step, B, tcap, use_tma)
+    torch.cuda.synchronize()
+    c = cache.view(B, tcap, 1024).float()
+    assert torch.equal(cache.view(B, tcap, 1024)[:, t], qkv[:, 512:])          # appended row
+    for b in range(B):
+        K = c[b, : t + 1, :512].reshape(t + 1, 8, 64)
+        V = c[b, : t + 1, 512:].reshape(t + 1, 8, 64)
+        ref = _ref(qkv[b, :512].float().reshape(8, 64), K, V)
+        err = (out[b].float() - ref).abs().max() / ref.abs().max()
+        assert torch.isfinite(out[b].float()).all() and err < 2e-2, (b, float(err))
+    out2 = eng.debug_attn_decode(True, qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:], cache, 0, tcap, None, step, B, tcap, use_tma)
+    assert torch.equal(out, out2)            # run-to-run reproducible
+
+
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_cross_attention_decode_ragged(eng, use_tma):
+    lens = [17, 97, 100, 253, 1, 16, 33, 631, 97, 97, 64] * 14
+    B, L = len(lens), 4
+    off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    ntok = int(off[-1])
+    g = torch.Generator(device="cuda").manual_seed(7)
+    kv = torch.randn(ntok, L * 1024, device="cuda", generator=g).to(torch.bfloat16)
+    q = torch.randn(B, 512, device="cuda", generator=g).to(torch.bfloat16)
+    for layer in (0, 3):
+        out = eng.debug_attn_decode(False, q, None, None, kv, layer * 1024, 0, off, None, B, max(lens), use_tma)
+        torch.cuda.synchronize()
+        for b in range(B):
+            rows = kv[int(off[b]):int(off[b + 1]), layer * 1024:(layer + 1) * 1024].float()
+            ref = _ref(q[b].float().reshape(8, 64), rows[:, :512].reshape(-1, 8, 64), rows[:, 512:].reshape(-1, 8, 64))
+            err = (out[b].float() - ref).abs().max() / ref.abs().max()
+            assert err < 2e-2, (layer, b, lens[b], float(err))

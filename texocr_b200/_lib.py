@@ -23,7 +23,7 @@ EXPORTS = (
     "texocr_create", "texocr_destroy", "texocr_last_error", "texocr_set_weight", "texocr_finalize_weights",
     "texocr_encode", "texocr_decoder_logits", "texocr_decoder_generate", "texocr_generate", "texocr_cross_entropy",
     "texocr_kernel_launches", "texocr_profile_enable", "texocr_profile_read", "texocr_set_option", "texocr_debug_read",
-    "texocr_debug_gemm",
+    "texocr_debug_gemm", "texocr_debug_attn_decode",
 )
 
 
@@ -72,6 +72,7 @@ def load_library() -> C.CDLL:
     lib.texocr_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
     lib.texocr_debug_read.restype = i64
     lib.texocr_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]
+    lib.texocr_debug_attn_decode.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i64, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib
@@ -236,6 +237,16 @@ class Engine:
                                                C.stride(0), epi, dt_a, dt_c, ptr(bias), ptr(res), 0 if res is None else res.stride(0),
                                                1 if use_tc else 0, ptr(A2), ptr(W2), self._stream()))
         return C
+
+    def debug_attn_decode(self, self_attn, q, knew, vnew, kv, col0, tcap, k_off, step, batch, max_keys, use_tma):
+        """Test hook: one decode-attention launch; returns bf16 [batch, 512]."""
+        out = torch.zeros((batch, 512), dtype=torch.bfloat16, device=self.device)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self._check(self.lib.texocr_debug_attn_decode(
+            self.h, 1 if self_attn else 0, q.data_ptr(), q.stride(0), ptr(knew), ptr(vnew), 0 if knew is None else knew.stride(0),
+            kv.data_ptr(), kv.shape[0], kv.stride(0), col0, tcap, ptr(k_off), ptr(step), out.data_ptr(), batch, max_keys,
+            1 if use_tma else 0, self._stream()))
+        return out
 
     def debug_read(self, name: str, numel: int) -> torch.Tensor:
         out = torch.empty(numel, dtype=torch.float32, device=self.device)

@@ -245,6 +245,6 @@ cudaError_t launch_attn_decode(const AttnDecodeArgs& a, int nk_cap, cudaStream_t
         if (e != cudaSuccess) return e;
         g_decode_smem_set[ti] = (int)smem;
     }
-    if (a.dt == DT_F32) return launch_pdl(attn_decode_kernel<float>, dim3(a.batch), dim3(256), smem, st, a, nk_cap);
-    return launch_pdl(attn_decode_kernel<bf16>, dim3(a.batch), dim3(256), smem, st, a, nk_cap);
+    if (a.dt == DT_F32) return launch_pdl(PDL_ATTN_SIMPLE, attn_decode_kernel<float>, dim3(a.batch), dim3(256), smem, st, a, nk_cap);
+    return launch_pdl(PDL_ATTN_SIMPLE, attn_decode_kernel<bf16>, dim3(a.batch), dim3(256), smem, st, a, nk_cap);
 }

@@ -1,11 +1,14 @@
 // Decode-step attention for the bf16 tier: a persistent, TMA-fed streaming kernel (the HBM-bound kernel of the generate loop).
 //
 // Work unit = (sequence b, head pair hp): 2 heads x nk keys x (K 128 B + V 128 B).  Units are dealt round-robin to
-// persistent CTAs (3 per SM).  Each CTA has one producer thread that issues 2-D TMA loads (box = 16 keys x 128 columns,
-// K and V tiles of the head pair) into an 8-stage shared-memory ring, running ahead across unit boundaries so the memory
-// pipe never drains, and two consumer warps (one per head) that do the online-softmax attention from shared memory:
-// lane = (key group of 4, 8-dim slice) -> 16-byte conflict-free smem reads, 3 shuffles per 4 keys.
-// Self-attention also folds in this step's own key/value (from the QKV GEMM output) and appends it to the cache.
+// persistent CTAs.  Each CTA has one producer thread that issues 2-D TMA loads (box = 16 keys x 64 columns, 128-byte
+// swizzle; K and V tiles of both heads) into an 8-stage shared-memory ring, running ahead across unit boundaries so the
+// memory pipe never drains, and two consumer warps (one per head) that run the flash-decoding inner loop on the legacy
+// tensor-core path: S = q.K^T and O += P.V as mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with the single query in row 0
+// of the 16-row A operand, operands fetched with ldmatrix from the swizzled tiles, online softmax in fp32 on 4 lanes.
+// (A SIMT inner loop needs ~7x the instructions per byte and is issue/latency-bound at ~70 % of HBM speed; tcgen05 is
+// pointless for a 1-row problem.)  Self-attention also folds in this step's own key/value (from the QKV GEMM output)
+// and appends it to the cache.
 //
 // Reference semantics: model/attention.py:148-173 with q length 1 (energy * 0.125, softmax, . v); no masks are active in
 // generate (model/decoder.py:95: mask all True; causal over a prefix == attend to everything cached).
@@ -16,7 +19,7 @@ namespace {
 
 constexpr int CH = 16;            // keys per stage
 constexpr int NS = 8;             // ring stages
-constexpr int TILE = CH * 256;    // bytes of one K (or V) tile: CH keys x 2 heads x 64 x bf16
+constexpr int TILE = CH * 256;    // bytes of the K (or V) tiles of one stage: CH keys x 2 heads x 64 x bf16
 constexpr int STAGE = 2 * TILE;
 constexpr float SCALE = 0.125f;
 
@@ -56,30 +59,44 @@ TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-TX_DEVINL void unpack8(const uint4& r, float* o) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+TX_DEVINL void ldsm_x4(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, uint32_t& d3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(addr));
 }
+TX_DEVINL void ldsm_x4_t(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, uint32_t& d3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(addr));
+}
+TX_DEVINL void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+TX_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+TX_DEVINL float2 unpack_bf16x2(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w)); }
 
-// WPH = consumer warps per head: the 16 keys of a stage are dealt to them in groups of 4, each keeps its own online-softmax
-// state and the partial states are merged once per unit (more independent dependency chains per SM: the per-warp chain
-// LDS -> FMA -> 3 shuffles -> max -> exp -> FMA is latency-bound).
-template <bool SELF, int WPH>
-__global__ void __launch_bounds__(32 * (1 + 2 * WPH)) attn_decode_tma_kernel(const __grid_constant__ CUtensorMap tm,
-                                                                           const __grid_constant__ CUtensorMap tm4, const Args a) {
+// Stage layout: [K head0 | K head1 | V head0 | V head1], each a 16 x 64 bf16 tile (2 KB) in the TMA 128B-swizzle layout:
+// element (row r, 16-byte chunk c) lives at r*128 + ((c ^ (r & 7)) << 4).
+constexpr int HTILE = CH * 128;
+
+template <bool SELF>
+__global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_constant__ CUtensorMap tm,
+                                                             const __grid_constant__ CUtensorMap tm4, const Args a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + NS * STAGE);
     uint64_t* empty = full + NS;
-    float* scratch = reinterpret_cast<float*>(empty + NS);          // [2 parity][2 heads][WPH][8 dg][10]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     pdl_launch_dependents();
+    // Rows fetched past the end of a sequence are masked (p = 0) but still enter the P.V MMA: make sure no stale NaN/Inf bit
+    // pattern can sit in a partially filled stage (0 * NaN = NaN).  Global over-fetch reads zero-initialised / finite rows.
+    for (int i = threadIdx.x; i < NS * STAGE / 16; i += blockDim.x) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm4) : "memory");
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2 * WPH); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -101,19 +118,23 @@ __global__ void __launch_bounds__(32 * (1 + 2 * WPH)) attn_decode_tma_kernel(con
                 for (int c = 0; c < nchunk; ++c, ++it) {
                     const int s = it % NS, ph = (it / NS) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* kt = ring + s * STAGE;
+                    uint8_t* st = ring + s * STAGE;
                     const int left = nk - c * CH;
                     const int kc = a.col0 + hp * 128, r = row0 + c * CH;
                     if (left >= CH) {
                         mbar_expect_tx(&full[s], STAGE);
-                        tma_load_2d(&tm, &full[s], kt, kc, r);
-                        tma_load_2d(&tm, &full[s], kt + TILE, kc + 512, r);
+                        tma_load_2d(&tm, &full[s], st, kc, r);
+                        tma_load_2d(&tm, &full[s], st + HTILE, kc + 64, r);
+                        tma_load_2d(&tm, &full[s], st + 2 * HTILE, kc + 512, r);
+                        tma_load_2d(&tm, &full[s], st + 3 * HTILE, kc + 576, r);
                     } else {               // tail: 4-row boxes, at most 3 rows fetched beyond the sequence
                         const int n4 = (left + 3) >> 2;
-                        mbar_expect_tx(&full[s], n4 * 2 * 1024);
+                        mbar_expect_tx(&full[s], n4 * 4 * 512);
                         for (int j = 0; j < n4; ++j) {
-                            tma_load_2d(&tm4, &full[s], kt + j * 1024, kc, r + 4 * j);
-                            tma_load_2d(&tm4, &full[s], kt + TILE + j * 1024, kc + 512, r + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + j * 512, kc, r + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + HTILE + j * 512, kc + 64, r + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + 2 * HTILE + j * 512, kc + 512, r + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + 3 * HTILE + j * 512, kc + 576, r + 4 * j);
                         }
                     }
                 }
@@ -121,141 +142,150 @@ __global__ void __launch_bounds__(32 * (1 + 2 * WPH)) attn_decode_tma_kernel(con
         }
         return;
     }
-    // ---------------------------------------------------------------- consumers
-    const int w = warp - 1, hd = w / WPH, part = w % WPH;
-    const int kg = lane >> 3, dg = lane & 7;
-    constexpr int ITER = 4 / WPH;          // key groups of 4 per warp per stage
-    int it = 0, parity = 0;
-    uint4 q_raw = make_uint4(0, 0, 0, 0), kn_raw = make_uint4(0, 0, 0, 0), vn_raw = make_uint4(0, 0, 0, 0);
+    // ---------------------------------------------------------------- consumers: warp 1 -> head 2*hp, warp 2 -> head 2*hp+1
+    const int hd = warp - 1;
+    const int g = lane >> 2, tq = lane & 3;             // mma fragment coordinates: row group / thread-in-group
+    const bool row0_lane = g == 0;                       // the single query lives in row 0 of the 16-row A operand
+    // ldmatrix address pieces (thread i supplies row i&7 of matrix i>>3)
+    const int lm_r = lane & 7, lm_m = lane >> 3;
+    int it = 0;
+    // header: q, this step's k and v for (b, head); lanes 0..3 hold the words of their fragment positions
+    uint32_t q_w[8], kn_w[8], vn_w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { q_w[i] = 0; kn_w[i] = 0; vn_w[i] = 0; }
     auto load_header = [&](int u) {
         const int b = u >> 2, h = (u & 3) * 2 + hd;
-        q_raw = *reinterpret_cast<const uint4*>(a.q + (size_t)b * a.ldq + h * 64 + dg * 8);
-        if (SELF && part == 0) {
-            kn_raw = *reinterpret_cast<const uint4*>(a.knew + (size_t)b * a.ldnew + h * 64 + dg * 8);
-            vn_raw = *reinterpret_cast<const uint4*>(a.vnew + (size_t)b * a.ldnew + h * 64 + dg * 8);
+        if (row0_lane) {
+            const uint32_t* qp = reinterpret_cast<const uint32_t*>(a.q + (size_t)b * a.ldq + h * 64);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { q_w[2 * s] = qp[8 * s + tq]; q_w[2 * s + 1] = qp[8 * s + 4 + tq]; }   // dims 16s+2t, 16s+8+2t
+            if (SELF) {
+                const uint32_t* kp = reinterpret_cast<const uint32_t*>(a.knew + (size_t)b * a.ldnew + h * 64);
+                const uint32_t* vp = reinterpret_cast<const uint32_t*>(a.vnew + (size_t)b * a.ldnew + h * 64);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) { kn_w[2 * s] = kp[8 * s + tq]; kn_w[2 * s + 1] = kp[8 * s + 4 + tq]; }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) vn_w[nt] = vp[4 * nt + tq];                                       // dims 8nt+2t, +1
+            }
         }
     };
     if ((int)blockIdx.x < units) load_header(blockIdx.x);
-    for (int u = blockIdx.x; u < units; u += gridDim.x, parity ^= 1) {
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int b = u >> 2, h = (u & 3) * 2 + hd;
-        float q8[8];
-        unpack8(q_raw, q8);
-        const uint4 kn_keep = kn_raw, vn_keep = vn_raw;
+        // A fragments of q (scaled by 0.125, exact in bf16): a0 = (row g, k 2t..), a2 = (row g, k 2t+8..); rows 8..15 zero
+        uint32_t qa[8];
+        float kn_f[16], vn_f[16], q_f[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 f = unpack_bf16x2(q_w[i]);
+            q_f[2 * i] = f.x * SCALE; q_f[2 * i + 1] = f.y * SCALE;
+            qa[i] = row0_lane ? pack_bf16x2(q_f[2 * i], q_f[2 * i + 1]) : 0u;
+            if (SELF) {
+                const float2 kf = unpack_bf16x2(kn_w[i]), vf = unpack_bf16x2(vn_w[i]);
+                kn_f[2 * i] = kf.x; kn_f[2 * i + 1] = kf.y; vn_f[2 * i] = vf.x; vn_f[2 * i + 1] = vf.y;
+            }
+        }
+        if (SELF && lane < 8) {      // append this step's k / v row to the cache (16 B per lane), K at h*64, V at 512 + h*64
+            const uint4 kr = *reinterpret_cast<const uint4*>(a.knew + (size_t)b * a.ldnew + h * 64 + lane * 8);
+            const uint4 vr = *reinterpret_cast<const uint4*>(a.vnew + (size_t)b * a.ldnew + h * 64 + lane * 8);
+            bf16* row = a.cache + ((size_t)b * a.tcap + t) * 1024 + h * 64 + lane * 8;
+            *reinterpret_cast<uint4*>(row) = kr;
+            *reinterpret_cast<uint4*>(row + 512) = vr;
+        }
         const int un = u + gridDim.x;
-        if (un < units) load_header(un);          // prefetch the next unit's q / new k,v while this one streams
+        if (un < units) load_header(un);          // prefetch the next unit's header while this one streams
         int nk;
         if (SELF) nk = t; else nk = a.k_off[b + 1] - a.k_off[b];
         const int nchunk = (nk + CH - 1) / CH;
-        float m = -INFINITY, l = 0.f, acc[8];
+        float m = -INFINITY, l = 0.f;
+        float o[8][4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
         for (int c = 0; c < nchunk; ++c, ++it) {
             const int s = it % NS, ph = (it / NS) & 1;
             mbar_wait(&full[s], ph);
-            const uint8_t* kt = ring + s * STAGE + hd * 128 + dg * 16;
-            const uint8_t* vt = kt + TILE;
-            float sc[ITER];
-            bool ok[ITER];
+            const uint32_t kt = smem_u32(ring + s * STAGE + hd * HTILE);
+            const uint32_t vt = kt + 2 * HTILE;
+            // ---- S = q.K^T : 2 n-tiles of 8 keys, 4 k-steps of 16 dims
+            float sc[2][4];
 #pragma unroll
-            for (int i = 0; i < ITER; ++i) {
-                const int kl = kg + 4 * (i * WPH + part);
-                ok[i] = c * CH + kl < nk;
-                float k8[8];
-                unpack8(*reinterpret_cast<const uint4*>(kt + kl * 256), k8);
-                float d = 0.f;
+            for (int j = 0; j < 2; ++j) {
+                sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+                const int r = 8 * j + lm_r;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) d = fmaf(q8[e], k8[e], d);
-                d += __shfl_xor_sync(0xffffffffu, d, 1);
-                d += __shfl_xor_sync(0xffffffffu, d, 2);
-                d += __shfl_xor_sync(0xffffffffu, d, 4);
-                sc[i] = ok[i] ? d * SCALE : -INFINITY;       // rows past the sequence may hold anything (even NaN): never used
-            }
-            float cm = sc[0];
-#pragma unroll
-            for (int i = 1; i < ITER; ++i) cm = fmaxf(cm, sc[i]);
-            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
-            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
-            const float mn = fmaxf(m, cm);
-            if (mn != -INFINITY) {                            // this warp's share of a tail stage may be empty
-                const float corr = __expf(m - mn);
-                l *= corr;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] *= corr;
-#pragma unroll
-                for (int i = 0; i < ITER; ++i) {
-                    if (ok[i]) {
-                        const float p = __expf(sc[i] - mn);
-                        l += p;
-                        float v8[8];
-                        unpack8(*reinterpret_cast<const uint4*>(vt + (kg + 4 * (i * WPH + part)) * 256), v8);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, v8[e], acc[e]);
-                    }
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(kt + r * 128 + (((4 * s2 + lm_m) ^ (r & 7)) << 4), b0, b1, b2, b3);
+                    mma_bf16(sc[j], qa[4 * s2], 0u, qa[4 * s2 + 1], 0u, b0, b1);
+                    mma_bf16(sc[j], qa[4 * s2 + 2], 0u, qa[4 * s2 + 3], 0u, b2, b3);
                 }
-                m = mn;
+            }
+            // row 0 scores: lane tq holds keys 8j+2tq, 8j+2tq+1
+            const int kbase = c * CH + 2 * tq;
+            float p[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                p[j][0] = (kbase + 8 * j < nk) ? sc[j][0] : -INFINITY;
+                p[j][1] = (kbase + 8 * j + 1 < nk) ? sc[j][1] : -INFINITY;
+            }
+            float cm = fmaxf(fmaxf(p[0][0], p[0][1]), fmaxf(p[1][0], p[1][1]));
+            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+            const float mn = fmaxf(m, cm);                 // finite on row 0: every stage holds at least one valid key
+            const float corr = __expf(m - mn);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { p[j][0] = __expf(p[j][0] - mn); p[j][1] = __expf(p[j][1] - mn); }
+            l = l * corr + (p[0][0] + p[0][1]) + (p[1][0] + p[1][1]);
+            m = mn;
+            const uint32_t pa0 = row0_lane ? pack_bf16x2(p[0][0], p[0][1]) : 0u;     // keys 2t, 2t+1
+            const uint32_t pa2 = row0_lane ? pack_bf16x2(p[1][0], p[1][1]) : 0u;     // keys 8+2t, 9+2t
+            // ---- O = O*corr + P.V : 8 n-tiles of 8 dims, one k-step of 16 keys
+            const int vr = (lane & 7) + 8 * ((lane >> 3) & 1);
+            // V rows past the end of the sequence were fetched (<= 3 of them) or are stale: they carry p = 0, but 0 * NaN = NaN,
+            // so their halves of the B fragments (keys 2t, 2t+1 | 2t+8, 2t+9) are cleared in the last, partial stage.
+            uint32_t vm_lo = 0xffffffffu, vm_hi = 0xffffffffu;
+            if (nk - c * CH < CH) {
+                const int k0 = c * CH + 2 * tq;
+                vm_lo = (k0 < nk ? 0x0000ffffu : 0u) | (k0 + 1 < nk ? 0xffff0000u : 0u);
+                vm_hi = (k0 + 8 < nk ? 0x0000ffffu : 0u) | (k0 + 9 < nk ? 0xffff0000u : 0u);
+            }
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(vt + vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4), b0, b1, b2, b3);
+                b0 &= vm_lo; b2 &= vm_lo; b1 &= vm_hi; b3 &= vm_hi;
+                o[2 * np][0] *= corr; o[2 * np][1] *= corr;
+                o[2 * np + 1][0] *= corr; o[2 * np + 1][1] *= corr;
+                mma_bf16(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
+                mma_bf16(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
-        // fold the 4 key groups of this warp
-        l += __shfl_xor_sync(0xffffffffu, l, 8);
-        l += __shfl_xor_sync(0xffffffffu, l, 16);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-        }
-        if (WPH > 1) {
-            float* slot = scratch + ((((parity * 2 + hd) * WPH + part) * 8 + dg) * 10);
-            if (part != 0 && kg == 0) {
-                slot[0] = m; slot[1] = l;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) slot[2 + e] = acc[e];
-            }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + hd), "r"(32 * WPH) : "memory");
-            if (part != 0) continue;
-#pragma unroll
-            for (int p2 = 1; p2 < WPH; ++p2) {
-                const float* o2 = scratch + ((((parity * 2 + hd) * WPH + p2) * 8 + dg) * 10);
-                const float m2 = o2[0];
-                const float mn = fmaxf(m, m2);
-                if (mn != -INFINITY) {
-                    const float c1 = __expf(m - mn), c2 = __expf(m2 - mn);
-                    l = l * c1 + o2[1] * c2;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] = acc[e] * c1 + o2[2 + e] * c2;
-                    m = mn;
-                }
-            }
-        }
         if (SELF) {
-            // this step's own key / value (from the QKV GEMM output); also appended to the cache for the next steps
-            float kn8[8], vn8[8];
-            unpack8(kn_keep, kn8);
-            unpack8(vn_keep, vn8);
+            // this step's own key / value: dot over the lane's 16 dims, folded over the 4 lanes of row 0
             float d = 0.f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) d = fmaf(q8[e], kn8[e], d);
+            for (int i = 0; i < 16; ++i) d = fmaf(q_f[i], kn_f[i], d);
             d += __shfl_xor_sync(0xffffffffu, d, 1);
             d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            d *= SCALE;
             const float mn = fmaxf(m, d);
-            const float corr = __expf(m - mn), p = __expf(d - mn);
-            l = l * corr + p;
+            const float corr = __expf(m - mn), pn = __expf(d - mn);
+            l = l * corr;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vn8[e], acc[e] * corr);
-            if (kg == 0) {      // row t of sequence b: K at column h*64, V at 512 + h*64
-                bf16* row = a.cache + ((size_t)b * a.tcap + t) * 1024 + h * 64 + dg * 8;
-                *reinterpret_cast<uint4*>(row) = kn_keep;
-                *reinterpret_cast<uint4*>(row + 512) = vn_keep;
+            for (int nt = 0; nt < 8; ++nt) {
+                o[nt][0] = fmaf(pn, vn_f[2 * nt], o[nt][0] * corr);
+                o[nt][1] = fmaf(pn, vn_f[2 * nt + 1], o[nt][1] * corr);
             }
+            l += (tq == 0) ? pn : 0.f;         // l is a per-lane partial, summed over the 4 lanes below
         }
-        if (kg == 0) {
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        if (row0_lane) {
             const float inv = 1.0f / l;
-            bf16* o = a.o + (size_t)b * a.ldo + h * 64 + dg * 8;
-            st4(o, make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv));
-            st4(o + 4, make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv));
+            uint32_t* op = reinterpret_cast<uint32_t*>(a.o + (size_t)b * a.ldo + h * 64);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) op[4 * nt + tq] = pack_bf16x2(o[nt][0] * inv, o[nt][1] * inv);
         }
     }
 }
@@ -276,14 +306,13 @@ cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base
                                    int max_ctas, cudaStream_t st) {
     if (a.batch <= 0) return cudaSuccess;
     CUtensorMap tm, tm4;
-    cudaError_t e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, CH, 128, 0, &tm);
+    cudaError_t e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, CH, 64, 1, &tm);
     if (e != cudaSuccess) return e;
-    if ((e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, 4, 128, 0, &tm4)) != cudaSuccess) return e;
-    constexpr int WPH = 2;
-    const size_t smem = (size_t)NS * STAGE + 128 + 2 * NS * 8 + 2 * 2 * WPH * 8 * 10 * 4 + 64;
+    if ((e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, 4, 64, 1, &tm4)) != cudaSuccess) return e;
+    const size_t smem = (size_t)NS * STAGE + 1024 + 2 * NS * 8 + 64;
     if (!g_smem_set) {
-        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<true, WPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<false, WPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         g_smem_set = 1;
     }
     Args k{};
@@ -292,7 +321,6 @@ cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base
     k.batch = a.batch; k.col0 = col0;
     const int units = a.batch * 4;
     const int grid = units < max_ctas ? units : max_ctas;
-    const dim3 block(32 * (1 + 2 * WPH));
-    if (a.knew) return launch_pdl(attn_decode_tma_kernel<true, WPH>, dim3(grid), block, smem, st, tm, tm4, k);
-    return launch_pdl(attn_decode_tma_kernel<false, WPH>, dim3(grid), block, smem, st, tm, tm4, k);
+    if (a.knew) return launch_pdl(PDL_ATTN_TMA, attn_decode_tma_kernel<true>, dim3(grid), dim3(96), smem, st, tm, tm4, k);
+    return launch_pdl(PDL_ATTN_TMA, attn_decode_tma_kernel<false>, dim3(grid), dim3(96), smem, st, tm, tm4, k);
 }

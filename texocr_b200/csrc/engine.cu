@@ -21,7 +21,11 @@
 #include "tc_gemm.h"
 
 static std::string g_create_error;
-int g_texocr_pdl = 1;
+// bits 0..5: programmatic dependent launch per kernel family (kernels.h); bit 8 / 9: LayerNorm / GEMM kernels release their
+// dependents only after their stores.  The GEMM kernel triggers late by default: with an early trigger the following
+// LayerNorm and the GEMM after it start while this GEMM is still running, and that three-deep overlap produced rare
+// run-to-run differences on B200 (1 row in ~10 calls at B=512; scripts/determinism_check.py) at < 2 % speed gain.
+int g_texocr_pdl = 0x23f;
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -80,6 +84,8 @@ static int ensure(texocr_handle* h, DevBuf& b, size_t bytes) {
     size_t want = std::max(bytes, (size_t)256);
     want = (want + 255) & ~(size_t)255;
     CK(cudaMalloc(&b.p, want));
+    CK(cudaMemset(b.p, 0, want));        // fresh workspaces start zeroed (no NaN bit patterns in never-written KV rows)
+    CK(cudaDeviceSynchronize());         // the memset runs on the legacy stream; our streams are non-blocking
     b.bytes = want;
     drop_graphs(h);      // pointers may have moved
     return 0;
@@ -118,6 +124,17 @@ static int upload_ints(texocr_handle* h, const std::vector<int>& v, cudaStream_t
     ENSURE(h->geom, bytes);
     CK(cudaMemcpyAsync(h->geom.p, h->h_geom, bytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(h->geom_ev, st));
+    return 0;
+}
+
+// Debug aid: fill every workspace with 0xFF bytes (NaN patterns) so that any read of memory the current call did not write
+// shows up in the results.  Enabled with texocr_set_option(h, "poison", 1).
+static int poison_workspaces(texocr_handle* h, cudaStream_t st) {
+    DevBuf* bufs[] = {&h->raw1, &h->act2, &h->actA, &h->actB, &h->rawMid, &h->actMid, &h->rawMid2, &h->actMid2, &h->raw3, &h->rawDs,
+                      &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3], &h->proj_out, &h->patch_cols,
+                      &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits, &h->enc_out, &h->enc_a,
+                      &h->crosskv, &h->kvcache, &h->out_ids};
+    for (DevBuf* b : bufs) if (b->p) CK(cudaMemsetAsync(b->p, 0xFF, b->bytes, st));
     return 0;
 }
 
@@ -1199,6 +1216,7 @@ int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, in
     if (!images || !hw || !out_ids || !n_steps) return fail(h, TEXOCR_ERR_ARG, "null argument");
     EncGeom g;
     int r;
+    if (h->poison && (r = poison_workspaces(h, st))) return r;
     if ((r = plan_geometry(h, hw, batch, g, st))) return r;
     const void* d_img = nullptr;
     if ((r = to_device(h, images, (size_t)total_pixels(hw, batch) * 4, h->img_stage, &d_img, st))) return r;
@@ -1265,10 +1283,11 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "poison")) { h->poison = value != 0; return 0; }
     if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(3, value)); drop_graphs(h); return 0; }
     if (!strcmp(name, "dbg_skip")) { h->dbg_skip = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "pdl")) {
-        g_texocr_pdl = value != 0;
+        g_texocr_pdl = (int)value;
         drop_graphs(h);
         return 0;
     }
@@ -1320,6 +1339,34 @@ int texocr_debug_gemm(texocr_handle* h, const void* A, const void* W, void* C, i
         LAUNCH(KC_MISC, 1, gemm_bytes(g, 2), gemm_flops(g), launch_gemm_tc(g, st));
     } else {
         LAUNCH(KC_MISC, 1, gemm_bytes(g, dt_a == DT_BF16 ? 2 : 4), gemm_flops(g), launch_gemm_simt(g, st));
+    }
+    return 0;
+}
+
+int texocr_debug_attn_decode(texocr_handle* h, int32_t self, const void* q, int32_t ldq, const void* knew, const void* vnew,
+                             int32_t ldnew, void* kv, int64_t kv_rows, int32_t ldkv, int32_t col0, int32_t tcap,
+                             const int32_t* k_off_dev, const int32_t* step_dev, void* out, int32_t batch, int32_t max_keys,
+                             int32_t use_tma, void* stream) {
+    if (!h) return TEXOCR_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    StreamHop hop__(h, stream);
+    cudaStream_t st = hop__.work;
+    AttnDecodeArgs a{};
+    char* base = (char*)kv;
+    a.q = q; a.ldq = ldq; a.o = out; a.ldo = 512; a.batch = batch; a.dt = DT_BF16; a.ldkv = ldkv;
+    if (self) {
+        a.knew = knew; a.vnew = vnew; a.ldnew = ldnew; a.kcache = base; a.vcache = base + 512 * 2;
+        a.batch_stride = (int64_t)tcap * ldkv; a.step = step_dev;
+    } else {
+        a.kcache = base + (size_t)col0 * 2; a.vcache = base + (size_t)(col0 + 512) * 2; a.k_off = k_off_dev;
+    }
+    if (use_tma) {
+        if (!attn_decode_tma_supported(a)) return fail(h, TEXOCR_ERR_ARG, "not supported by the TMA attention kernel");
+        if (!self) a.kcache = base;
+        LAUNCH(KC_MISC, 1, 0.0, 0.0, launch_attn_decode_tma(a, kv, kv_rows, self ? 1024 : ldkv, self ? 0 : col0, tcap,
+                                                              h->num_sms * h->attn_ctas_per_sm, st));
+    } else {
+        LAUNCH(KC_MISC, 1, 0.0, 0.0, launch_attn_decode(a, max_keys, st));
     }
     return 0;
 }

@@ -101,7 +101,8 @@ struct texocr_handle {
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
     bool use_tma_attn = true;
+    bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate
     int dbg_skip = 0;        // timing experiments only: 1 self-attn, 2 cross-attn, 4 LayerNorms, 8 GEMMs (results are garbage)
     int num_sms = 148;
-    int attn_ctas_per_sm = 2;     // persistent decode-attention CTAs per SM (64 KB ring each); leaves room for the GEMM CTAs of other branches
+    int attn_ctas_per_sm = 3;     // persistent decode-attention CTAs per SM (64 KB ring each); leaves room for the GEMM CTAs of other branches
 };

@@ -7,16 +7,18 @@
 enum { DT_F32 = 0, DT_BF16 = 1 };
 
 // Launch with programmatic dependent launch enabled (kernels call pdl_wait() before reading their inputs).
-extern int g_texocr_pdl;      // 1 = launch decode-path kernels with programmatic dependent launch (engine.cu)
+// Programmatic dependent launch per kernel family: bit k of g_texocr_pdl enables it for family k (engine.cu).
+enum { PDL_GEMM = 0, PDL_LN = 1, PDL_EMBED = 2, PDL_ARGMAX = 3, PDL_ATTN_TMA = 4, PDL_ATTN_SIMPLE = 5 };
+extern int g_texocr_pdl;
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(int family, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = g_texocr_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = ((g_texocr_pdl >> family) & 1) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 #endif
@@ -87,6 +89,7 @@ struct Ln2Args {
     float* o1f; void* o1a;                 // x1 as fp32 and/or as activation type (nullable)
     void* o2a;                             // x2 as activation type (nullable)
     int dt_a;
+    int late_trigger;                      // PDL: release the dependent kernel after the stores instead of at entry
 };
 cudaError_t launch_ln2(const Ln2Args& a, cudaStream_t st);
 // x[b] = tok_emb[id[b]] + pos_emb[pos]; xn = LN(x).  Decode step: ids = cur_tok [B], pos = *step.

@@ -33,10 +33,10 @@ template <typename T> TX_DEVINL void store8(T* p, const float* v) {
 
 template <typename TAct>
 __global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
-    pdl_launch_dependents();
+    if (!a.late_trigger) pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
-    if (row >= a.rows) return;
+    if (row >= a.rows) { if (a.late_trigger) pdl_launch_dependents(); return; }
     float v[8];
     ld8(a.in + (size_t)row * D + col, v);
     if (a.g1) layer_norm8(v, a.g1, a.b1, col);
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
         layer_norm8(v, a.g2, a.b2, col);
         if (a.o2a) store8(reinterpret_cast<TAct*>(a.o2a) + (size_t)row * D + col, v);
     }
+    if (a.late_trigger) pdl_launch_dependents();
 }
 
 template <typename TAct>
@@ -163,11 +164,13 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 
 }  // namespace
 
-cudaError_t launch_ln2(const Ln2Args& a, cudaStream_t st) {
+cudaError_t launch_ln2(const Ln2Args& a_in, cudaStream_t st) {
+    Ln2Args a = a_in;
+    a.late_trigger = (g_texocr_pdl >> 8) & 1;
     if (a.rows <= 0) return cudaSuccess;
     const int blocks = (a.rows + 7) / 8;
-    if (a.dt_a == DT_F32) return launch_pdl(ln2_kernel<float>, dim3(blocks), dim3(256), 0, st, a);
-    return launch_pdl(ln2_kernel<bf16>, dim3(blocks), dim3(256), 0, st, a);
+    if (a.dt_a == DT_F32) return launch_pdl(PDL_LN, ln2_kernel<float>, dim3(blocks), dim3(256), 0, st, a);
+    return launch_pdl(PDL_LN, ln2_kernel<bf16>, dim3(blocks), dim3(256), 0, st, a);
 }
 
 cudaError_t launch_embed_ln(const int64_t* ids, const int* step, int T, int rows, const float* tok_emb,
@@ -176,12 +179,12 @@ cudaError_t launch_embed_ln(const int64_t* ids, const int* step, int T, int rows
     if (rows <= 0) return cudaSuccess;
     const int blocks = (rows + 7) / 8;
     if (dt_a == DT_F32)
-        return launch_pdl(embed_ln_kernel<float>, dim3(blocks), dim3(256), 0, st, ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (float*)xn);
-    return launch_pdl(embed_ln_kernel<bf16>, dim3(blocks), dim3(256), 0, st, ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (bf16*)xn);
+        return launch_pdl(PDL_EMBED, embed_ln_kernel<float>, dim3(blocks), dim3(256), 0, st, ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (float*)xn);
+    return launch_pdl(PDL_EMBED, embed_ln_kernel<bf16>, dim3(blocks), dim3(256), 0, st, ids, step, T, rows, tok_emb, pos_emb, vocab, g, b, x, (bf16*)xn);
 }
 
 cudaError_t launch_argmax_step(const ArgmaxArgs& a, cudaStream_t st) {
-    return launch_pdl(argmax_step_kernel, dim3((a.B + 7) / 8), dim3(256), 0, st, a);
+    return launch_pdl(PDL_ARGMAX, argmax_step_kernel, dim3((a.B + 7) / 8), dim3(256), 0, st, a);
 }
 
 cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_t rows, int V, float* row_loss,

@@ -27,6 +27,7 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 struct TcParams {
     void* C; int M, N, K, ldc;
     const float* bias; const float* res; int ldres;
+    int late_trigger;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -118,7 +119,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int nkb = p.K / BK;
 
-    pdl_launch_dependents();
+    if (!p.late_trigger) pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -242,6 +243,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (p.late_trigger) pdl_launch_dependents();
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
@@ -312,7 +314,7 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
         attr_set = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    return launch_pdl(kern, grid, dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
+    return launch_pdl(PDL_GEMM, kern, grid, dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
 }
 
 template <int BN, int SPLIT>
@@ -350,7 +352,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
     const bool split = g.A2 != nullptr;
     if (split) bn = g.N <= 64 ? 64 : 128;
-    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres};
+    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1};
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
     if ((e = get_map(g.A, g.M, g.K, g.lda, BM, &a)) != cudaSuccess) return e;
