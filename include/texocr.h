@@ -140,9 +140,10 @@ TEXOCR_API int texocr_debug_gemm(texocr_handle* h, const void* A, const void* W,
                       int32_t lda, int32_t ldw, int32_t ldc, int32_t epi, int32_t dt_a, int32_t dt_c, const float* bias,
                       const float* res, int32_t ldres, int32_t use_tc, const void* A2, const void* W2, void* stream);
 
-/* Test hook: one decode-attention launch (bf16).  self != 0: q/knew/vnew are [batch, ld] rows (head h at h*64), kv is the
- * [batch*tcap, 1024] cache (K | V), *step_dev keys already cached; the kernel appends row step.  self == 0: kv is a packed
- * [rows, ldkv] matrix, k_off_dev[batch+1] gives each sequence's row range, col0 the column of head 0's K.
+/* Test hook: one decode-attention launch (bf16) on the engine's head-major K/V layout (rows of 128 = K 64 | V 64).
+ * self != 0: q/knew/vnew are [batch, ld] rows (head h at h*64), kv is the cache [batch][8 heads][tcap][128] (kv_rows =
+ * batch*8*tcap), *step_dev keys already cached; the kernel appends key `step`.  self == 0: kv is [8 heads][ntok][128]
+ * (kv_rows = 8*ntok), k_off_dev[batch+1] gives each sequence's token range.  ldkv / col0 are ignored.
  * use_tma selects the persistent TMA kernel, otherwise the simple per-sequence kernel.  out: bf16 [batch, 512]. */
 TEXOCR_API int texocr_debug_attn_decode(texocr_handle* h, int32_t self, const void* q, int32_t ldq, const void* knew, const void* vnew,
                              int32_t ldnew, void* kv, int64_t kv_rows, int32_t ldkv, int32_t col0, int32_t tcap,

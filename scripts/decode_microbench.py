@@ -37,23 +37,10 @@ def decode_us(label):
     print(f"{label}: generate(256) {t256:.1f} ms, generate(64) {t64:.1f} ms -> decode {(t256 - t64) / 192 * 1000:.0f} us/step (t in 64..256)")
 
 
-for cps in (3, 2):
+eng.set_option("fuse_ln", 0)
+for cps in (3, 4, 6):
     eng.set_option("attn_ctas_per_sm", cps)
-    for nb, stag in ((1, 0), (2, 100), (4, 0), (4, 50), (8, 25)):
+    for nb, stag in ((1, 0), (4, 0), (4, 60), (8, 30)):
         eng.set_option("decode_branches", nb)
         eng.set_option("stagger_us", stag)
-        decode_us(f"attn_ctas/sm={cps} branches={nb} stagger={stag}us")
-eng.set_option("decode_branches", 1)
-eng.set_option("attn_ctas_per_sm", 3)
-for skip, label in ((3, "no attention"), (12, "attention only")):
-    eng.set_option("dbg_skip", skip)
-    decode_us(f"branches=1 {label}")
-eng.set_option("dbg_skip", 0)
-eng.set_option("decode_branches", 0)
-eng.set_option("stagger_us", 60)
-for pdl in (0x3f, 0x3f | 512, 0x3f | 768, 0x3f | 256, 0):
-    eng.set_option("pdl", pdl)
-    decode_us(f"pdl mask {pdl:#x} (auto branches)")
-    eng.set_option("decode_branches", 1)
-    decode_us(f"pdl mask {pdl:#x} (1 branch)")
-    eng.set_option("decode_branches", 0)
+        decode_us(f"NS=4 attn_ctas/sm={cps} branches={nb} stagger={stag}us")

@@ -30,17 +30,18 @@ def _ref(q, K, V):
 def test_self_attention_decode(eng, t, use_tma, B):
     tcap = 256
     g = torch.Generator(device="cuda").manual_seed(t + 1)
-    cache = torch.randn(B * tcap, 1024, device="cuda", generator=g).to(torch.bfloat16)
-    cache.view(B, tcap, 1024)[:, t:] = float("nan")           # rows not yet written must never matter
+    cache = torch.randn(B * 8 * tcap, 128, device="cuda", generator=g).to(torch.bfloat16)     # [b][head][key][K 64 | V 64]
+    cache.view(B, 8, tcap, 128)[:, :, t:] = float("nan")      # rows not yet written must never matter
     qkv = torch.randn(B, 1536, device="cuda", generator=g).to(torch.bfloat16)
     step = torch.tensor([t], dtype=torch.int32, device="cuda")
     out = eng.debug_attn_decode(True, qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:], cache, 0, tcap, None, step, B, tcap, use_tma)
     torch.cuda.synchronize()
-    c = cache.view(B, tcap, 1024).float()
-    assert torch.equal(cache.view(B, tcap, 1024)[:, t], qkv[:, 512:])          # appended row
+    c = cache.view(B, 8, tcap, 128).float()
+    assert torch.equal(cache.view(B, 8, tcap, 128)[:, :, t, :64], qkv[:, 512:1024].view(B, 8, 64))     # appended key
+    assert torch.equal(cache.view(B, 8, tcap, 128)[:, :, t, 64:], qkv[:, 1024:].view(B, 8, 64))        # appended value
     for b in range(B):
-        K = c[b, : t + 1, :512].reshape(t + 1, 8, 64)
-        V = c[b, : t + 1, 512:].reshape(t + 1, 8, 64)
+        K = c[b, :, : t + 1, :64].permute(1, 0, 2)
+        V = c[b, :, : t + 1, 64:].permute(1, 0, 2)
         ref = _ref(qkv[b, :512].float().reshape(8, 64), K, V)
         err = (out[b].float() - ref).abs().max() / ref.abs().max()
         assert torch.isfinite(out[b].float()).all() and err < 2e-2, (b, float(err))
@@ -55,13 +56,15 @@ def test_cross_attention_decode_ragged(eng, use_tma):
     off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
     ntok = int(off[-1])
     g = torch.Generator(device="cuda").manual_seed(7)
-    kv = torch.randn(ntok, L * 1024, device="cuda", generator=g).to(torch.bfloat16)
+    kv_all = torch.randn(L, 8 * ntok, 128, device="cuda", generator=g).to(torch.bfloat16)    # [layer][head][token][K 64 | V 64]
     q = torch.randn(B, 512, device="cuda", generator=g).to(torch.bfloat16)
     for layer in (0, 3):
-        out = eng.debug_attn_decode(False, q, None, None, kv, layer * 1024, 0, off, None, B, max(lens), use_tma)
+        kv = kv_all[layer]
+        out = eng.debug_attn_decode(False, q, None, None, kv, 0, 0, off, None, B, max(lens), use_tma)
         torch.cuda.synchronize()
-        for b in range(B):
-            rows = kv[int(off[b]):int(off[b + 1]), layer * 1024:(layer + 1) * 1024].float()
-            ref = _ref(q[b].float().reshape(8, 64), rows[:, :512].reshape(-1, 8, 64), rows[:, 512:].reshape(-1, 8, 64))
+        kvf = kv.view(8, ntok, 128).float()
+        for b in range(0, B, 3):
+            rows = kvf[:, int(off[b]):int(off[b + 1])]
+            ref = _ref(q[b].float().reshape(8, 64), rows[:, :, :64].permute(1, 0, 2), rows[:, :, 64:].permute(1, 0, 2))
             err = (out[b].float() - ref).abs().max() / ref.abs().max()
             assert err < 2e-2, (layer, b, lens[b], float(err))

@@ -212,6 +212,18 @@ def test_tma_attention_matches_simple_kernel(m16):
     assert agree > 0.97, agree
 
 
+def test_layernorm_fused_gemm_is_bit_identical(m16):
+    """tc_gemm_ln_kernel computes the shared double LayerNorm with the arithmetic of ln2_kernel: same token ids."""
+    img = synth.synth_images(300, 64, 384, seed=31).cuda()
+    eng = m16.engine()
+    outs = []
+    for fuse in (1, 0):
+        eng.set_option("fuse_ln", fuse)
+        outs.append(m16.generate(img, 40))
+    eng.set_option("fuse_ln", 1)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_input_validation_raises(m32):
     with pytest.raises(RuntimeError, match="multiples of 16"):
         m32.generate(torch.zeros(1, 1, 60, 384, device="cuda"), 8)

@@ -151,8 +151,9 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnDecodeArgs a, int 
     int nk;
     if (a.knew) {     // self-attention: append this step's key / value at position t, then attend to 0..t
         const int t = *a.step;
-        T* kc = reinterpret_cast<T*>(a.kcache) + (size_t)b * a.batch_stride + h * HD;
-        T* vc = reinterpret_cast<T*>(a.vcache) + (size_t)b * a.batch_stride + h * HD;
+        const size_t hs = a.head_stride ? (size_t)a.head_stride : (size_t)HD;
+        T* kc = reinterpret_cast<T*>(a.kcache) + (size_t)b * a.batch_stride + h * hs;
+        T* vc = reinterpret_cast<T*>(a.vcache) + (size_t)b * a.batch_stride + h * hs;
         const T* kn = reinterpret_cast<const T*>(a.knew) + (size_t)b * a.ldnew + h * HD;
         const T* vn = reinterpret_cast<const T*>(a.vnew) + (size_t)b * a.ldnew + h * HD;
         kc[(size_t)t * a.ldkv + 2 * lane] = kn[2 * lane];
@@ -163,8 +164,9 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnDecodeArgs a, int 
     } else {
         const int off = a.k_off[b];
         nk = a.k_len ? a.k_len[b] : a.k_off[b + 1] - off;
-        kbase = reinterpret_cast<const T*>(a.kcache) + (size_t)off * a.ldkv + h * HD;
-        vbase = reinterpret_cast<const T*>(a.vcache) + (size_t)off * a.ldkv + h * HD;
+        const size_t hs = a.head_stride ? (size_t)a.head_stride : (size_t)HD;
+        kbase = reinterpret_cast<const T*>(a.kcache) + (size_t)off * a.ldkv + h * hs;
+        vbase = reinterpret_cast<const T*>(a.vcache) + (size_t)off * a.ldkv + h * hs;
     }
     s_q[h][2 * lane] = to_f(Q[2 * lane]);
     s_q[h][2 * lane + 1] = to_f(Q[2 * lane + 1]);
@@ -222,6 +224,33 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnDecodeArgs a, int 
 }
 
 }  // namespace
+
+template <typename T>
+__global__ void __launch_bounds__(256) crosskv_head_major_kernel(const T* __restrict__ in, T* __restrict__ out, int ntok, int layers) {
+    // one thread per 8 elements of the output: idx -> (l, h, tok, part K/V, chunk of 8)
+    const long idx = (long)blockIdx.x * 256 + threadIdx.x;
+    const long total = (long)layers * 8 * ntok * 16;
+    if (idx >= total) return;
+    const int chunk = (int)(idx & 7), part = (int)((idx >> 3) & 1);
+    long rest = idx >> 4;
+    const int tok = (int)(rest % ntok); rest /= ntok;
+    const int h = (int)(rest & 7), l = (int)(rest >> 3);
+    const T* src = in + ((size_t)tok * layers + l) * 1024 + part * 512 + h * 64 + chunk * 8;
+    T* dst = out + idx * 8;
+    float v[8];
+    ld8(src, v);
+    st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+    st4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+cudaError_t launch_crosskv_head_major(const void* in, void* out, int ntok, int layers, int dt, cudaStream_t st) {
+    const long total = (long)layers * 8 * ntok * 16;
+    if (total <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (dt == DT_F32) crosskv_head_major_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, (float*)out, ntok, layers);
+    else crosskv_head_major_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)in, (bf16*)out, ntok, layers);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_attn_varlen(const AttnVarlenArgs& a, cudaStream_t st) {
     if (a.batch <= 0 || a.max_q <= 0) return cudaSuccess;

@@ -15,10 +15,12 @@
 #include "common.cuh"
 #include "tc_gemm.h"
 
+int g_attn_full_tail = 0;
+
 namespace {
 
 constexpr int CH = 16;            // keys per stage
-constexpr int NS = 8;             // ring stages
+constexpr int NS = 4;             // ring stages (32 KB ring: several CTAs per SM and room for other kernels' CTAs)
 constexpr int TILE = CH * 256;    // bytes of the K (or V) tiles of one stage: CH keys x 2 heads x 64 x bf16
 constexpr int STAGE = 2 * TILE;
 constexpr float SCALE = 0.125f;
@@ -26,11 +28,13 @@ constexpr float SCALE = 0.125f;
 struct Args {
     const bf16* q; int ldq;
     const bf16* knew; const bf16* vnew; int ldnew;     // self only
-    bf16* cache; int tcap;                              // self: [B*tcap][1024] rows of this layer (append target)
+    bf16* cache;                                        // self: element (row 0, col 0) of the matrix the tensor map covers (append target)
     const int* k_off;                                   // cross: token offsets [B+1]
     const int* step;                                    // self: keys already cached
     bf16* o; int ldo;
-    int batch, col0;
+    int batch;
+    int ld, col0, col_h, v_col, row_h, row_b;           // KvLayout (kernels.h)
+    int full_tail;                                      // debug: fetch the last, partial stage with full 16-row boxes
 };
 
 TX_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,10 +93,8 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     pdl_launch_dependents();
-    // Rows fetched past the end of a sequence are masked (p = 0) but still enter the P.V MMA: make sure no stale NaN/Inf bit
-    // pattern can sit in a partially filled stage (0 * NaN = NaN).  Global over-fetch reads zero-initialised / finite rows.
-    for (int i = threadIdx.x; i < NS * STAGE / 16; i += blockDim.x) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // Rows past the end of a sequence (fetched by the last box or stale in a partially filled stage) may hold anything:
+    // their scores are replaced by -inf and their V fragments are cleared below, so the ring needs no initialisation.
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm4) : "memory");
@@ -103,38 +105,42 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
     pdl_wait();
 
     const int units = a.batch * 4;
-    const int t = SELF ? *a.step : 0;
+    const int t = SELF ? ldcg_i32(a.step) : 0;
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer
         if (lane == 0) {
             int it = 0;
+            asm volatile("fence.proxy.async.global;" ::: "memory");     // K/V rows were appended by generic-proxy stores of earlier kernels
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int b = u >> 2, hp = u & 3;
                 int row0, nk;
-                if (SELF) { row0 = b * a.tcap; nk = t; }
-                else { row0 = a.k_off[b]; nk = a.k_off[b + 1] - row0; }
+                if (SELF) { row0 = b * a.row_b; nk = t; }
+                else { row0 = ldcg_i32(a.k_off + b); nk = ldcg_i32(a.k_off + b + 1) - row0; }
                 const int nchunk = (nk + CH - 1) / CH;
+                const int h0 = 2 * hp, h1 = h0 + 1;
+                const int kc0 = a.col0 + h0 * a.col_h, kc1 = a.col0 + h1 * a.col_h;
+                const int r0 = row0 + h0 * a.row_h, r1 = row0 + h1 * a.row_h;
                 for (int c = 0; c < nchunk; ++c, ++it) {
                     const int s = it % NS, ph = (it / NS) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = ring + s * STAGE;
                     const int left = nk - c * CH;
-                    const int kc = a.col0 + hp * 128, r = row0 + c * CH;
-                    if (left >= CH) {
+                    const int rc = c * CH;
+                    if (left >= CH || (a.full_tail & 1)) {
                         mbar_expect_tx(&full[s], STAGE);
-                        tma_load_2d(&tm, &full[s], st, kc, r);
-                        tma_load_2d(&tm, &full[s], st + HTILE, kc + 64, r);
-                        tma_load_2d(&tm, &full[s], st + 2 * HTILE, kc + 512, r);
-                        tma_load_2d(&tm, &full[s], st + 3 * HTILE, kc + 576, r);
+                        tma_load_2d(&tm, &full[s], st, kc0, r0 + rc);
+                        tma_load_2d(&tm, &full[s], st + HTILE, kc1, r1 + rc);
+                        tma_load_2d(&tm, &full[s], st + 2 * HTILE, kc0 + a.v_col, r0 + rc);
+                        tma_load_2d(&tm, &full[s], st + 3 * HTILE, kc1 + a.v_col, r1 + rc);
                     } else {               // tail: 4-row boxes, at most 3 rows fetched beyond the sequence
                         const int n4 = (left + 3) >> 2;
                         mbar_expect_tx(&full[s], n4 * 4 * 512);
                         for (int j = 0; j < n4; ++j) {
-                            tma_load_2d(&tm4, &full[s], st + j * 512, kc, r + 4 * j);
-                            tma_load_2d(&tm4, &full[s], st + HTILE + j * 512, kc + 64, r + 4 * j);
-                            tma_load_2d(&tm4, &full[s], st + 2 * HTILE + j * 512, kc + 512, r + 4 * j);
-                            tma_load_2d(&tm4, &full[s], st + 3 * HTILE + j * 512, kc + 576, r + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + j * 512, kc0, r0 + rc + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + HTILE + j * 512, kc1, r1 + rc + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + 2 * HTILE + j * 512, kc0 + a.v_col, r0 + rc + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + 3 * HTILE + j * 512, kc1 + a.v_col, r1 + rc + 4 * j);
                         }
                     }
                 }
@@ -158,14 +164,14 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
         if (row0_lane) {
             const uint32_t* qp = reinterpret_cast<const uint32_t*>(a.q + (size_t)b * a.ldq + h * 64);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) { q_w[2 * s] = qp[8 * s + tq]; q_w[2 * s + 1] = qp[8 * s + 4 + tq]; }   // dims 16s+2t, 16s+8+2t
+            for (int s = 0; s < 4; ++s) { q_w[2 * s] = ldcg_u32(qp + 8 * s + tq); q_w[2 * s + 1] = ldcg_u32(qp + 8 * s + 4 + tq); }   // dims 16s+2t, 16s+8+2t
             if (SELF) {
                 const uint32_t* kp = reinterpret_cast<const uint32_t*>(a.knew + (size_t)b * a.ldnew + h * 64);
                 const uint32_t* vp = reinterpret_cast<const uint32_t*>(a.vnew + (size_t)b * a.ldnew + h * 64);
 #pragma unroll
-                for (int s = 0; s < 4; ++s) { kn_w[2 * s] = kp[8 * s + tq]; kn_w[2 * s + 1] = kp[8 * s + 4 + tq]; }
+                for (int s = 0; s < 4; ++s) { kn_w[2 * s] = ldcg_u32(kp + 8 * s + tq); kn_w[2 * s + 1] = ldcg_u32(kp + 8 * s + 4 + tq); }
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) vn_w[nt] = vp[4 * nt + tq];                                       // dims 8nt+2t, +1
+                for (int nt = 0; nt < 8; ++nt) vn_w[nt] = ldcg_u32(vp + 4 * nt + tq);                            // dims 8nt+2t, +1
             }
         }
     };
@@ -186,16 +192,18 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
             }
         }
         if (SELF && lane < 8) {      // append this step's k / v row to the cache (16 B per lane), K at h*64, V at 512 + h*64
-            const uint4 kr = *reinterpret_cast<const uint4*>(a.knew + (size_t)b * a.ldnew + h * 64 + lane * 8);
-            const uint4 vr = *reinterpret_cast<const uint4*>(a.vnew + (size_t)b * a.ldnew + h * 64 + lane * 8);
-            bf16* row = a.cache + ((size_t)b * a.tcap + t) * 1024 + h * 64 + lane * 8;
+            const uint4 kr = ldcg_u4(a.knew + (size_t)b * a.ldnew + h * 64 + lane * 8);
+            const uint4 vr = ldcg_u4(a.vnew + (size_t)b * a.ldnew + h * 64 + lane * 8);
+            bf16* row = a.cache + ((size_t)b * a.row_b + (size_t)h * a.row_h + t) * a.ld + a.col0 + h * a.col_h + lane * 8;
             *reinterpret_cast<uint4*>(row) = kr;
-            *reinterpret_cast<uint4*>(row + 512) = vr;
+            *reinterpret_cast<uint4*>(row + a.v_col) = vr;
+            // the next step reads this row through the async proxy (TMA): order the generic-proxy stores against it
+            asm volatile("fence.proxy.async.global;" ::: "memory");
         }
         const int un = u + gridDim.x;
         if (un < units) load_header(un);          // prefetch the next unit's header while this one streams
         int nk;
-        if (SELF) nk = t; else nk = a.k_off[b + 1] - a.k_off[b];
+        if (SELF) nk = t; else nk = ldcg_i32(a.k_off + b + 1) - ldcg_i32(a.k_off + b);
         const int nchunk = (nk + CH - 1) / CH;
         float m = -INFINITY, l = 0.f;
         float o[8][4];
@@ -204,6 +212,7 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
         for (int c = 0; c < nchunk; ++c, ++it) {
             const int s = it % NS, ph = (it / NS) & 1;
             mbar_wait(&full[s], ph);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             const uint32_t kt = smem_u32(ring + s * STAGE + hd * HTILE);
             const uint32_t vt = kt + 2 * HTILE;
             // ---- S = q.K^T : 2 n-tiles of 8 keys, 4 k-steps of 16 dims
@@ -259,6 +268,10 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
                 mma_bf16(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
                 mma_bf16(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
             }
+            // The stage is about to be handed back to the TMA producer: order this warp's generic-proxy reads (ldmatrix) before
+            // the async-proxy overwrite.  Without the cross-proxy fence the refill of a reused stage occasionally overtook the
+            // last V reads (1-3 % error in one head of one sequence, a few times per thousand launches under concurrency).
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
@@ -296,19 +309,16 @@ int g_smem_set = 0;
 
 bool attn_decode_tma_supported(const AttnDecodeArgs& a) {
     if (a.dt != DT_BF16 || a.ldkv % 8 != 0 || a.ldq % 8 != 0 || a.ldo % 8 != 0) return false;
-    if (a.knew && (a.ldkv != 1024 || a.ldnew % 8 != 0)) return false;
+    if (a.knew && a.ldnew % 8 != 0) return false;
     return true;
 }
 
-// map_rows: number of rows of the K/V matrix the tensor map covers (self: B*tcap of this layer; cross: total tokens);
-// map_base: its first row (column 0); col0: column of head 0's K inside a row (cross: layer*1024).
-cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base, long map_rows, int map_cols, int col0, int tcap,
-                                   int max_ctas, cudaStream_t st) {
+cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const KvLayout& lay, int max_ctas, cudaStream_t st) {
     if (a.batch <= 0) return cudaSuccess;
     CUtensorMap tm, tm4;
-    cudaError_t e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, CH, 64, 1, &tm);
+    cudaError_t e = tma_map_2d_bf16(lay.map_base, lay.map_rows, lay.map_cols, lay.ld, CH, 64, 1, &tm);
     if (e != cudaSuccess) return e;
-    if ((e = tma_map_2d_bf16(map_base, map_rows, map_cols, a.ldkv, 4, 64, 1, &tm4)) != cudaSuccess) return e;
+    if ((e = tma_map_2d_bf16(lay.map_base, lay.map_rows, lay.map_cols, lay.ld, 4, 64, 1, &tm4)) != cudaSuccess) return e;
     const size_t smem = (size_t)NS * STAGE + 1024 + 2 * NS * 8 + 64;
     if (!g_smem_set) {
         if ((e = cudaFuncSetAttribute(attn_decode_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -317,8 +327,9 @@ cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base
     }
     Args k{};
     k.q = (const bf16*)a.q; k.ldq = a.ldq; k.knew = (const bf16*)a.knew; k.vnew = (const bf16*)a.vnew; k.ldnew = a.ldnew;
-    k.cache = (bf16*)a.kcache; k.tcap = tcap; k.k_off = a.k_off; k.step = a.step; k.o = (bf16*)a.o; k.ldo = a.ldo;
-    k.batch = a.batch; k.col0 = col0;
+    k.cache = (bf16*)const_cast<void*>(lay.map_base); k.k_off = a.k_off; k.step = a.step; k.o = (bf16*)a.o; k.ldo = a.ldo;
+    k.full_tail = g_attn_full_tail;
+    k.batch = a.batch; k.ld = lay.ld; k.col0 = lay.col0; k.col_h = lay.col_h; k.v_col = lay.v_col; k.row_h = lay.row_h; k.row_b = lay.row_b;
     const int units = a.batch * 4;
     const int grid = units < max_ctas ? units : max_ctas;
     if (a.knew) return launch_pdl(PDL_ATTN_TMA, attn_decode_tma_kernel<true>, dim3(grid), dim3(96), smem, st, tm, tm4, k);

@@ -52,6 +52,35 @@ TX_DEVINL void ld8(const bf16* p, float* o) {
     }
 }
 
+// Loads of data that earlier kernels (re)write at the same address every step / sub-layer go to L2 (ld.global.cg): with
+// several streams' kernels resident on an SM, a line cached in its L1 by an earlier kernel can survive into a later one
+// (observed on B200 as rare stale reads of the step counter / query rows once K/V stopped streaming through L1).
+TX_DEVINL int ldcg_i32(const int* p) { return __ldcg(p); }
+TX_DEVINL uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+TX_DEVINL uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
+TX_DEVINL float4 ld4cg(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+TX_DEVINL float4 ld4cg(const bf16* p) {
+    uint2 r = __ldcg(reinterpret_cast<const uint2*>(p));
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+TX_DEVINL void ld8cg(const float* p, float* o) {
+    float4 a = ld4cg(p), b = ld4cg(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+TX_DEVINL void ld8cg(const bf16* p, float* o) {
+    uint4 r = __ldcg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        o[2 * i] = f.x;
+        o[2 * i + 1] = f.y;
+    }
+}
+
 TX_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

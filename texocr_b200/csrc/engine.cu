@@ -22,10 +22,9 @@
 
 static std::string g_create_error;
 // bits 0..5: programmatic dependent launch per kernel family (kernels.h); bit 8 / 9: LayerNorm / GEMM kernels release their
-// dependents only after their stores.  The GEMM kernel triggers late by default: with an early trigger the following
-// LayerNorm and the GEMM after it start while this GEMM is still running, and that three-deep overlap produced rare
-// run-to-run differences on B200 (1 row in ~10 calls at B=512; scripts/determinism_check.py) at < 2 % speed gain.
-int g_texocr_pdl = 0x23f;
+// dependents only after their stores (experiment switches; the default is an early trigger everywhere).
+int g_texocr_pdl = 0x3f;
+extern int g_attn_full_tail;
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -133,7 +132,7 @@ static int poison_workspaces(texocr_handle* h, cudaStream_t st) {
     DevBuf* bufs[] = {&h->raw1, &h->act2, &h->actA, &h->actB, &h->rawMid, &h->actMid, &h->rawMid2, &h->actMid2, &h->raw3, &h->rawDs,
                       &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3], &h->proj_out, &h->patch_cols,
                       &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits, &h->enc_out, &h->enc_a,
-                      &h->crosskv, &h->kvcache, &h->out_ids};
+                      &h->crosskv, &h->crosskv_hm, &h->kvcache, &h->out_ids};
     for (DevBuf* b : bufs) if (b->p) CK(cudaMemsetAsync(b->p, 0xFF, b->bytes, st));
     return 0;
 }
@@ -788,50 +787,95 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
     int* step = ds.step + branch;
     const size_t e = h->esz;
     int r;
-    LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4 + e), 0.0,
-           launch_embed_ln(ds.cur_tok + row0, step, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b,
-                           rowf(h->x, rc, 256), rowa(h, h->xn, rc, 256), h->dt, st));
+    const bool fuse = h->fuse_ln && h->dt == DT_BF16 && h->use_tcgen05 && !(h->dbg_skip & 12);
+    float* sbuf = rowf(h->s, rc, 256);
+    float* xbuf = rowf(h->x, rc, 256);
+    void* xnbuf = rowa(h, h->xn, rc, 256);
+    // GEMM whose A operand is the (double) LayerNorm of the residual stream in `s`: fused kernel, or LN kernel + plain GEMM
+    auto gemm_ln = [&](const void* W, int N, void* C, int ldc, int epi, int dt_c, const float* bias, bool first_ln, bool write_x,
+                       const float* fin_g, const float* fin_b) -> int {
+        GemmArgs ga = mk_gemm(xnbuf, 256, W, 256, C, ldc, rows, N, 256, epi, h->dt, dt_c, bias, nullptr, 0);
+        const float *g1 = nullptr, *b1 = nullptr, *g2 = h->dec_ln_g, *b2 = h->dec_ln_b;
+        if (fin_g) { g1 = fin_g; b1 = fin_b; g2 = nullptr; b2 = nullptr; }
+        else if (first_ln) { g1 = h->dec_ln_g; b1 = h->dec_ln_b; }
+        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(ga, e) + (double)rows * 256 * 8, gemm_flops(ga),
+               launch_gemm_tc_ln(ga, sbuf, g1, b1, g2, b2, write_x ? xbuf : nullptr, st));
+        return 0;
+    };
+    if (fuse) {
+        LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4), 0.0,
+               launch_embed_ln(ds.cur_tok + row0, step, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, nullptr, nullptr, sbuf, nullptr, h->dt, st));
+    } else {
+        LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4 + e), 0.0,
+               launch_embed_ln(ds.cur_tok + row0, step, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b,
+                               xbuf, xnbuf, h->dt, st));
+    }
     const double tkeys = t_host >= 0 ? (double)(t_host + 1) : 0.0;
     char* qb = (char*)rowa(h, h->qkv, rc, 1536);
     for (int l = 0; l < L; ++l) {
         // ---- causal self-attention over the KV cache
-        GemmArgs gq = mk_gemm(rowa(h, h->xn, rc, 256), 256, h->dec_self[l].wqkv, 256, qb, 1536, rows, 1536, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
-        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gq, e), gemm_flops(gq), run_gemm(h, gq, st));
+        if (fuse) {
+            // layer 0: x = embedding (no LayerNorm before the first block input's residual); later layers: x = LN(s)
+            if ((r = gemm_ln(h->dec_self[l].wqkv, 1536, qb, 1536, EPI_STORE, h->dt, nullptr, l > 0, true, nullptr, nullptr))) return r;
+        } else {
+            GemmArgs gq = mk_gemm(xnbuf, 256, h->dec_self[l].wqkv, 256, qb, 1536, rows, 1536, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gq, e), gemm_flops(gq), run_gemm(h, gq, st));
+        }
+        // KV cache, head-major: [layer][sequence][head][key][K 64 | V 64] -- every (sequence, head) is one contiguous stream
         AttnDecodeArgs ad{};
         char* kv = (char*)h->kvcache.p + ((size_t)l * B + row0) * tcap * 1024 * e;
         ad.q = qb; ad.ldq = 1536; ad.knew = qb + 512 * e; ad.vnew = qb + 1024 * e; ad.ldnew = 1536;
-        ad.kcache = kv; ad.vcache = kv + 512 * e; ad.ldkv = 1024; ad.batch_stride = (int64_t)tcap * 1024;
+        ad.kcache = kv; ad.vcache = kv + 64 * e; ad.ldkv = 128; ad.batch_stride = (int64_t)tcap * 1024; ad.head_stride = (int64_t)tcap * 128;
         ad.step = step; ad.o = rowa(h, h->o, rc, 512); ad.ldo = 512; ad.batch = rows; ad.dt = h->dt;
+        const KvLayout lay_self{kv, (long)rows * 8 * tcap, 128, 128, 0, 0, 64, tcap, 8 * tcap};
         if (h->dbg_skip & 1) {}
-        else if (h->use_tma_attn && attn_decode_tma_supported(ad))
+        else if ((h->use_tma_attn == 1 || h->use_tma_attn == 2) && attn_decode_tma_supported(ad))
             LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512,
-                   launch_attn_decode_tma(ad, kv, (long)rows * tcap, 1024, 0, tcap, h->num_sms * h->attn_ctas_per_sm, st));
+                   launch_attn_decode_tma(ad, lay_self, h->num_sms * h->attn_ctas_per_sm, st));
         else
             LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512, launch_attn_decode(ad, tcap, st));
         if ((r = sub_attn_out(h, rc, h->dec_self[l], st))) return r;
-        if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
         // ---- cross-attention over the (pre-projected) encoder memory; q goes to the first 512 columns of this branch's qkv rows
-        GemmArgs gc = mk_gemm(rowa(h, h->xn, rc, 256), 256, h->dec_cross[l].wq, 256, qb, 512, rows, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
-        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gc, e), gemm_flops(gc), run_gemm(h, gc, st));
+        if (fuse) {
+            if ((r = gemm_ln(h->dec_cross[l].wq, 512, qb, 512, EPI_STORE, h->dt, nullptr, true, true, nullptr, nullptr))) return r;
+        } else {
+            if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+            GemmArgs gc = mk_gemm(xnbuf, 256, h->dec_cross[l].wq, 256, qb, 512, rows, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gc, e), gemm_flops(gc), run_gemm(h, gc, st));
+        }
+        // encoder-memory K/V, head-major: [layer][head][token][K 64 | V 64]
         AttnDecodeArgs ac{};
-        char* ckv = (char*)h->crosskv.p + (size_t)l * 1024 * e;
-        ac.q = qb; ac.ldq = 512; ac.kcache = ckv; ac.vcache = ckv + 512 * e; ac.ldkv = L * 1024;
+        const long ntok_all = h->crosskv_rows;
+        char* ckv = (char*)h->crosskv_hm.p + (size_t)l * 8 * ntok_all * 128 * e;
+        ac.q = qb; ac.ldq = 512; ac.kcache = ckv; ac.vcache = ckv + 64 * e; ac.ldkv = 128; ac.head_stride = ntok_all * 128;
         ac.k_off = d_enc_off + row0; ac.o = rowa(h, h->o, rc, 512); ac.ldo = 512; ac.batch = rows; ac.dt = h->dt;
+        const KvLayout lay_cross{ckv, 8 * ntok_all, 128, 128, 0, 0, 64, (int)ntok_all, 0};
         if (h->dbg_skip & 2) {}
-        else if (h->use_tma_attn && attn_decode_tma_supported(ac))
+        else if ((h->use_tma_attn == 1 || h->use_tma_attn == 3) && attn_decode_tma_supported(ac))
             LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512,
-                   launch_attn_decode_tma(ac, h->crosskv.p, (long)h->crosskv_rows, L * 1024, l * 1024, 0, h->num_sms * h->attn_ctas_per_sm, st));
+                   launch_attn_decode_tma(ac, lay_cross, h->num_sms * h->attn_ctas_per_sm, st));
         else
             LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512, launch_attn_decode(ac, max_s, st));
         if ((r = sub_attn_out(h, rc, h->dec_cross[l], st))) return r;
-        if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
         // ---- GeGLU MLP
-        if ((r = sub_mlp(h, rc, h->dec_mlp[l], st))) return r;
-        if ((r = sub_norm(h, rc, l == L - 1, h->dec_norm_g, h->dec_norm_b, nullptr, rowa(h, h->xn, rc, 256), st))) return r;
+        if (fuse) {
+            if ((r = gemm_ln(h->dec_mlp[l].w1, 2048, rowa(h, h->hid, rc, 1024), 1024, EPI_GEGLU, h->dt, h->dec_mlp[l].b1, true, true, nullptr, nullptr))) return r;
+            GemmArgs g2 = mk_gemm(rowa(h, h->hid, rc, 1024), 1024, h->dec_mlp[l].w2, 1024, sbuf, 256, rows, 256, 1024, EPI_BIAS_RES, h->dt, DT_F32,
+                                  h->dec_mlp[l].b2, xbuf, 256);
+            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(g2, e), gemm_flops(g2), run_gemm(h, g2, st));
+        } else {
+            if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+            if ((r = sub_mlp(h, rc, h->dec_mlp[l], st))) return r;
+            if ((r = sub_norm(h, rc, l == L - 1, h->dec_norm_g, h->dec_norm_b, nullptr, xnbuf, st))) return r;
+        }
     }
     float* lg = h->logits.as<float>() + (size_t)row0 * c.vocab_size;
-    GemmArgs gl = mk_gemm(rowa(h, h->xn, rc, 256), 256, h->w_logits, 256, lg, c.vocab_size, rows, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
-    LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gl, e), gemm_flops(gl), run_gemm(h, gl, st));
+    if (fuse) {
+        if ((r = gemm_ln(h->w_logits, c.vocab_size, lg, c.vocab_size, EPI_STORE, DT_F32, h->b_logits, false, false, h->dec_norm_g, h->dec_norm_b))) return r;
+    } else {
+        GemmArgs gl = mk_gemm(xnbuf, 256, h->w_logits, 256, lg, c.vocab_size, rows, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
+        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gl, e), gemm_flops(gl), run_gemm(h, gl, st));
+    }
     ArgmaxArgs aa{};
     aa.logits = lg; aa.B = rows; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>() + (size_t)row0 * tcap; aa.out_ld = tcap;
     aa.cur_tok = ds.cur_tok + row0; aa.step = step; aa.seen_eos = ds.seen + row0; aa.done_step = ds.done_step + branch;
@@ -842,7 +886,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
 
 struct BranchPlan { int n; int row0[MAX_BRANCH]; int rows[MAX_BRANCH]; };
 static BranchPlan plan_branches(texocr_handle* h, int B) {
-    int n = h->decode_branches > 0 ? h->decode_branches : (B >= 256 ? 4 : (B >= 64 ? 2 : 1));
+    int n = h->decode_branches > 0 ? h->decode_branches : std::max(1, B / 64);     // ~64 rows per branch, up to MAX_BRANCH
     n = std::max(1, std::min(std::min(n, MAX_BRANCH), B));
     BranchPlan p;
     p.n = n;
@@ -883,6 +927,12 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     const int tcap = max_len;
     int r;
     if ((r = ensure_rows(h, B))) return r;
+    {   // the decode loop streams the memory K/V per (sequence, head): re-lay the GEMM output head-major, once
+        const int ntok = h->crosskv_rows;
+        ENSURE(h->crosskv_hm, (size_t)ntok * c.dec_layers * 1024 * h->esz);
+        LAUNCH(KC_MISC, 1, (double)ntok * c.dec_layers * 1024 * h->esz * 2, 0.0,
+               launch_crosskv_head_major(h->crosskv.p, h->crosskv_hm.p, ntok, c.dec_layers, h->dt, st));
+    }
     ENSURE(h->logits, (size_t)B * c.vocab_size * 4);
     ENSURE(h->kvcache, (size_t)c.dec_layers * B * tcap * 1024 * h->esz);
     ENSURE(h->dec_state, dec_state_bytes(B));
@@ -908,7 +958,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     for (int i = 0; i < bp.n; ++i) bst[i] = (bp.n == 1 || !graph_ok) ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
     if (graph_ok) {
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
-                         h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
+                         h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
             drop_graphs(h);
             const int64_t before = h->launches;
@@ -924,7 +974,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
             h->gkey.kernels = (int)(h->launches - before) / bp.n;
             h->launches = before;        // capture does not execute
             h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
-            h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv.p; h->gkey.x = h->x.p;
+            h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv_hm.p; h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
         }
         if (bp.n > 1) {      // fork: every branch stream waits for the work already queued on st, then starts with its phase shift
             CK(cudaEventRecord(h->fork_ev, st));
@@ -1030,7 +1080,7 @@ void texocr_destroy(texocr_handle* h) {
     DevBuf* bufs[] = {&h->geom, &h->img_stage, &h->raw1, &h->act2, &h->actA, &h->actB, &h->rawMid, &h->actMid, &h->rawMid2, &h->actMid2,
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
                       &h->proj_out, &h->patch_cols, &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
-                      &h->enc_out, &h->enc_a, &h->crosskv, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
+                      &h->enc_out, &h->enc_a, &h->crosskv, &h->crosskv_hm, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
                       &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->h_geom) cudaFreeHost(h->h_geom);
@@ -1283,8 +1333,10 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "attn_full_tail")) { g_attn_full_tail = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "fuse_ln")) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "poison")) { h->poison = value != 0; return 0; }
-    if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(3, value)); drop_graphs(h); return 0; }
+    if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(8, value)); drop_graphs(h); return 0; }
     if (!strcmp(name, "dbg_skip")) { h->dbg_skip = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "pdl")) {
         g_texocr_pdl = (int)value;
@@ -1292,7 +1344,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "tma_attention")) {
-        h->use_tma_attn = value != 0;
+        h->use_tma_attn = (int)value;
         drop_graphs(h);
         return 0;
     }
@@ -1322,6 +1374,18 @@ int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_
         CK(cudaMemcpy(out, src, (size_t)n * 4, is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
         return n;
     }
+    {   // raw workspace taps (byte-exact copies reinterpreted as float32 words): name -> buffer
+        struct { const char* n; DevBuf* b; } taps[] = {{"logits", &h->logits}, {"kvcache", &h->kvcache}, {"x", &h->x}, {"s", &h->s},
+                                                       {"xn", &h->xn}, {"qkv", &h->qkv}, {"o", &h->o}, {"hid", &h->hid},
+                                                       {"crosskv_hm", &h->crosskv_hm}, {"enc_out", &h->enc_out}};
+        for (auto& t : taps)
+            if (!strcmp(name, t.n)) {
+                if (!t.b->p) return fail(h, TEXOCR_ERR_STATE, "buffer '%s' not allocated", name);
+                const int64_t n = std::min<int64_t>((int64_t)(t.b->bytes / 4), cap_elems);
+                CK(cudaMemcpy(out, t.b->p, (size_t)n * 4, is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost));
+                return n;
+            }
+    }
     return fail(h, TEXOCR_ERR_ARG, "unknown debug tap '%s'", name);
 }
 
@@ -1348,23 +1412,24 @@ int texocr_debug_attn_decode(texocr_handle* h, int32_t self, const void* q, int3
                              const int32_t* k_off_dev, const int32_t* step_dev, void* out, int32_t batch, int32_t max_keys,
                              int32_t use_tma, void* stream) {
     if (!h) return TEXOCR_ERR_ARG;
+    (void)ldkv; (void)col0;
     CK(cudaSetDevice(h->device));
     StreamHop hop__(h, stream);
     cudaStream_t st = hop__.work;
     AttnDecodeArgs a{};
     char* base = (char*)kv;
-    a.q = q; a.ldq = ldq; a.o = out; a.ldo = 512; a.batch = batch; a.dt = DT_BF16; a.ldkv = ldkv;
-    if (self) {
-        a.knew = knew; a.vnew = vnew; a.ldnew = ldnew; a.kcache = base; a.vcache = base + 512 * 2;
-        a.batch_stride = (int64_t)tcap * ldkv; a.step = step_dev;
-    } else {
-        a.kcache = base + (size_t)col0 * 2; a.vcache = base + (size_t)(col0 + 512) * 2; a.k_off = k_off_dev;
+    a.q = q; a.ldq = ldq; a.o = out; a.ldo = 512; a.batch = batch; a.dt = DT_BF16; a.ldkv = 128;
+    a.kcache = base; a.vcache = base + 64 * 2;
+    KvLayout lay{kv, (long)kv_rows, 128, 128, 0, 0, 64, 0, 0};
+    if (self) {     // kv: [batch][8][tcap][128]
+        a.knew = knew; a.vnew = vnew; a.ldnew = ldnew; a.batch_stride = (int64_t)tcap * 1024; a.head_stride = (int64_t)tcap * 128;
+        a.step = step_dev; lay.row_h = tcap; lay.row_b = 8 * tcap;
+    } else {        // kv: [8][ntok][128], kv_rows = 8 * ntok
+        a.k_off = k_off_dev; a.head_stride = (kv_rows / 8) * 128; lay.row_h = (int)(kv_rows / 8);
     }
     if (use_tma) {
         if (!attn_decode_tma_supported(a)) return fail(h, TEXOCR_ERR_ARG, "not supported by the TMA attention kernel");
-        if (!self) a.kcache = base;
-        LAUNCH(KC_MISC, 1, 0.0, 0.0, launch_attn_decode_tma(a, kv, kv_rows, self ? 1024 : ldkv, self ? 0 : col0, tcap,
-                                                              h->num_sms * h->attn_ctas_per_sm, st));
+        LAUNCH(KC_MISC, 1, 0.0, 0.0, launch_attn_decode_tma(a, lay, h->num_sms * h->attn_ctas_per_sm, st));
     } else {
         LAUNCH(KC_MISC, 1, 0.0, 0.0, launch_attn_decode(a, max_keys, st));
     }

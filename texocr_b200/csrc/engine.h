@@ -70,13 +70,13 @@ struct texocr_handle {
     cudaEvent_t geom_ev = nullptr, hop_in = nullptr, hop_out = nullptr;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaStream_t branch_stream[8] = {nullptr}; cudaEvent_t join_ev[8] = {nullptr}; cudaEvent_t fork_ev = nullptr;
-    int decode_branches = 0;                   // 0 = automatic (4 for B >= 256, 2 for B >= 64)
+    int decode_branches = 0;                   // 0 = automatic (one branch per 64 rows, at most 8)
     DevBuf img_stage;                          // device copy of host images
     DevBuf raw1, act2, actA, actB, rawMid, actMid, rawMid2, actMid2, raw3, rawDs;
     DevBuf gn_partial, gn_stats[4];
     DevBuf proj_out, patch_cols, backbone_a, col;
     DevBuf x, s, xn, qkv, o, hid, logits;
-    DevBuf enc_out, enc_a, crosskv, kvcache;
+    DevBuf enc_out, enc_a, crosskv, crosskv_hm, kvcache;      // crosskv: GEMM output [tok][L*1024]; crosskv_hm: head-major copy for decoding
     DevBuf ids_stage, mask_stage, enc_stage, tgt_stage, row_loss, scalars;
     DevBuf dec_state;                          // int64 cur_tok[B] | int32 step, done_step, block_counter, pad | int32 seen[B]
     DevBuf out_ids;                            // int64 [B, max_len]
@@ -89,8 +89,8 @@ struct texocr_handle {
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;        // branch 0 (kept under these names)
     cudaGraph_t bgraph[8] = {nullptr}; cudaGraphExec_t bgraph_exec[8] = {nullptr};   // one single-step graph per branch
     cudaEvent_t poll_ev[2][8] = {{nullptr}};
-    int stagger_us = 60;                        // start offset between consecutive branches
-    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; } gkey;
+    int stagger_us = 30;                        // start offset between consecutive branches
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; } gkey;
 
     // ---- instrumentation
     int64_t launches = 0;
@@ -100,9 +100,10 @@ struct texocr_handle {
     double prof_ms[KC_COUNT] = {0}; double prof_bytes[KC_COUNT] = {0}; double prof_flops[KC_COUNT] = {0};
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
-    bool use_tma_attn = true;
+    int use_tma_attn = 1;     // 0 = simple kernel, 1 = TMA kernel for self + cross, 2 = self only, 3 = cross only
+    bool fuse_ln = false;    // decode step: LayerNorms computed inside the consuming tcgen05 GEMM (bf16 tier)
     bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate
     int dbg_skip = 0;        // timing experiments only: 1 self-attn, 2 cross-attn, 4 LayerNorms, 8 GEMMs (results are garbage)
     int num_sms = 148;
-    int attn_ctas_per_sm = 3;     // persistent decode-attention CTAs per SM (64 KB ring each); leaves room for the GEMM CTAs of other branches
+    int attn_ctas_per_sm = 4;     // persistent decode-attention CTAs per SM (64 KB ring each); leaves room for the GEMM CTAs of other branches
 };

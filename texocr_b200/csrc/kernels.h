@@ -129,9 +129,10 @@ cudaError_t launch_attn_varlen(const AttnVarlenArgs& a, cudaStream_t st);
 struct AttnDecodeArgs {
     const void* q; int ldq;            // [B, ldq], head h at q + h*64
     const void* knew; const void* vnew; int ldnew;   // self: this step's k/v rows (appended at *step); null for cross
-    void* kcache; void* vcache;        // self: [B, t_max, 512]; cross: packed rows [sum S, ldkv]
-    int ldkv;                          // row stride in elements
-    int64_t batch_stride;              // self: t_max*ldkv; cross: unused
+    void* kcache; void* vcache;        // K / V of head 0, key 0 (self: of sequence 0); V usually = K + 64 (head-major rows)
+    int ldkv;                          // key (row) stride in elements
+    int64_t batch_stride;              // self: elements between sequences; cross: unused
+    int64_t head_stride;               // elements between heads (0 -> 64: heads side by side inside a row)
     const int* k_off; const int* k_len;   // cross: per-row range; null for self
     const int* step;                   // self: number of cached keys before this step = *step
     void* o; int ldo;
@@ -143,6 +144,14 @@ cudaError_t launch_attn_decode(const AttnDecodeArgs& a, int nk_cap, cudaStream_t
 // bf16 tier: persistent TMA-fed streaming version of the decode attention (attn_decode_tma.cu).
 // map_base / map_rows / map_cols describe the 2-D K|V matrix the rows live in (row stride a.ldkv); col0 = column of
 // head 0's K inside a row; tcap = cache rows per sequence (self-attention).
+// Where the K|V rows of (sequence b, head h) live inside the 2-D matrix the tensor map covers:
+//   column of K = col0 + h*col_h, column of V = that + v_col, first row = (self ? b*row_b : k_off[b]) + h*row_h.
+// Head-major cache (the engine's layout): rows of 128 = [K 64 | V 64], col_h = 0, v_col = 64, row_h = keys per head.
+struct KvLayout {
+    const void* map_base; long map_rows; int map_cols; int ld;
+    int col0, col_h, v_col, row_h, row_b;
+};
 bool attn_decode_tma_supported(const AttnDecodeArgs& a);
-cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const void* map_base, long map_rows, int map_cols, int col0, int tcap,
-                                   int max_ctas, cudaStream_t st);
+cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const KvLayout& lay, int max_ctas, cudaStream_t st);
+// [tok][L*1024] (per layer: K 512 | V 512, heads side by side; the cross-K/V GEMM output) -> [L][8][tok][K 64 | V 64]
+cudaError_t launch_crosskv_head_major(const void* in, void* out, int ntok, int layers, int dt, cudaStream_t st);

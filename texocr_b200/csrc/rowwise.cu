@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
     if (row >= a.rows) { if (a.late_trigger) pdl_launch_dependents(); return; }
     float v[8];
-    ld8(a.in + (size_t)row * D + col, v);
+    ld8cg(a.in + (size_t)row * D + col, v);
     if (a.g1) layer_norm8(v, a.g1, a.b1, col);
     if (a.o1f) store8(a.o1f + (size_t)row * D + col, v);
     if (a.o1a) store8(reinterpret_cast<TAct*>(a.o1a) + (size_t)row * D + col, v);
@@ -58,15 +58,16 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
     if (row >= rows) return;
-    long id = (long)ids[row];
+    long id = (long)__ldcg(reinterpret_cast<const long long*>(ids) + row);
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-    const int pos = step ? *step : (row % T);
+    const int pos = step ? ldcg_i32(step) : (row % T);
     float v[8], pe[8];
     ld8(tok_emb + (size_t)id * D + col, v);
     ld8(pos_emb + (size_t)pos * D + col, pe);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += pe[i];
     store8(x + (size_t)row * D + col, v);
+    if (g == nullptr) return;          // embedding only: the consumer GEMM applies the LayerNorm itself (tc_gemm_ln_kernel)
     layer_norm8(v, g, b, col);
     store8(xn + (size_t)row * D + col, v);
 }
@@ -75,14 +76,14 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
     __shared__ int s_last;
     pdl_launch_dependents();
     pdl_wait();
-    const int t = *a.step;
+    const int t = ldcg_i32(a.step);
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row < a.B) {
         const float* l = a.logits + (size_t)row * a.V;
         float best = -INFINITY;
         int bi = 0x7fffffff;
         for (int i = lane; i < a.V; i += 32) {
-            const float v = l[i];
+            const float v = __ldcg(l + i);
             if (v > best) { best = v; bi = i; }       // ascending scan: first maximum wins (torch argmax)
         }
 #pragma unroll

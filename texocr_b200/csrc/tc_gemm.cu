@@ -95,6 +95,75 @@ TX_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
 // cute::UMMA::InstrDescriptor: c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
+// Epilogue shared by the GEMM kernels: thread = accumulator row (TMEM lane), 32 columns per tcgen05.ld.
+template <int BN, int EPI, typename TC>
+TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p) {
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < p.M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+            const int n = n0 + c0;
+            if (!row_ok || n >= p.N) continue;
+            const int nvalid = min(32, p.N - n);            // multiple of 8
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+            if (p.bias) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nvalid) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
+                }
+            }
+            if (EPI == EPI_STORE) {
+                TC* out = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc + n;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (i < nvalid) {
+                        st4(out + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                        st4(out + i + 4, make_float4(v[i + 4], v[i + 5], v[i + 6], v[i + 7]));
+                    }
+                }
+            } else if (EPI == EPI_BIAS_RES) {
+                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + n;
+                const float* rs = p.res + (size_t)m * p.ldres + n;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nvalid) {
+                        const float4 r = ld4cg(rs + i);
+                        st4(out + i, make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w));
+                    }
+                }
+            } else if (EPI == EPI_GLU_RES) {
+                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + (n >> 1);
+                const float* rs = p.res + (size_t)m * p.ldres + (n >> 1);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (i < nvalid) {
+                        const float4 r = ld4cg(rs + (i >> 1));
+                        st4(out + (i >> 1), make_float4(v[i] * sigmoidf_(v[i + 1]) + r.x, v[i + 2] * sigmoidf_(v[i + 3]) + r.y,
+                                                        v[i + 4] * sigmoidf_(v[i + 5]) + r.z, v[i + 6] * sigmoidf_(v[i + 7]) + r.w));
+                    }
+                }
+            } else {    // EPI_GEGLU -> bf16
+                bf16* out = reinterpret_cast<bf16*>(p.C) + (size_t)m * p.ldc + (n >> 1);
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (i < nvalid)
+                        st4(out + (i >> 1), make_float4(v[i] * gelu_erf(v[i + 1]), v[i + 2] * gelu_erf(v[i + 3]),
+                                                        v[i + 4] * gelu_erf(v[i + 5]), v[i + 6] * gelu_erf(v[i + 7])));
+                }
+            }
+        }
+}
+
 template <int BN, int SPLIT> struct Smem {
     static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
     static constexpr int NOPS = SPLIT == 3 ? 2 : 1;                 // hi (+ lo) copies per operand
@@ -175,71 +244,131 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(tmem_full);            // accumulator complete
         }
     } else {
-        // ---------------- epilogue: thread = accumulator row (TMEM lane), 32 columns per tcgen05.ld
-        mbar_wait(tmem_full, 0);
+        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (p.late_trigger) pdl_launch_dependents();
+    if (warp == 1) {
         tcgen05_fence_after();
-        const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
-        const bool row_ok = m < p.M;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-            const int n = n0 + c0;
-            if (!row_ok || n >= p.N) continue;
-            const int nvalid = min(32, p.N - n);            // multiple of 8
-            float v[32];
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm-fused GEMM
+// C = epi( LN2(LN1(S)) . W^T ) for K = 256: the shared double LayerNorm of model/attention.py:242-259 is computed by the
+// CTA itself and written straight into the swizzled A tiles (no xn round trip through HBM, no separate LN launch).
+// Every n-tile CTA of an m-block recomputes the (cheap) LayerNorm of its 128 rows; the n-tile-0 CTA also stores the
+// fp32 residual stream x = LN1(S).  Same arithmetic, in the same order, as ln2_kernel (rowwise.cu) -> identical bits.
+struct LnParams {
+    const float* in;                        // S rows [M, 256]
+    const float* g1; const float* b1;       // nullable: first LN skipped
+    const float* g2; const float* b2;       // nullable: second LN skipped
+    float* x_out;                           // nullable: fp32 copy of the first-stage result (residual stream)
+};
+
+template <int BN> struct SmemLn {
+    static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2, NKB = 4;
+    static constexpr int TOTAL = NKB * (A_BYTES + W_BYTES) + 1024 + 256;
+};
+
+TX_DEVINL void ln8(float* v, const float* __restrict__ g, const float* __restrict__ b, int col) {
+    float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-            if (p.bias) {
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / 256);
+    float q = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (i < nvalid) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                    }
-                }
-            }
-            if (EPI == EPI_STORE) {
-                TC* out = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc + n;
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 256) + 1e-5f);
+    float gg[8], bb[8];
+    ld8(g + col, gg);
+    ld8(b + col, bb);
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    if (i < nvalid) {
-                        st4(out + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-                        st4(out + i + 4, make_float4(v[i + 4], v[i + 5], v[i + 6], v[i + 7]));
-                    }
-                }
-            } else if (EPI == EPI_BIAS_RES) {
-                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + n;
-                const float* rs = p.res + (size_t)m * p.ldres + n;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (i < nvalid) {
-                        const float4 r = ld4(rs + i);
-                        st4(out + i, make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w));
-                    }
-                }
-            } else if (EPI == EPI_GLU_RES) {
-                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + (n >> 1);
-                const float* rs = p.res + (size_t)m * p.ldres + (n >> 1);
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    if (i < nvalid) {
-                        const float4 r = ld4(rs + (i >> 1));
-                        st4(out + (i >> 1), make_float4(v[i] * sigmoidf_(v[i + 1]) + r.x, v[i + 2] * sigmoidf_(v[i + 3]) + r.y,
-                                                        v[i + 4] * sigmoidf_(v[i + 5]) + r.z, v[i + 6] * sigmoidf_(v[i + 7]) + r.w));
-                    }
-                }
-            } else {    // EPI_GEGLU -> bf16
-                bf16* out = reinterpret_cast<bf16*>(p.C) + (size_t)m * p.ldc + (n >> 1);
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    if (i < nvalid)
-                        st4(out + (i >> 1), make_float4(v[i] * gelu_erf(v[i + 1]), v[i + 2] * gelu_erf(v[i + 3]),
-                                                        v[i + 4] * gelu_erf(v[i + 5]), v[i + 6] * gelu_erf(v[i + 7])));
-                }
+    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+}
+
+template <int BN, int EPI, typename TC>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmW, const TcParams p, const LnParams ln) {
+    using S = SmemLn<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem;                                   // [4 k-blocks][128 rows x 64] swizzled
+    uint8_t* smem_w = smem + S::NKB * S::A_BYTES;             // [4 k-blocks][BN rows x 64]
+    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem_w + S::NKB * S::W_BYTES);
+    uint64_t* a_ready = w_full + S::NKB;
+    uint64_t* tmem_full = a_ready + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+    if (!p.late_trigger) pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        for (int s = 0; s < S::NKB; ++s) mbar_init(&w_full[s], 1);
+        mbar_init(a_ready, 4);
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {                    // weights: all four k-blocks at once (they are L2-resident)
+            for (int kb = 0; kb < S::NKB; ++kb) {
+                mbar_expect_tx(&w_full[kb], S::W_BYTES);
+                tma_load_2d(&tmW, &w_full[kb], smem_w + kb * S::W_BYTES, kb * BK, n0);
             }
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            mbar_wait(a_ready, 0);
+            tcgen05_fence_after();
+            for (int kb = 0; kb < S::NKB; ++kb) {
+                mbar_wait(&w_full[kb], 0);
+                tcgen05_fence_after();
+                const uint32_t a_s = smem_u32(smem_a + kb * S::A_BYTES), w_s = smem_u32(smem_w + kb * S::W_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_smem_desc(a_s + k * UMMA_K * 2), make_smem_desc(w_s + k * UMMA_K * 2), idesc, (kb | k) != 0);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ---------------- LayerNorm prologue: warp q owns rows 32q..32q+31 of the tile, lane owns 8 consecutive columns
+        const int q = warp & 3;
+        const int col = lane * 8;
+        const int kb = lane >> 3, chunk = lane & 7;
+        for (int i = 0; i < 32; ++i) {
+            const int r = q * 32 + i, m = m0 + r;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (m < p.M) {
+                ld8(ln.in + (size_t)m * 256 + col, v);
+                if (ln.g1) ln8(v, ln.g1, ln.b1, col);
+                if (ln.x_out && blockIdx.x == 0) {
+                    st4(ln.x_out + (size_t)m * 256 + col, make_float4(v[0], v[1], v[2], v[3]));
+                    st4(ln.x_out + (size_t)m * 256 + col + 4, make_float4(v[4], v[5], v[6], v[7]));
+                }
+                if (ln.g2) ln8(v, ln.g2, ln.b2, col);
+            }
+            bf16* dst = reinterpret_cast<bf16*>(smem_a + kb * S::A_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+            st4(dst, make_float4(v[0], v[1], v[2], v[3]));
+            st4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready)) : "memory");
+        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -332,6 +461,51 @@ cudaError_t launch_epi(const GemmArgs& g, const CUtensorMap& a, const CUtensorMa
 }
 
 }  // namespace
+
+namespace {
+template <int BN, int EPI, typename TC>
+cudaError_t launch_ln_cfg(const CUtensorMap& w, const TcParams& p, const LnParams& ln, cudaStream_t st) {
+    using S = SmemLn<BN>;
+    static bool attr_set = false;
+    auto kern = tc_gemm_ln_kernel<BN, EPI, TC>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+    return launch_pdl(PDL_GEMM, kern, grid, dim3(192), (size_t)S::TOTAL, st, w, p, ln);
+}
+template <int BN>
+cudaError_t launch_ln_epi(const GemmArgs& g, const CUtensorMap& w, const TcParams& p, const LnParams& ln, cudaStream_t st) {
+    switch (g.epi) {
+        case EPI_STORE:
+            if (g.dt_c == DT_F32) return launch_ln_cfg<BN, EPI_STORE, float>(w, p, ln, st);
+            return launch_ln_cfg<BN, EPI_STORE, bf16>(w, p, ln, st);
+        case EPI_GEGLU: return launch_ln_cfg<BN, EPI_GEGLU, bf16>(w, p, ln, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+}  // namespace
+
+// GEMM whose A operand is LN2(LN1(S)) computed in the kernel (K must be 256).  g.A is ignored.
+cudaError_t launch_gemm_tc_ln(const GemmArgs& g, const float* s_in, const float* g1, const float* b1, const float* g2,
+                              const float* b2, float* x_out, cudaStream_t st) {
+    if (g.M <= 0) return cudaSuccess;
+    if (g.K != 256 || g.N % 8 != 0 || g.ldw % 8 != 0 || (g.epi != EPI_STORE && g.epi != EPI_GEGLU)) return cudaErrorInvalidValue;
+    const long mt = (g.M + BM - 1) / BM;
+    int bn = 128;
+    if (mt * ((g.N + 127) / 128) < 120) bn = 64;
+    if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
+    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1};
+    LnParams ln{s_in, g1, b1, g2, b2, x_out};
+    CUtensorMap w;
+    cudaError_t e;
+    if ((e = get_map(g.W, g.N, g.K, g.ldw, bn, &w)) != cudaSuccess) return e;
+    if (bn == 128) return launch_ln_epi<128>(g, w, p, ln, st);
+    if (bn == 64) return launch_ln_epi<64>(g, w, p, ln, st);
+    return launch_ln_epi<32>(g, w, p, ln, st);
+}
 
 bool tc_gemm_supported(const GemmArgs& g) {
     if (g.dt_a != DT_BF16 || g.conv) return false;
