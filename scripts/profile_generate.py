@@ -19,6 +19,7 @@ ap.add_argument("--max-len", type=int, default=256)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--branches", type=int, default=0, help="decode branches (0 = engine default)")
 args = ap.parse_args()
 cfg = spec.default_config(max_length=256)
 cfg["device"] = "cuda:0"
@@ -28,6 +29,8 @@ m.load_state_dict(synth.seeded_state_dict(d, seed=0))
 img = synth.synth_images(args.batch, 64, 384, seed=1234).cuda()
 if args.no_graph:
     m.engine().set_option("cuda_graph", 0)
+if args.branches:
+    m.engine().set_option("decode_branches", args.branches)
 for _ in range(args.warm):
     m.generate(img, args.max_len)
 torch.cuda.synchronize()

@@ -70,7 +70,7 @@ static cudaEvent_t get_event(texocr_handle* h) {
 
 // ------------------------------------------------------------------------------------------------ memory helpers
 static void drop_graphs(texocr_handle* h) {
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
         if (h->bgraph_exec[i]) { cudaGraphExecDestroy(h->bgraph_exec[i]); h->bgraph_exec[i] = nullptr; }
         if (h->bgraph[i]) { cudaGraphDestroy(h->bgraph[i]); h->bgraph[i] = nullptr; }
     }
@@ -761,7 +761,7 @@ static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_t
 }
 
 // ------------------------------------------------------------------------------------------------ decode step
-constexpr int MAX_BRANCH = 8;
+constexpr int MAX_BRANCH = 16;
 struct DecState {
     int64_t* cur_tok; int* step; int* done_step; int* block_counter; int* seen;     // step/done/counter: [MAX_BRANCH]
 };
@@ -886,7 +886,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
 
 struct BranchPlan { int n; int row0[MAX_BRANCH]; int rows[MAX_BRANCH]; };
 static BranchPlan plan_branches(texocr_handle* h, int B) {
-    int n = h->decode_branches > 0 ? h->decode_branches : std::max(1, B / 64);     // ~64 rows per branch, up to MAX_BRANCH
+    int n = h->decode_branches > 0 ? h->decode_branches : std::min(8, std::max(1, B / 64));     // ~64 rows per branch, 8 by default
     n = std::max(1, std::min(std::min(n, MAX_BRANCH), B));
     BranchPlan p;
     p.n = n;
@@ -1075,7 +1075,7 @@ void texocr_destroy(texocr_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     drop_graphs(h);
-    for (int s2 = 0; s2 < 2; ++s2) for (int i = 0; i < 8; ++i) if (h->poll_ev[s2][i]) cudaEventDestroy(h->poll_ev[s2][i]);
+    for (int s2 = 0; s2 < 2; ++s2) for (int i = 0; i < 16; ++i) if (h->poll_ev[s2][i]) cudaEventDestroy(h->poll_ev[s2][i]);
     for (void* p : h->weight_allocs) cudaFree(p);
     DevBuf* bufs[] = {&h->geom, &h->img_stage, &h->raw1, &h->act2, &h->actA, &h->actB, &h->rawMid, &h->actMid, &h->rawMid2, &h->actMid2,
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
@@ -1089,7 +1089,7 @@ void texocr_destroy(texocr_handle* h) {
     if (h->hop_in) cudaEventDestroy(h->hop_in);
     if (h->hop_out) cudaEventDestroy(h->hop_out);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
         if (h->branch_stream[i]) cudaStreamDestroy(h->branch_stream[i]);
         if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]);
     }

@@ -69,7 +69,7 @@ struct texocr_handle {
     int* h_geom = nullptr; size_t h_geom_cap = 0;   // pinned staging for geom
     cudaEvent_t geom_ev = nullptr, hop_in = nullptr, hop_out = nullptr;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
-    cudaStream_t branch_stream[8] = {nullptr}; cudaEvent_t join_ev[8] = {nullptr}; cudaEvent_t fork_ev = nullptr;
+    cudaStream_t branch_stream[16] = {nullptr}; cudaEvent_t join_ev[16] = {nullptr}; cudaEvent_t fork_ev = nullptr;
     int decode_branches = 0;                   // 0 = automatic (one branch per 64 rows, at most 8)
     DevBuf img_stage;                          // device copy of host images
     DevBuf raw1, act2, actA, actB, rawMid, actMid, rawMid2, actMid2, raw3, rawDs;
@@ -87,8 +87,8 @@ struct texocr_handle {
     // ---- decode-step CUDA graph
     bool use_graph = true;
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;        // branch 0 (kept under these names)
-    cudaGraph_t bgraph[8] = {nullptr}; cudaGraphExec_t bgraph_exec[8] = {nullptr};   // one single-step graph per branch
-    cudaEvent_t poll_ev[2][8] = {{nullptr}};
+    cudaGraph_t bgraph[16] = {nullptr}; cudaGraphExec_t bgraph_exec[16] = {nullptr};   // one single-step graph per branch
+    cudaEvent_t poll_ev[2][16] = {{nullptr}};
     int stagger_us = 30;                        // start offset between consecutive branches
     struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; } gkey;
 
