@@ -10,48 +10,45 @@ namespace {
 
 // ------------------------------------------------------------------ stem conv 7x7 stride 2, Cin = 1
 // model/resnet.py:219 + utils.py:98-123: SAME padding of an even extent with k=7,s=2 is (2,3).
-// One warp per run of output pixels; lane = output channel pair (lane, lane+32); the 2x49 filter taps
-// live in registers, the input window is a broadcast read.
+// CTA = one output row of one image; the 49x64 standardised filter bank sits in shared memory for the whole row, the
+// input window (7 rows x 69 columns) of each 32-pixel segment is staged in shared memory.  Thread = (output channel,
+// group of 8 pixels): filter taps are conflict-free reads, the input pixel is a warp-wide broadcast, stores are 256-byte
+// rows of the NHWC output.
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w,
-                                                        float* __restrict__ raw1, ImgGeom g, int total_p1) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float w0[49], w1[49];
-#pragma unroll
-    for (int t = 0; t < 49; ++t) {
-        w0[t] = w[t * 64 + lane];
-        w1[t] = w[t * 64 + lane + 32];
-    }
-    const int pix_per_warp = 16;
-    const int base = (blockIdx.x * 8 + warp) * pix_per_warp;
-    int b = -1, H = 0, W = 0, p_lo = 0, p_hi = 0;      // image of the current run of pixels
-    for (int i = 0; i < pix_per_warp; ++i) {
-        const int p = base + i;
-        if (p >= total_p1) return;
-        if (b < 0 || p >= p_hi) {
-            b = find_image(g.img_off, g.nimg, 1, p);
-            H = g.img_hw[2 * b]; W = g.img_hw[2 * b + 1];
-            p_lo = g.img_off[b] >> 2; p_hi = g.img_off[b + 1] >> 2;
+                                                        float* __restrict__ raw1, ImgGeom g) {
+    __shared__ float ws[49 * 64];
+    __shared__ float win[7][72];
+    const int b = blockIdx.y, oy = blockIdx.x;
+    const int H = g.img_hw[2 * b], W = g.img_hw[2 * b + 1];
+    const int H1 = H >> 1, W1 = W >> 1;
+    if (oy >= H1) return;
+    for (int i = threadIdx.x; i < 49 * 64; i += 256) ws[i] = w[i];
+    const float* im = img + g.img_off[b];
+    float* out = raw1 + ((size_t)(g.img_off[b] >> 2) + (size_t)oy * W1) * 64;
+    const int c = threadIdx.x & 63, pg = threadIdx.x >> 6;
+    for (int x0 = 0; x0 < W1; x0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 7 * 69; i += 256) {          // input columns 2*x0-2 .. 2*x0+66, rows 2*oy-2 .. 2*oy+4
+            const int ky = i / 69, cx = i - ky * 69;
+            const int iy = 2 * oy + ky - 2, ix = 2 * x0 + cx - 2;
+            win[ky][cx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(im + (size_t)iy * W + ix) : 0.f;
         }
-        const int w1d = W >> 1;
-        const int local = p - p_lo;
-        const int oy = local / w1d, ox = local - oy * w1d;
-        const float* im = img + g.img_off[b];
-        float a0 = 0.f, a1 = 0.f;
+        __syncthreads();
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky) {
-            const int iy = 2 * oy + ky - 2;
-            if (iy < 0 || iy >= H) continue;
 #pragma unroll
             for (int kx = 0; kx < 7; ++kx) {
-                const int ix = 2 * ox + kx - 2;
-                if (ix < 0 || ix >= W) continue;
-                const float v = __ldg(im + (size_t)iy * W + ix);
-                a0 = fmaf(v, w0[ky * 7 + kx], a0);
-                a1 = fmaf(v, w1[ky * 7 + kx], a1);
+                const float wt = ws[(ky * 7 + kx) * 64 + c];
+#pragma unroll
+                for (int px = 0; px < 8; ++px) acc[px] = fmaf(win[ky][2 * (pg * 8 + px) + kx], wt, acc[px]);
             }
         }
-        raw1[(size_t)p * 64 + lane] = a0;
-        raw1[(size_t)p * 64 + lane + 32] = a1;
+#pragma unroll
+        for (int px = 0; px < 8; ++px) {
+            const int ox = x0 + pg * 8 + px;
+            if (ox < W1) out[(size_t)ox * 64 + c] = acc[px];
+        }
     }
 }
 
@@ -302,8 +299,9 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
 cudaError_t launch_stem_conv(const float* img, const float* w, float* raw1, const int* img_off, const int* img_hw,
                              int nimg, int total_p1, cudaStream_t st) {
     ImgGeom g{img_off, img_hw, nimg};
-    const int blocks = (total_p1 + 127) / 128;
-    stem_conv_kernel<<<blocks, 256, 0, st>>>(img, w, raw1, g, total_p1);
+    (void)total_p1;
+    dim3 grid(80, nimg);             // output rows per image: H/2 <= 80 (H <= 160); rows past an image's height exit at once
+    stem_conv_kernel<<<grid, 256, 0, st>>>(img, w, raw1, g);
     return cudaGetLastError();
 }
 

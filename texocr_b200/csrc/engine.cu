@@ -731,7 +731,8 @@ static int run_encoder(texocr_handle* h, const float* d_img, const EncGeom& g, c
         av.causal = 0; av.dt = h->dt;
         double aflops = 0.0;
         for (int b = 0; b < g.B; ++b) { const double n = g.tok_off[b + 1] - g.tok_off[b]; aflops += 4.0 * n * n * 512; }
-        LAUNCH(KC_ENC_ATTN, 1, (double)R * 2048 * h->esz, aflops, launch_attn_varlen(av, st));
+        if (h->use_tcgen05 && attn_enc_mma_supported(av)) LAUNCH(KC_ENC_ATTN, 1, (double)R * 2048 * h->esz, aflops, launch_attn_enc_mma(av, st));
+        else LAUNCH(KC_ENC_ATTN, 1, (double)R * 2048 * h->esz, aflops, launch_attn_varlen(av, st));
         if ((r = sub_attn_out(h, rc, h->enc_attn[l], st))) return r;
         if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
         if ((r = sub_mlp(h, rc, h->enc_mlp[l], st))) return r;

@@ -126,6 +126,9 @@ struct AttnVarlenArgs {
     int batch, max_q, causal, dt;
 };
 cudaError_t launch_attn_varlen(const AttnVarlenArgs& a, cudaStream_t st);
+// bf16, unmasked, non-causal (encoder self-attention): mma.sync flash-attention kernel (attn_enc_mma.cu)
+bool attn_enc_mma_supported(const AttnVarlenArgs& a);
+cudaError_t launch_attn_enc_mma(const AttnVarlenArgs& a, cudaStream_t st);
 struct AttnDecodeArgs {
     const void* q; int ldq;            // [B, ldq], head h at q + h*64
     const void* knew; const void* vnew; int ldnew;   // self: this step's k/v rows (appended at *step); null for cross

@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_gemm.h"
@@ -95,88 +96,112 @@ TX_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
 // cute::UMMA::InstrDescriptor: c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
 constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
-// Epilogue shared by the GEMM kernels: thread = accumulator row (TMEM lane), 32 columns per tcgen05.ld.
+// Epilogue shared by the GEMM kernels.  Thread = accumulator row (TMEM lane), 32 columns per tcgen05.ld.  Global traffic
+// goes through a per-warp staging tile in shared memory (the pipeline stages are idle once the accumulator is complete),
+// so that residual loads and output stores are whole 64..128-byte row segments per quarter-warp instead of one row per
+// lane: the epilogue, not the MMA loop, bounds these K <= 1024 GEMMs.
+constexpr int STG_STRIDE = 144;                 // bytes per staged row (128 + 16: conflict-free 16-byte accesses)
+constexpr int STG_WARP = 32 * STG_STRIDE;       // staging bytes per epilogue warp
+
+// copy a [32 rows x RB bytes] tile between the warp's staging area and global memory, 16 bytes per lane
+template <int RB, bool TO_GLOBAL>
+TX_DEVINL void stage_copy(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int lane, int rows_ok, int bytes_ok) {
+    constexpr int CPR = RB / 16, RPI = 32 / CPR;
+    const int rr = lane / CPR, ch = lane % CPR;
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) {
+        const int row = it * RPI + rr;
+        if (row < rows_ok && ch * 16 < bytes_ok) {
+            uint4* sp = reinterpret_cast<uint4*>(stg + row * STG_STRIDE + ch * 16);
+            uint4* gp = reinterpret_cast<uint4*>(gptr + (size_t)row * grow_bytes + ch * 16);
+            if (TO_GLOBAL) *gp = *sp; else *sp = __ldcg(gp);
+        }
+    }
+}
+
 template <int BN, int EPI, typename TC>
-TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p) {
-        mbar_wait(tmem_full, 0);
-        tcgen05_fence_after();
-        const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
-        const bool row_ok = m < p.M;
+TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
+                             uint8_t* smem_idle) {
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;
+    uint8_t* stg = smem_idle + q * STG_WARP;
+    uint8_t* my = stg + lane * STG_STRIDE;                      // this thread's staged row
+    const int mrow0 = m0 + q * 32;
+    const int rows_ok = min(32, p.M - mrow0);                   // <= 0: nothing of this warp's rows is inside the matrix
+    constexpr bool PAIRS = (EPI == EPI_GLU_RES || EPI == EPI_GEGLU);
+    constexpr int NOUT = PAIRS ? 16 : 32;
+    using TO = typename std::conditional<EPI == EPI_STORE, TC, typename std::conditional<EPI == EPI_GEGLU, bf16, float>::type>::type;
+    constexpr int RB = NOUT * (int)sizeof(TO);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-            const int n = n0 + c0;
-            if (!row_ok || n >= p.N) continue;
-            const int nvalid = min(32, p.N - n);            // multiple of 8
-            float v[32];
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+        const int n = n0 + c0;
+        if (rows_ok <= 0 || n >= p.N) continue;                 // warp-uniform
+        const int nvalid = min(32, p.N - n);                    // multiple of 8
+        const int ncol = PAIRS ? (n >> 1) : n, nvalid_out = PAIRS ? (nvalid >> 1) : nvalid;
+        float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-            if (p.bias) {
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        if (p.bias) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (i < nvalid) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                    }
-                }
-            }
-            if (EPI == EPI_STORE) {
-                TC* out = reinterpret_cast<TC*>(p.C) + (size_t)m * p.ldc + n;
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    if (i < nvalid) {
-                        st4(out + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-                        st4(out + i + 4, make_float4(v[i + 4], v[i + 5], v[i + 6], v[i + 7]));
-                    }
-                }
-            } else if (EPI == EPI_BIAS_RES) {
-                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + n;
-                const float* rs = p.res + (size_t)m * p.ldres + n;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (i < nvalid) {
-                        const float4 r = ld4cg(rs + i);
-                        st4(out + i, make_float4(v[i] + r.x, v[i + 1] + r.y, v[i + 2] + r.z, v[i + 3] + r.w));
-                    }
-                }
-            } else if (EPI == EPI_GLU_RES) {
-                float* out = reinterpret_cast<float*>(p.C) + (size_t)m * p.ldc + (n >> 1);
-                const float* rs = p.res + (size_t)m * p.ldres + (n >> 1);
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    if (i < nvalid) {
-                        const float4 r = ld4cg(rs + (i >> 1));
-                        st4(out + (i >> 1), make_float4(v[i] * sigmoidf_(v[i + 1]) + r.x, v[i + 2] * sigmoidf_(v[i + 3]) + r.y,
-                                                        v[i + 4] * sigmoidf_(v[i + 5]) + r.z, v[i + 6] * sigmoidf_(v[i + 7]) + r.w));
-                    }
-                }
-            } else {    // EPI_GEGLU -> bf16
-                bf16* out = reinterpret_cast<bf16*>(p.C) + (size_t)m * p.ldc + (n >> 1);
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    if (i < nvalid)
-                        st4(out + (i >> 1), make_float4(v[i] * gelu_erf(v[i + 1]), v[i + 2] * gelu_erf(v[i + 3]),
-                                                        v[i + 4] * gelu_erf(v[i + 5]), v[i + 6] * gelu_erf(v[i + 7])));
+            for (int i = 0; i < 32; i += 4) {
+                if (i < nvalid) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
                 }
             }
         }
+        float o[NOUT];
+        if (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES) {
+            // residual tile -> staging (coalesced), then every thread picks up its own row
+            stage_copy<NOUT * 4, false>(stg, reinterpret_cast<uint8_t*>(const_cast<float*>(p.res) + (size_t)mrow0 * p.ldres + ncol),
+                                        (size_t)p.ldres * 4, lane, rows_ok, nvalid_out * 4);
+            __syncwarp();
+            float r[NOUT];
+#pragma unroll
+            for (int i = 0; i < NOUT; i += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(my + i * 4);
+                r[i] = t.x; r[i + 1] = t.y; r[i + 2] = t.z; r[i + 3] = t.w;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i)
+                o[i] = (EPI == EPI_BIAS_RES) ? v[i] + r[i] : v[2 * i] * sigmoidf_(v[2 * i + 1]) + r[i];
+        } else if (EPI == EPI_GEGLU) {
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) o[i] = v[2 * i] * gelu_erf(v[2 * i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) o[i] = v[i];
+        }
+        // outputs -> staging (own row) -> coalesced global stores
+        TO* mine = reinterpret_cast<TO*>(my);
+#pragma unroll
+        for (int i = 0; i < NOUT; i += 4) st4(mine + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+        __syncwarp();
+        stage_copy<RB, true>(stg, reinterpret_cast<uint8_t*>(reinterpret_cast<TO*>(p.C) + (size_t)mrow0 * p.ldc + ncol),
+                             (size_t)p.ldc * sizeof(TO), lane, rows_ok, nvalid_out * (int)sizeof(TO));
+        __syncwarp();
+    }
 }
 
-template <int BN, int SPLIT> struct Smem {
+// NSTG = 0: as many stages as fit (deep prefetch for the latency-bound small-M decode GEMMs); NSTG = 2: two stages, so that
+// 2-3 CTAs share an SM and one CTA's epilogue / ramp-up overlaps another's MMA loop (large-M encoder GEMMs).
+template <int BN, int SPLIT, int NSTG = 0> struct Smem {
     static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
     static constexpr int NOPS = SPLIT == 3 ? 2 : 1;                 // hi (+ lo) copies per operand
     static constexpr int STAGE = NOPS * (A_BYTES + W_BYTES);
-    static constexpr int STAGES = (STAGE * 4 <= 160 * 1024) ? 4 : (STAGE * 3 <= 200 * 1024 ? 3 : 2);
+    static constexpr int STAGES = NSTG ? NSTG : ((STAGE * 4 <= 160 * 1024) ? 4 : (STAGE * 3 <= 200 * 1024 ? 3 : 2));
     static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI, typename TC, int SPLIT>
+template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
-    using S = Smem<BN, SPLIT>;
+    using S = Smem<BN, SPLIT, NSTG>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
@@ -244,7 +269,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(tmem_full);            // accumulator complete
         }
     } else {
-        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p);
+        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -368,7 +393,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmW, const TcParams p, con
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready)) : "memory");
-        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p);
+        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem_a);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -431,12 +456,12 @@ cudaError_t tma_map_2d_bf16(const void* ptr, long rows, int cols, long ld, int b
 
 namespace {
 
-template <int BN, int EPI, typename TC, int SPLIT>
-cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
-                       cudaStream_t st) {
-    using S = Smem<BN, SPLIT>;
+template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
+cudaError_t launch_cfg2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                        cudaStream_t st) {
+    using S = Smem<BN, SPLIT, NSTG>;
     static bool attr_set = false;
-    auto kern = tc_gemm_kernel<BN, EPI, TC, SPLIT>;
+    auto kern = tc_gemm_kernel<BN, EPI, TC, SPLIT, NSTG>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
@@ -444,6 +469,15 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
     return launch_pdl(PDL_GEMM, kern, grid, dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
+}
+
+template <int BN, int EPI, typename TC, int SPLIT>
+cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                       cudaStream_t st) {
+    // many tiles (encoder / teacher-forced sizes): shallow pipeline, several CTAs per SM; few tiles: deep pipeline
+    const long tiles = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
+    if (SPLIT == 1 && BN >= 64 && tiles >= 592) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
+    return launch_cfg2<BN, EPI, TC, SPLIT, 0>(a, w, a2, w2, p, st);
 }
 
 template <int BN, int SPLIT>
