@@ -18,6 +18,7 @@
 
 #include <algorithm>
 
+#include "decode_mega.h"
 #include "tc_gemm.h"
 
 static std::string g_create_error;
@@ -48,7 +49,7 @@ static int fail_cuda(texocr_handle* h, cudaError_t e, const char* what, int line
 // ------------------------------------------------------------------------------------------------ profiling / launch accounting
 static const char* kclass_name[KC_COUNT] = {
     "stem_conv", "gn_stats", "gn_apply", "conv_gemm", "enc_gemm", "enc_attn", "enc_rowwise", "crosskv_gemm",
-    "dec_gemm", "dec_attn_self", "dec_attn_cross", "dec_rowwise", "dec_argmax", "tf_gemm", "tf_attn", "tf_rowwise", "misc"};
+    "dec_gemm", "dec_attn_self", "dec_attn_cross", "dec_rowwise", "dec_argmax", "tf_gemm", "tf_attn", "tf_rowwise", "misc", "dec_mega"};
 
 static cudaEvent_t get_event(texocr_handle* h) {
     if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
@@ -917,6 +918,81 @@ static int enqueue_all_branches(texocr_handle* h, const BranchPlan& bp, bool for
     return 0;
 }
 
+// bf16 tier: the whole loop as launches of the cluster-persistent decode kernel (decode_mega.cu), `mega_steps` steps each.
+static int run_generate_mega(texocr_handle* h, const DecState& ds, int eos, const int* d_enc_off, double sum_s, int B, int tcap,
+                             int groups, int64_t* out_ids, int32_t* n_steps, cudaStream_t st) {
+    const texocr_config& c = h->cfg;
+    const int L = c.dec_layers;
+    ENSURE(h->mega_part, (size_t)B * MEGA_CLUSTER * 8);
+    for (int s2 = 0; s2 < 2; ++s2)
+        if (!h->poll_ev[s2][0]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][0], cudaEventDisableTiming));
+    MegaArgs a{};
+    a.B = B; a.L = L; a.V = c.vocab_size; a.tcap = tcap; a.eos = eos; a.G = groups;
+    for (int l = 0; l < L; ++l) {
+        MegaLayerW& w = a.layer[l];
+        w.wqkv = h->dec_self[l].wqkv; w.wo_s = h->dec_self[l].wo; w.bo_s = h->dec_self[l].bo;
+        w.wq_c = h->dec_cross[l].wq; w.wo_c = h->dec_cross[l].wo; w.bo_c = h->dec_cross[l].bo;
+        w.w1 = h->dec_mlp[l].w1; w.b1 = h->dec_mlp[l].b1; w.w2 = h->dec_mlp[l].w2; w.b2 = h->dec_mlp[l].b2;
+    }
+    a.w_logits = h->w_logits; a.b_logits = h->b_logits; a.tok_emb = h->tok_emb; a.pos_emb = h->pos_emb;
+    a.ln_g = h->dec_ln_g; a.ln_b = h->dec_ln_b; a.fin_g = h->dec_norm_g; a.fin_b = h->dec_norm_b;
+    a.cur_tok = ds.cur_tok; a.step = ds.step; a.done_step = ds.done_step; a.seen = ds.seen; a.out_ids = h->out_ids.as<int64_t>();
+    a.x = h->x.as<float>(); a.s = h->s.as<float>(); a.qkv = h->qkv.p; a.o = h->o.p; a.hid = h->hid.p;
+    a.part_val = h->mega_part.as<float>(); a.part_idx = h->mega_part.as<int>() + (size_t)B * MEGA_CLUSTER;
+    a.kv_self = h->kvcache.p; a.kv_cross = h->crosskv_hm.p; a.ntok = h->crosskv_rows; a.enc_off = d_enc_off;
+    static const bool timing = getenv("TEXOCR_MEGA_TIMING") != nullptr;      // debug: per-phase time breakdown on stderr
+    if (timing) {
+        ENSURE(h->mega_dbg, 16 * 8);
+        CK(cudaMemsetAsync(h->mega_dbg.p, 0, 16 * 8, st));
+        a.dbg_time = (unsigned long long*)h->mega_dbg.p;
+    }
+    int issued = 0, polls = 0;
+    bool stop = false;
+    while (issued < tcap && !stop) {
+        a.nsteps = std::min(h->mega_steps, tcap - issued);
+        // algorithmic traffic of the launch: every cached key / memory token is read once per step and layer (K + V, 8 heads)
+        double keys = 0.0;
+        for (int t = issued; t < issued + a.nsteps; ++t) keys += (double)B * (t + 1) + sum_s;
+        const double flops_step = 2.0 * B * ((double)L * (256.0 * 1536 + 512.0 * 512 + 256.0 * 512 + 512.0 * 512 + 256.0 * 2048 + 1024.0 * 256) + 256.0 * c.vocab_size);
+        LAUNCH(KC_DEC_MEGA, 1, keys * L * 1024 * h->esz, flops_step * a.nsteps + 4.0 * keys * L * 512, launch_decode_mega(a, st));
+        issued += a.nsteps;
+        if (eos >= 0 && issued < tcap) {      // host runs ahead of the device by at most two launches
+            const int slot = polls & 1;
+            if (polls >= 1) {
+                CK(cudaEventSynchronize(h->poll_ev[slot ^ 1][0]));
+                bool all = true;
+                for (int i = 0; i < groups; ++i) all = all && h->h_poll[(slot ^ 1) * MAX_BRANCH + i] > 0;
+                if (all) stop = true;
+            }
+            CK(cudaMemcpyAsync(&h->h_poll[slot * MAX_BRANCH], ds.done_step, (size_t)groups * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->poll_ev[slot][0], st));
+            ++polls;
+        }
+    }
+    CK(cudaMemcpyAsync(&h->h_poll[2 * MAX_BRANCH], ds.done_step, MAX_BRANCH * 4, cudaMemcpyDeviceToHost, st));
+    int r;
+    if ((r = from_device(h, out_ids, h->out_ids.p, (size_t)B * tcap * 8, st))) return r;
+    CK(cudaStreamSynchronize(st));
+    int done = 0;
+    bool all_done = true;
+    for (int i = 0; i < groups; ++i) {
+        const int d = h->h_poll[2 * MAX_BRANCH + i];
+        all_done = all_done && d > 0;
+        done = std::max(done, d);
+    }
+    *n_steps = all_done ? done : tcap;
+    if (timing) {
+        unsigned long long tt[16];
+        CK(cudaMemcpy(tt, h->mega_dbg.p, sizeof tt, cudaMemcpyDeviceToHost));
+        static const char* nm[16] = {"qkv", "out_s", "q_c", "out_c", "ff1", "ff2", "logits", "self_attn", "cross_attn", "argmax", "cluster_sync", "kernel", "prologue", "operand_wait", "mma", "-"};
+        const double ctas = (double)groups * MEGA_CLUSTER;
+        fprintf(stderr, "[mega timing] B=%d steps=%d active_clusters=%d; per-CTA mean, us per step:", B, issued, decode_mega_active_clusters());
+        for (int i = 0; i < 15; ++i) fprintf(stderr, " %s=%.1f", nm[i], tt[i] / ctas / issued * 1e-3);
+        fprintf(stderr, "\n");
+    }
+    return 0;
+}
+
 // enc memory must already be projected into h->crosskv; d_enc_off = per-row token offsets (device, B+1)
 static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const int* d_enc_off, int max_s, double sum_s, int B,
                         int max_len, int64_t* out_ids, int32_t* n_steps, cudaStream_t st) {
@@ -942,6 +1018,12 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     DecState ds = dec_state(h, B);
     CK(cudaMemsetAsync((char*)h->dec_state.p + (size_t)B * 8, 0, dec_state_bytes(B) - (size_t)B * 8, st));
     CK(cudaMemcpyAsync(ds.cur_tok, d_start, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+    {
+        if (h->decode_mega && h->dt == DT_BF16 && decode_mega_supported(B, c.dec_layers, c.vocab_size, nullptr)) {
+            const int groups = decode_mega_groups(B);
+            if (groups <= MAX_BRANCH) return run_generate_mega(h, ds, eos, d_enc_off, sum_s, B, tcap, groups, out_ids, n_steps, st);
+        }
+    }
     const BranchPlan bp = plan_branches(h, B);
     for (int i = 0; i < bp.n; ++i) {
         if (!h->branch_stream[i]) {
@@ -1082,7 +1164,7 @@ void texocr_destroy(texocr_handle* h) {
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
                       &h->proj_out, &h->patch_cols, &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
                       &h->enc_out, &h->enc_a, &h->crosskv, &h->crosskv_hm, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
-                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids};
+                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);
@@ -1354,6 +1436,8 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
         h->decode_branches = (int)value;
         return 0;
     }
+    if (!strcmp(name, "decode_mega")) { h->decode_mega = (int)value; return 0; }
+    if (!strcmp(name, "mega_steps")) { h->mega_steps = (int)std::max<int64_t>(1, std::min<int64_t>(4096, value)); return 0; }
     if (!strcmp(name, "tcgen05")) {
         h->use_tcgen05 = value != 0;
         drop_graphs(h);

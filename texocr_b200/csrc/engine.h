@@ -36,7 +36,7 @@ struct MlpW { void* w1 = nullptr; float* b1 = nullptr; void* w2 = nullptr; float
 enum KClass {
     KC_STEM = 0, KC_GN_STATS, KC_GN_APPLY, KC_CONV, KC_ENC_GEMM, KC_ENC_ATTN, KC_ENC_ROW, KC_CROSSKV_GEMM,
     KC_DEC_GEMM, KC_DEC_ATTN_SELF, KC_DEC_ATTN_CROSS, KC_DEC_ROW, KC_DEC_ARGMAX, KC_TF_GEMM, KC_TF_ATTN, KC_TF_ROW,
-    KC_MISC, KC_COUNT
+    KC_MISC, KC_DEC_MEGA, KC_COUNT
 };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; double bytes, flops; };
@@ -80,6 +80,8 @@ struct texocr_handle {
     DevBuf ids_stage, mask_stage, enc_stage, tgt_stage, row_loss, scalars;
     DevBuf dec_state;                          // int64 cur_tok[B] | int32 step, done_step, block_counter, pad | int32 seen[B]
     DevBuf out_ids;                            // int64 [B, max_len]
+    DevBuf mega_dbg;
+    DevBuf mega_part;                          // cluster-persistent decode kernel: per-CTA argmax partials [B][16] (float | int)
     int* h_poll = nullptr;                     // pinned: done_step polls
     int last_backbone_pixels = 0;
     int crosskv_rows = 0;
@@ -100,6 +102,9 @@ struct texocr_handle {
     double prof_ms[KC_COUNT] = {0}; double prof_bytes[KC_COUNT] = {0}; double prof_flops[KC_COUNT] = {0};
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
+    int decode_mega = 0;      // bf16 tier: 1 = experimental cluster-persistent decode kernel (decode_mega.cu), 0 = per-branch kernel graphs.
+                              // Token-identical to the branch path but ~1.8x slower at B = 512 (issue-bound at 8 warps per SM)
+    int mega_steps = 16;      // decode steps per launch of that kernel (also the early-exit polling interval)
     int use_tma_attn = 1;     // 0 = simple kernel, 1 = TMA kernel for self + cross, 2 = self only, 3 = cross only
     bool fuse_ln = false;    // decode step: LayerNorms computed inside the consuming tcgen05 GEMM (bf16 tier)
     bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate

@@ -454,6 +454,22 @@ cudaError_t tma_map_2d_bf16(const void* ptr, long rows, int cols, long ld, int b
     return cudaSuccess;
 }
 
+// 3-D bf16 tensor [d2][d1][d0] (d0 contiguous; strides of d1 / d2 in bytes); box = b2 x b1 x b0, 128-byte swizzle, zero OOB fill.
+cudaError_t tma_map_3d_bf16(const void* ptr, int d0, long d1, long d2, long stride1_bytes, long stride2_bytes, int b0, int b1, int b2,
+                            CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaError_t e = get_encode();
+    if (e != cudaSuccess) return e;
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)stride1_bytes, (cuuint64_t)stride2_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 namespace {
 
 template <int BN, int EPI, typename TC, int SPLIT, int NSTG>

@@ -17,3 +17,6 @@ cudaError_t launch_gemm_tc_ln(const GemmArgs& g, const float* s_in, const float*
 // matrix [rows, cols] (row stride ld elements), box = box_rows x box_cols, optional 128-byte swizzle, zero OOB fill.
 cudaError_t tma_map_2d_bf16(const void* ptr, long rows, int cols, long ld, int box_rows, int box_cols, int swizzle128,
                             CUtensorMap* out);
+// 3-D variant (d0 contiguous, byte strides for d1 / d2), 128-byte swizzle; not cached.
+cudaError_t tma_map_3d_bf16(const void* ptr, int d0, long d1, long d2, long stride1_bytes, long stride2_bytes, int b0, int b1, int b2,
+                            CUtensorMap* out);
