@@ -105,6 +105,15 @@ TEXOCR_API int texocr_decoder_generate(texocr_handle* h, const int64_t* start_to
 TEXOCR_API int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, int32_t batch, int32_t max_len,
                     int64_t* out_ids, int32_t* n_steps, void* stream);
 
+/* replaces: the sampling branch of AutoRegressiveDecoder.generate (model/decoder.py:103-108) for every later
+ * texocr_generate / texocr_decoder_generate call on this handle: keep the k = int((1 - threshold) * vocab) largest
+ * logits (utils.py:85-91; threshold 0.9 -> k = 99 of 1000), p = softmax(kept / temp), one draw per row and step.
+ * The draw is the inverse CDF in vocabulary order at u = (x >> 8) * 2^-24 with x = word 0 of
+ * Philox4x32-10(key = seed, counter = (row, step, call, 0)), call = number of sampled generate calls since this
+ * function: reproducible and independent of how the batch is split; parity with torch.multinomial is
+ * distribution-level (tests/test_gpu_sampling.py).  temp <= 0 restores greedy decoding.  vocab <= 1024. */
+TEXOCR_API int texocr_set_sampling(texocr_handle* h, double temp, double threshold, uint64_t seed);
+
 /* replaces: AutoRegressiveDecoder.forward / OCRModel.forward loss (model/decoder.py:124-145):
  * mean cross-entropy (no ignore_index) of logits [rows, vocab] against targets int64 [rows]. */
 TEXOCR_API int texocr_cross_entropy(texocr_handle* h, const float* logits, const int64_t* targets, int64_t rows,
@@ -132,6 +141,11 @@ TEXOCR_API int texocr_set_option(texocr_handle* h, const char* name, int64_t val
 /* Debug tap: copy an internal activation of the last texocr_encode call to `out` (host or device).
  * name = "backbone" -> float32 [sum h_i*w_i, 1024] (NHWC pixels).  Returns element count or <0. */
 TEXOCR_API int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_t cap_elems);
+
+/* Test hook: one token-selection step (greedy or, after texocr_set_sampling, sampled) on device logits
+ * float32 [rows, vocab] with the given step / call counters; out_ids int64 [rows] (host or device). */
+TEXOCR_API int texocr_debug_sample_step(texocr_handle* h, const float* logits, int32_t rows, int32_t step, uint32_t call,
+                             int64_t* out_ids);
 
 /* Test hook: run one GEMM  C[M,N] = epi(A[M,K] . W[N,K]^T)  on device buffers through the engine's own kernels.
  * dt_a: 0 = fp32 operands (FFMA kernel), 1 = bf16 operands; use_tc != 0 selects the tcgen05 kernel (bf16 only);

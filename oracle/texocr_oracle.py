@@ -273,7 +273,7 @@ def generate_greedy_recompute(sd: SD, enc: torch.Tensor, max_len: int, bos: int 
 
 
 def generate_greedy_cached(sd: SD, enc: torch.Tensor, max_len: int, bos: int = 998, eos: Optional[int] = 997,
-                           gaps: Optional[list] = None, logits_out: Optional[list] = None) -> torch.Tensor:
+                           gaps: Optional[list] = None, logits_out: Optional[list] = None, select=None) -> torch.Tensor:
     """Same token sequence as ``generate_greedy_recompute`` while ``max_len <= decoder max_len``
     (token-identical in fp32), with per-layer K/V kept between steps and the encoder
     memory projected once.  Used where the O(T^2) reference loop would take minutes."""
@@ -318,7 +318,7 @@ def generate_greedy_cached(sd: SD, enc: torch.Tensor, max_len: int, bos: int = 9
                 x = F.layer_norm(x, (D,), g, b, 1e-5)
         x = F.layer_norm(x, (D,), sd["decoder.net.norm.weight"], sd["decoder.net.norm.bias"], 1e-5)
         logits = F.linear(x[:, 0], sd["decoder.net.to_logits.weight"], sd["decoder.net.to_logits.bias"])
-        tok = logits.argmax(dim=-1)
+        tok = logits.argmax(dim=-1) if select is None else select(logits, t)      # select: sampling (below)
         if gaps is not None:
             top2 = logits.topk(2, dim=-1).values
             gaps.append((top2[:, 0] - top2[:, 1]).clone())
@@ -339,6 +339,56 @@ def model_generate(sd: SD, src: torch.Tensor, max_len: int, bos: int = 998, eos:
         enc = encoder_forward(sd, src, kind)
         fn = generate_greedy_cached if cached else generate_greedy_recompute
         return fn(sd, enc, max_len, bos, eos, gaps)
+
+
+# ------------------------------------------------------------------------------------------------ sampling
+def topk_filter(logits: torch.Tensor, threshold: float = 0.9) -> torch.Tensor:
+    """utils.py:85-91: keep the k = int((1 - threshold) * vocab) largest logits of every row, -inf elsewhere
+    (k = 99 for threshold 0.9, vocab 1000: the product is 99.99999999999997 in double arithmetic)."""
+    k = int((1 - threshold) * logits.shape[-1])
+    val, ind = torch.topk(logits, k)
+    out = torch.full_like(logits, float("-inf"))
+    out.scatter_(1, ind, val)
+    return out
+
+
+def sample_probs(logits: torch.Tensor, temp: float, threshold: float = 0.9) -> torch.Tensor:
+    """model/decoder.py:104-107: the distribution torch.multinomial draws the next token from."""
+    return F.softmax(topk_filter(logits, threshold) / temp, dim=-1)
+
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al., SC'11), the counter-based generator of the CUDA path: 4 x uint32 out."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c0, c1, c2, c3 = (int(v) & MASK for v in ctr)
+    k0, k1 = (int(v) & MASK for v in key)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c3 ^ k1) & MASK, p0 & MASK
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c0, c1, c2, c3
+
+
+def philox_uniform(seed: int, row: int, step: int, call: int = 0) -> float:
+    """u in [0, 1) of (row, step) in sampled generate call number `call` (include/texocr.h, texocr_set_sampling)."""
+    x = philox4x32_10((row, step, call, 0), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))[0]
+    return (x >> 8) * (1.0 / 16777216.0)
+
+
+def sample_inverse_cdf(probs: torch.Tensor, u: float) -> int:
+    """First vocabulary index whose cumulative probability exceeds u * total (the CUDA path's draw)."""
+    c = torch.cumsum(probs.double(), dim=0)
+    idx = int(torch.searchsorted(c, torch.tensor(u * float(c[-1]), dtype=torch.float64), right=True))
+    return idx if idx < probs.numel() else int(torch.nonzero(probs > 0).flatten()[-1])      # rounding: last kept index
+
+
+def make_sampler(temp: float, threshold: float = 0.9, seed: int = 0, call: int = 0):
+    """`select` callback for generate_greedy_cached: the reference's top-k / temperature draw with the CUDA path's RNG."""
+    def select(logits: torch.Tensor, t: int) -> torch.Tensor:
+        probs = sample_probs(logits, temp, threshold)
+        return torch.tensor([sample_inverse_cdf(probs[r], philox_uniform(seed, r, t, call)) for r in range(logits.shape[0])],
+                            dtype=torch.long)
+    return select
 
 
 def batch_acc(pred: torch.Tensor, target: torch.Tensor, pad_token: int) -> float:

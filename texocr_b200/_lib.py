@@ -23,7 +23,7 @@ EXPORTS = (
     "texocr_create", "texocr_destroy", "texocr_last_error", "texocr_set_weight", "texocr_finalize_weights",
     "texocr_encode", "texocr_decoder_logits", "texocr_decoder_generate", "texocr_generate", "texocr_cross_entropy",
     "texocr_kernel_launches", "texocr_profile_enable", "texocr_profile_read", "texocr_set_option", "texocr_debug_read",
-    "texocr_debug_gemm", "texocr_debug_attn_decode",
+    "texocr_debug_gemm", "texocr_debug_attn_decode", "texocr_set_sampling", "texocr_debug_sample_step",
 )
 
 
@@ -69,6 +69,8 @@ def load_library() -> C.CDLL:
     lib.texocr_profile_enable.argtypes = [vp, i32]
     lib.texocr_profile_read.argtypes = [vp, C.POINTER(ProfileRow), i32]
     lib.texocr_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.texocr_set_sampling.argtypes = [vp, C.c_double, C.c_double, C.c_uint64]
+    lib.texocr_debug_sample_step.argtypes = [vp, vp, i32, i32, C.c_uint32, vp]
     lib.texocr_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
     lib.texocr_debug_read.restype = i64
     lib.texocr_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]
@@ -225,6 +227,18 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.texocr_set_option(self.h, name.encode(), int(value)))
+
+    def set_sampling(self, temp: float, threshold: float = 0.9, seed: int = 0):
+        """temp > 0: later generate calls sample like model/decoder.py:103-108 (top-k filter, softmax(/temp), one draw);
+        temp <= 0: greedy.  Draws are reproducible for a given seed."""
+        self._check(self.lib.texocr_set_sampling(self.h, float(temp), float(threshold), int(seed) & (2 ** 64 - 1)))
+
+    def debug_sample_step(self, logits: torch.Tensor, step: int = 0, call: int = 0) -> torch.Tensor:
+        """Test hook: the token-selection kernel on float32 device logits (rows, vocab) -> int64 (rows,)."""
+        logits = _f32c(logits)
+        out = torch.empty((logits.shape[0],), dtype=torch.int64, device=self.device)
+        self._check(self.lib.texocr_debug_sample_step(self.h, logits.data_ptr(), logits.shape[0], int(step), int(call), out.data_ptr()))
+        return out
 
     def debug_gemm(self, A, W, C, epi=0, bias=None, res=None, use_tc=True, A2=None, W2=None):
         """Test hook: C = epi(A @ W.T) through the engine's GEMM kernels (tensors on the device, row-major)."""

@@ -764,16 +764,18 @@ static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_t
 
 // ------------------------------------------------------------------------------------------------ decode step
 constexpr int MAX_BRANCH = 16;
+static int sampling_k(const texocr_handle* h);
 struct DecState {
-    int64_t* cur_tok; int* step; int* done_step; int* block_counter; int* seen;     // step/done/counter: [MAX_BRANCH]
+    int64_t* cur_tok; int* step; int* done_step; int* block_counter; unsigned* call_ctr; int* seen;     // step/done/counter: [MAX_BRANCH]
 };
-static size_t dec_state_bytes(int B) { return (size_t)B * 8 + 3 * MAX_BRANCH * 4 + (size_t)B * 4; }
+static size_t dec_state_bytes(int B) { return (size_t)B * 8 + (3 * MAX_BRANCH + 4) * 4 + (size_t)B * 4; }
 static DecState dec_state(texocr_handle* h, int B) {
     DecState d;
     char* p = (char*)h->dec_state.p;
     d.cur_tok = (int64_t*)p;
     int* ip = (int*)(p + (size_t)B * 8);
-    d.step = ip; d.done_step = ip + MAX_BRANCH; d.block_counter = ip + 2 * MAX_BRANCH; d.seen = ip + 3 * MAX_BRANCH;
+    d.step = ip; d.done_step = ip + MAX_BRANCH; d.block_counter = ip + 2 * MAX_BRANCH; d.call_ctr = (unsigned*)(ip + 3 * MAX_BRANCH);
+    d.seen = ip + 3 * MAX_BRANCH + 4;
     return d;
 }
 
@@ -882,9 +884,15 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
     aa.logits = lg; aa.B = rows; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>() + (size_t)row0 * tcap; aa.out_ld = tcap;
     aa.cur_tok = ds.cur_tok + row0; aa.step = step; aa.seen_eos = ds.seen + row0; aa.done_step = ds.done_step + branch;
     aa.block_counter = ds.block_counter + branch; aa.eos = eos;
+    if (h->samp_temp > 0.0) {
+        aa.topk = sampling_k(h); aa.inv_temp = (float)(1.0 / h->samp_temp); aa.seed = h->samp_seed; aa.row_base = row0; aa.call_ctr = ds.call_ctr;
+    }
     LAUNCH(KC_DEC_ARGMAX, 1, (double)rows * c.vocab_size * 4, 0.0, launch_argmax_step(aa, st));
     return 0;
 }
+
+// k of the reference's top-k filter: int((1 - threshold) * vocab) in double arithmetic, as Python evaluates it (utils.py:87)
+static int sampling_k(const texocr_handle* h) { return (int)((1.0 - h->samp_threshold) * (double)h->cfg.vocab_size); }
 
 struct BranchPlan { int n; int row0[MAX_BRANCH]; int rows[MAX_BRANCH]; };
 static BranchPlan plan_branches(texocr_handle* h, int B) {
@@ -1018,8 +1026,12 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     DecState ds = dec_state(h, B);
     CK(cudaMemsetAsync((char*)h->dec_state.p + (size_t)B * 8, 0, dec_state_bytes(B) - (size_t)B * 8, st));
     CK(cudaMemcpyAsync(ds.cur_tok, d_start, (size_t)B * 8, cudaMemcpyDeviceToDevice, st));
+    if (h->samp_temp > 0.0) {      // every sampled generate call draws from a fresh Philox sub-stream
+        h->h_poll[3 * MAX_BRANCH] = (int)h->samp_calls++;
+        CK(cudaMemcpyAsync(ds.call_ctr, &h->h_poll[3 * MAX_BRANCH], 4, cudaMemcpyHostToDevice, st));
+    }
     {
-        if (h->decode_mega && h->dt == DT_BF16 && decode_mega_supported(B, c.dec_layers, c.vocab_size, nullptr)) {
+        if (h->decode_mega && h->samp_temp <= 0.0 && h->dt == DT_BF16 && decode_mega_supported(B, c.dec_layers, c.vocab_size, nullptr)) {
             const int groups = decode_mega_groups(B);
             if (groups <= MAX_BRANCH) return run_generate_mega(h, ds, eos, d_enc_off, sum_s, B, tcap, groups, out_ids, n_steps, st);
         }
@@ -1041,7 +1053,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     for (int i = 0; i < bp.n; ++i) bst[i] = (bp.n == 1 || !graph_ok) ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
     if (graph_ok) {
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
-                         h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
+                         h->gkey.samp == (h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0) && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
             drop_graphs(h);
             const int64_t before = h->launches;
@@ -1056,6 +1068,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
             h->graph = h->bgraph[0]; h->graph_exec = h->bgraph_exec[0];
             h->gkey.kernels = (int)(h->launches - before) / bp.n;
             h->launches = before;        // capture does not execute
+            h->gkey.samp = h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0;
             h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
             h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv_hm.p; h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
         }
@@ -1410,6 +1423,46 @@ int texocr_profile_read(texocr_handle* h, texocr_profile_row* rows, int32_t cap)
     }
     for (int k = 0; k < KC_COUNT; ++k) { h->prof_ms[k] = h->prof_bytes[k] = h->prof_flops[k] = 0; h->prof_n[k] = 0; }
     return n;
+}
+
+int texocr_set_sampling(texocr_handle* h, double temp, double threshold, uint64_t seed) {
+    if (!h) return TEXOCR_ERR_ARG;
+    if (temp > 0.0) {
+        if (!(threshold >= 0.0 && threshold < 1.0)) return fail(h, TEXOCR_ERR_ARG, "sampling threshold must be in [0, 1)");
+        if (h->cfg.vocab_size > 1024) return fail(h, TEXOCR_ERR_ARG, "sampling supports vocab_size <= 1024");
+        const int k = (int)((1.0 - threshold) * (double)h->cfg.vocab_size);
+        if (k < 1) return fail(h, TEXOCR_ERR_ARG, "top-k filter keeps k = %d logits: the reference's softmax would be all-NaN", k);
+    }
+    h->samp_temp = temp > 0.0 ? temp : 0.0; h->samp_threshold = threshold; h->samp_seed = seed; h->samp_calls = 0;
+    drop_graphs(h);
+    return 0;
+}
+
+int texocr_debug_sample_step(texocr_handle* h, const float* logits, int32_t rows, int32_t step, uint32_t call, int64_t* out_ids) {
+    if (!h || !logits || !out_ids || rows <= 0 || step < 0) return TEXOCR_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    const int V = h->cfg.vocab_size;
+    char* scratch = nullptr;
+    const size_t nb = (size_t)rows * 8 * 2 + (size_t)rows * 4 + 64;
+    CK(cudaMalloc(&scratch, nb));
+    CK(cudaMemset(scratch, 0, nb));
+    ArgmaxArgs aa{};
+    aa.logits = logits; aa.B = rows; aa.V = V; aa.out_ids = (int64_t*)scratch; aa.out_ld = 1;
+    aa.cur_tok = (int64_t*)(scratch + (size_t)rows * 8);
+    int* ip = (int*)(scratch + (size_t)rows * 16);
+    aa.step = ip; aa.done_step = ip + 1; aa.block_counter = ip + 2; aa.call_ctr = (unsigned*)(ip + 3); aa.seen_eos = ip + 8;
+    aa.eos = -1;
+    if (h->samp_temp > 0.0) { aa.topk = sampling_k(h); aa.inv_temp = (float)(1.0 / h->samp_temp); aa.seed = h->samp_seed; aa.row_base = 0; }
+    const int64_t off = -(int64_t)step;        // the kernel writes out_ids[row * out_ld + step]
+    aa.out_ids += off;
+    CK(cudaMemcpy(ip, &step, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ip + 3, &call, 4, cudaMemcpyHostToDevice));
+    cudaError_t e = launch_argmax_step(aa, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out_ids, scratch, (size_t)rows * 8, is_device_ptr(out_ids) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost);
+    cudaFree(scratch);
+    if (e != cudaSuccess) return fail_cuda(h, e, "debug_sample_step", __LINE__);
+    return 0;
 }
 
 int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {

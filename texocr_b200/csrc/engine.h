@@ -92,7 +92,7 @@ struct texocr_handle {
     cudaGraph_t bgraph[16] = {nullptr}; cudaGraphExec_t bgraph_exec[16] = {nullptr};   // one single-step graph per branch
     cudaEvent_t poll_ev[2][16] = {{nullptr}};
     int stagger_us = 30;                        // start offset between consecutive branches
-    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; } gkey;
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; } gkey;
 
     // ---- instrumentation
     int64_t launches = 0;
@@ -109,6 +109,8 @@ struct texocr_handle {
     bool fuse_ln = false;    // decode step: LayerNorms computed inside the consuming tcgen05 GEMM (bf16 tier)
     bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate
     int dbg_skip = 0;        // timing experiments only: 1 self-attn, 2 cross-attn, 4 LayerNorms, 8 GEMMs (results are garbage)
+    // sampling (texocr_set_sampling): temp <= 0 = greedy
+    double samp_temp = 0.0, samp_threshold = 0.9; uint64_t samp_seed = 0; uint32_t samp_calls = 0;
     int num_sms = 148;
     int attn_ctas_per_sm = 4;     // persistent decode-attention CTAs per SM (64 KB ring each); leaves room for the GEMM CTAs of other branches
 };

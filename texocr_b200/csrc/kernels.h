@@ -106,6 +106,9 @@ struct ArgmaxArgs {
     int* done_step;                      // first step count at which all rows had an EOS (0 = not yet)
     int* block_counter;                  // scratch, zero-initialised
     int eos;
+    // sampling (model/decoder.py:103-108): topk > 0 replaces the argmax by a draw from softmax(top-k logits / temp);
+    // u = Philox4x32-10(key = seed, counter = (row_base + row, step, *call_ctr, 0)); requires V <= 1024
+    int topk; float inv_temp; unsigned long long seed; int row_base; const unsigned* call_ctr;
 };
 cudaError_t launch_argmax_step(const ArgmaxArgs& a, cudaStream_t st);
 cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_t rows, int V, float* row_loss,

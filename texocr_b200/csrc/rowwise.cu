@@ -72,13 +72,102 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict
     store8(xn + (size_t)row * D + col, v);
 }
 
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so a draw depends only on (seed, row, step)
+TX_DEVINL uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * ctr.x, p1 = (unsigned long long)0xCD9E8D57u * ctr.z;
+        ctr = make_uint4((uint32_t)(p1 >> 32) ^ ctr.y ^ key.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ ctr.w ^ key.y, (uint32_t)p0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+TX_DEVINL uint32_t order_key(float v) {          // monotonic float -> uint (larger float, larger key)
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// One draw per row (one warp): top-k filter (k-th largest found by a bitwise radix descent over the warp's <= 1024 values),
+// p = exp((v - max) / temp) over the kept values, inverse CDF in vocabulary order at u.  model/decoder.py:103-108, utils.py:85-91.
+TX_DEVINL int sample_row(const float* __restrict__ l, int V, int k, float inv_temp, float u, int lane) {
+    const int per = (V + 31) >> 5, i0 = lane * per;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (i < per && i0 + i < V) ? __ldcg(l + i0 + i) : -INFINITY;
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cnt += (i < per && i0 + i < V && order_key(v[i]) >= cand) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (cnt >= k) prefix = cand;
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+    mx = warp_max(mx);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const bool keep = i < per && i0 + i < V && order_key(v[i]) >= prefix;
+        v[i] = keep ? expf((v[i] - mx) * inv_temp) : 0.f;
+        part += v[i];
+    }
+    float incl = part;                            // inclusive scan of the lane sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const float total = __shfl_sync(0xffffffffu, incl, 31);
+    const float target = u * total;
+    const unsigned hit = __ballot_sync(0xffffffffu, incl > target && part > 0.f);
+    int tok = -1;
+    if (hit) {
+        const int L = __ffs(hit) - 1;
+        if (lane == L) {
+            float c = incl - part;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                c += v[i];
+                if (tok < 0 && v[i] > 0.f && c > target) tok = i0 + i;
+            }
+            if (tok < 0) {                        // rounding: the lane's last kept value
+#pragma unroll
+                for (int i = 0; i < 32; ++i) if (v[i] > 0.f) tok = i0 + i;
+            }
+        }
+        tok = __shfl_sync(0xffffffffu, tok, L);
+    } else {                                      // target rounded up to the total: last kept index of the row
+        int last = -1;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (v[i] > 0.f) last = i0 + i;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        tok = last < 0 ? 0 : last;
+    }
+    return tok;
+}
+
 __global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
     __shared__ int s_last;
     pdl_launch_dependents();
     pdl_wait();
     const int t = ldcg_i32(a.step);
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row < a.B) {
+    if (row < a.B && a.topk > 0) {
+        const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(a.row_base + row), (uint32_t)t, a.call_ctr ? __ldcg(a.call_ctr) : 0u, 0u),
+                                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        const float u = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
+        const int tok = sample_row(a.logits + (size_t)row * a.V, a.V, a.topk, a.inv_temp, u, lane);
+        if (lane == 0) {
+            a.out_ids[(size_t)row * a.out_ld + t] = tok;
+            a.cur_tok[row] = tok;
+            if (a.eos >= 0 && tok == a.eos) a.seen_eos[row] = 1;
+        }
+    } else if (row < a.B) {
         const float* l = a.logits + (size_t)row * a.V;
         float best = -INFINITY;
         int bi = 0x7fffffff;

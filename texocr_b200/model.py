@@ -95,7 +95,15 @@ class _Decoder(_Holder):
         if start_tokens.shape[1] != 1:
             raise NotImplementedError("texocr_b200 generates from a single start column (the BOS column of "
                                       "model/ocr_model.py:57); longer prompts are not implemented")
-        out = self._owner().decoder_generate(start_tokens, eos_tok, enc, max_len)
+        sample = bool(kwargs.get("sample", False))
+        eng = self._owner().engine()
+        if sample:
+            eng.set_sampling(temp, 0.9, int(kwargs.get("seed", 0)))
+        try:
+            out = self._owner().decoder_generate(start_tokens, eos_tok, enc, max_len)
+        finally:
+            if sample:
+                eng.set_sampling(0.0)
         return out.squeeze(0) if squeeze else out
 
     def forward(self, x, mask=None, return_out=False, **kwargs):
@@ -203,10 +211,19 @@ class OCRModel(nn.Module):
         return self.decoder(trg, enc=enc, mask=trg_mask)       # return_out is accepted and ignored, as in the reference
 
     @torch.no_grad()
-    def generate(self, src, max_len: int, temp: float = 0.3):
-        """Greedy decode; (B, n_steps) int64 on the model's device.  ``src`` may also be a list of (1,H,W)
-        images of different sizes (ragged batch) -- an extension over the reference's same-size batches."""
-        return self.engine().generate(src, max_len)
+    def generate(self, src, max_len: int, temp: float = 0.3, sample: bool = False, seed: int = 0):
+        """(B, n_steps) int64 on the model's device.  Greedy by default (the temp -> 0 limit of model/decoder.py:103-108,
+        the path BASELINE.json measures); ``sample=True`` draws like the reference (top-k 0.9 filter, softmax(/temp),
+        one multinomial draw per step) from a Philox stream seeded with ``seed``.  ``src`` may also be a list of
+        (1,H,W) images of different sizes (ragged batch) -- an extension over the reference's same-size batches."""
+        eng = self.engine()
+        if not sample:
+            return eng.generate(src, max_len)
+        eng.set_sampling(temp, 0.9, seed)
+        try:
+            return eng.generate(src, max_len)
+        finally:
+            eng.set_sampling(0.0)
 
 
 def create_model(config: dict, encoder_kind: str = "hybrid", precision: Optional[str] = None) -> OCRModel:
