@@ -271,3 +271,27 @@ def test_input_validation_raises(m32):
         m32.encoder(torch.zeros(1, 1, 64, 1024, device="cuda"))
     with pytest.raises(RuntimeError, match="max_length"):
         m32.generate(torch.zeros(1, 1, 64, 384, device="cuda"), 257)
+
+
+def test_packed_blob_and_resized_positional_table(tmp_path, sd, dims, m16):
+    """SURVEY.md 8(f3): the bf16 tier built from a 'mixed' blob is bit-identical to the one built from the fp32 state dict;
+    a checkpoint with a longer positional table (model/ocr_model.py:82-90) lifts the max_len limit accordingly."""
+    import texocr_b200
+    from texocr_b200 import checkpoint
+    path = str(tmp_path / "w.bin")
+    checkpoint.save_blob(sd, dims, path, dtype="mixed")
+    back, d2 = checkpoint.load_blob(path)
+    cfg = spec.default_config(max_length=d2.max_length)
+    cfg["device"] = "cuda:0"
+    mb = texocr_b200.create_model(cfg, precision="bf16")
+    mb.load_state_dict(back)
+    img = synth.synth_images(16, 64, 384, seed=77).cuda()
+    assert torch.equal(mb.generate(img, 48), m16.generate(img, 48))
+    sd2 = dict(sd)
+    gen = torch.Generator().manual_seed(3)
+    sd2[checkpoint.POS_KEY] = torch.cat((sd[checkpoint.POS_KEY], torch.randn(44, 256, generator=gen) * 0.02), 0)     # 300 rows
+    checkpoint.load_state_dict_resizing(mb, sd2)
+    out = mb.generate(img, 290)
+    assert out.shape == (16, 290) and torch.equal(out[:, :48], m16.generate(img, 48))
+    with pytest.raises(RuntimeError, match="max_length"):
+        m16.generate(img, 290)

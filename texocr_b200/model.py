@@ -12,9 +12,10 @@ Same names, argument meaning and error behaviour as the reference for the infere
 
 The module tree only HOLDS parameters under the reference's state_dict names, so
 ``state_dict()/load_state_dict()/to()/eval()`` behave as a caller of the reference expects; all
-arithmetic happens in libtexocr_b200.so.  Deliberate deviations: ``generate`` is greedy
-(argmax -- ``temp`` is accepted and ignored), inputs must be multiples of 16 with H<=160, W<=1008,
-``max_len <= config['max_length']``, and there is no CPU execution path.
+arithmetic happens in libtexocr_b200.so.  Deliberate deviations: ``generate`` is greedy by
+default (argmax; ``sample=True`` selects the reference's top-k / temperature draw with a reproducible Philox stream),
+inputs must be multiples of 16 with H<=160, W<=1008, ``max_len <= config['max_length']``, and there is no CPU
+execution path.
 """
 from __future__ import annotations
 
@@ -165,6 +166,19 @@ class OCRModel(nn.Module):
             self._engine = Engine(self.dims, self.state_dict(), self.precision, idx)
             self._engine_key = key
         return self._engine
+
+    def resize_pos_embedding(self, new_len: int):
+        """TeXOCRWrapper.__init__ (model/ocr_model.py:82-90): a checkpoint whose decoder positional table has another
+        length than config['max_length'] replaces the table; the engine is rebuilt for that length on next use."""
+        import dataclasses
+        if new_len == self.dims.max_length:
+            return self
+        key = "decoder.net.pos_embedding.embedding.weight"
+        old = self.state_dict()[key]
+        _attach(self, key, nn.Parameter(torch.zeros((new_len, old.shape[1]), dtype=old.dtype, device=old.device), requires_grad=False))
+        self.dims = dataclasses.replace(self.dims, max_length=int(new_len))
+        self.decoder.net.max_len = int(new_len)
+        return self
 
     def set_precision(self, precision: str):
         self.precision = precision
