@@ -105,6 +105,15 @@ TEXOCR_API int texocr_decoder_generate(texocr_handle* h, const int64_t* start_to
 TEXOCR_API int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, int32_t batch, int32_t max_len,
                     int64_t* out_ids, int32_t* n_steps, void* stream);
 
+/* replaces: the deterministic part of img_transform (data_wrangling/dataset.py:365-371: ToTensor -> Grayscale(1) ->
+ * Invert; the RandomAffine in front of it is train-time noise and is not applied) for a ragged batch: uint8 images,
+ * H x W x C interleaved with C = 1 or 3, concatenated in `pixels`; hwc int32 [batch][3] = (H, W, C).  Output: float32
+ * images 1 - gray/255 packed like texocr_encode / texocr_generate take them, every image zero-padded (white background)
+ * at the right / bottom to a multiple of pad_multiple (16 = the encoder's patch grid; 1 = none); out_hw int32 [batch][2].
+ * pixels / out_images may be host or device pointers; bit-exact with torchvision on the CPU.  Needs no weights. */
+TEXOCR_API int texocr_preprocess_u8(texocr_handle* h, const uint8_t* pixels, const int32_t* hwc, int32_t batch,
+                         int32_t pad_multiple, float* out_images, int32_t* out_hw, void* stream);
+
 /* replaces: the sampling branch of AutoRegressiveDecoder.generate (model/decoder.py:103-108) for every later
  * texocr_generate / texocr_decoder_generate call on this handle: keep the k = int((1 - threshold) * vocab) largest
  * logits (utils.py:85-91; threshold 0.9 -> k = 99 of 1000), p = softmax(kept / temp), one draw per row and step.

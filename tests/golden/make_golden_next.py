@@ -120,6 +120,41 @@ def main():
     js["process_out"] = [process_output(s) for s in js["process_in"]]
     with open(os.path.join(HERE, "golden_tokenizer_v1.json"), "w") as f:
         json.dump(js, f)
+    # ---------------------------------------------------------------- f4: input side
+    from PIL import Image
+    from torchvision import transforms
+    from TeXOCR.data_wrangling.dataset import BucketBatchSampler, img_transform
+    det = transforms.Compose(img_transform.transforms[1:])          # ToTensor -> Grayscale(1) -> Invert (RandomAffine skipped)
+    assert [type(t).__name__ for t in det.transforms] == ["ToTensor", "Grayscale", "Invert"]
+    prep = {}
+    irng = np.random.Generator(np.random.PCG64(17))
+    for i, (h, w, c) in enumerate([(37, 50, 3), (64, 384, 1), (48, 200, 3), (16, 16, 1)]):
+        arr = irng.integers(0, 256, size=(h, w, c), dtype=np.uint8)
+        pil = Image.fromarray(arr[..., 0], mode="L") if c == 1 else Image.fromarray(arr, mode="RGB")
+        prep[f"img{i}_u8"] = arr
+        prep[f"img{i}_f32"] = det(pil).numpy()
+    class FakeSet:                                                   # what BucketBatchSampler reads from a dataset
+        def __init__(self, sizes):
+            from collections import defaultdict
+            self.sizes = defaultdict(list)
+            for i, s_ in enumerate(sizes):
+                self.sizes[s_].append(i)
+        def __len__(self):
+            return sum(len(v) for v in self.sizes.values())
+    size_pool = [(384, 64), (208, 48), (1008, 160), (128, 32)]
+    sizes = [size_pool[int(v)] for v in irng.integers(0, 4, size=41)]
+    prep["bucket_sizes"] = np.array(sizes)
+    for name, kw in {"plain": dict(keep_small=True, shuffle=False), "drop": dict(keep_small=False, shuffle=False),
+                     "shuf": dict(keep_small=True, shuffle=True)}.items():
+        smp = BucketBatchSampler(FakeSet(sizes), batch_size=4, drop_last=False, seed=3, **kw)
+        for epoch in range(2):
+            batches = list(iter(smp))
+            flat = np.full((len(batches), 4), -1, dtype=np.int64)
+            for bi, b in enumerate(batches):
+                flat[bi, :len(b)] = b
+            prep[f"bucket_{name}_e{epoch}"] = flat
+        prep[f"bucket_{name}_len"] = np.array(len(smp))
+    np.savez_compressed(os.path.join(HERE, "golden_prep_v1.npz"), **prep)
     print("wrote golden_next_v1.npz", {k: v.shape for k, v in out.items()})
     print("tokenizer vocab", len(vocab), "latex rows", [len(r) for r in enc_rows])
     print("sampled tokens row0", toks[0, :16].tolist(), "min margin", margins.min())

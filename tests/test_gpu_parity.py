@@ -295,3 +295,28 @@ def test_packed_blob_and_resized_positional_table(tmp_path, sd, dims, m16):
     assert out.shape == (16, 290) and torch.equal(out[:, :48], m16.generate(img, 48))
     with pytest.raises(RuntimeError, match="max_length"):
         m16.generate(img, 290)
+
+
+def test_preprocess_u8_bit_exact_with_torchvision_pipeline(m32):
+    """texocr_preprocess_u8 == ToTensor -> Grayscale(1) -> Invert of the reference (golden from torchvision),
+    bit for bit, for a ragged RGB / L batch, host and device inputs, with the zero padding to the 16-pixel grid."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_prep_v1.npz"))
+    imgs = [torch.from_numpy(g[f"img{i}_u8"]) for i in range(4)]
+    refs = [torch.from_numpy(g[f"img{i}_f32"]) for i in range(4)]
+    eng = m32.engine()
+    for src in (imgs, [t.cuda() for t in imgs]):
+        exact = eng.preprocess_u8(src, pad_multiple=1)
+        for o, r in zip(exact, refs):
+            assert o.shape == r.shape and torch.equal(o.cpu(), r)
+        padded = eng.preprocess_u8(src, pad_multiple=16)
+        for o, r in zip(padded, refs):
+            H, W = r.shape[1:]
+            assert o.shape[1] % 16 == 0 and o.shape[2] % 16 == 0 and o.shape[1] - H < 16 and o.shape[2] - W < 16
+            assert torch.equal(o[:, :H, :W].cpu(), r)
+            assert float(o[:, H:, :].abs().sum()) == 0.0 and float(o[:, :, W:].abs().sum()) == 0.0
+    # straight into the path: a ragged batch of preprocessed images decodes
+    out = m32.generate(eng.preprocess_u8(imgs, 16), 8)
+    assert out.shape == (4, 8)
+    with pytest.raises(RuntimeError, match="channels"):
+        eng.preprocess_u8([torch.zeros(16, 16, 4, dtype=torch.uint8)])

@@ -23,7 +23,7 @@ EXPORTS = (
     "texocr_create", "texocr_destroy", "texocr_last_error", "texocr_set_weight", "texocr_finalize_weights",
     "texocr_encode", "texocr_decoder_logits", "texocr_decoder_generate", "texocr_generate", "texocr_cross_entropy",
     "texocr_kernel_launches", "texocr_profile_enable", "texocr_profile_read", "texocr_set_option", "texocr_debug_read",
-    "texocr_debug_gemm", "texocr_debug_attn_decode", "texocr_set_sampling", "texocr_debug_sample_step",
+    "texocr_debug_gemm", "texocr_debug_attn_decode", "texocr_set_sampling", "texocr_debug_sample_step", "texocr_preprocess_u8",
 )
 
 
@@ -70,6 +70,7 @@ def load_library() -> C.CDLL:
     lib.texocr_profile_read.argtypes = [vp, C.POINTER(ProfileRow), i32]
     lib.texocr_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.texocr_set_sampling.argtypes = [vp, C.c_double, C.c_double, C.c_uint64]
+    lib.texocr_preprocess_u8.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     lib.texocr_debug_sample_step.argtypes = [vp, vp, i32, i32, C.c_uint32, vp]
     lib.texocr_debug_read.argtypes = [vp, C.c_char_p, vp, i64]
     lib.texocr_debug_read.restype = i64
@@ -227,6 +228,32 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         self._check(self.lib.texocr_set_option(self.h, name.encode(), int(value)))
+
+    def preprocess_u8(self, images: Sequence[torch.Tensor], pad_multiple: int = 16) -> List[torch.Tensor]:
+        """uint8 images (H, W) / (H, W, 1) / (H, W, 3), host or device -> list of float32 (1, Hp, Wp) device tensors
+        (ToTensor -> Grayscale -> Invert of data_wrangling/dataset.py:365-371, zero-padded to multiples of pad_multiple)."""
+        flat, hwc = [], []
+        for im in images:
+            im = torch.as_tensor(im)
+            if im.dtype != torch.uint8 or im.ndim not in (2, 3):
+                raise ValueError("preprocess_u8 takes uint8 images of shape (H, W) or (H, W, C)")
+            c = 1 if im.ndim == 2 else im.shape[2]
+            hwc += [im.shape[0], im.shape[1], c]
+            flat.append(im.reshape(-1))
+        dev = all(t.is_cuda for t in flat)
+        buf = torch.cat([t if dev else t.cpu() for t in flat]).contiguous()
+        B = len(images)
+        pm = int(pad_multiple)
+        sizes = [((hwc[3 * b] + pm - 1) // pm * pm, (hwc[3 * b + 1] + pm - 1) // pm * pm) for b in range(B)]
+        out = torch.empty((sum(h * w for h, w in sizes),), dtype=torch.float32, device=self.device)
+        out_hw = (C.c_int32 * (2 * B))()
+        self._check(self.lib.texocr_preprocess_u8(self.h, buf.data_ptr(), _i32_array(hwc), B, pm, out.data_ptr(), out_hw, self._stream()))
+        res, off = [], 0
+        for b in range(B):
+            h, w = out_hw[2 * b], out_hw[2 * b + 1]
+            res.append(out[off:off + h * w].view(1, h, w))
+            off += h * w
+        return res
 
     def set_sampling(self, temp: float, threshold: float = 0.9, seed: int = 0):
         """temp > 0: later generate calls sample like model/decoder.py:103-108 (top-k filter, softmax(/temp), one draw);

@@ -1177,7 +1177,7 @@ void texocr_destroy(texocr_handle* h) {
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
                       &h->proj_out, &h->patch_cols, &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
                       &h->enc_out, &h->enc_a, &h->crosskv, &h->crosskv_hm, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
-                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg};
+                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg, &h->prep_meta, &h->prep_in, &h->prep_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);
@@ -1372,6 +1372,49 @@ int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, in
     if ((r = run_encoder(h, (const float*)d_img, g, st))) return r;
     if ((r = run_crosskv(h, h->enc_out.as<float>(), h->dt == DT_F32 ? nullptr : h->enc_a.p, g.ntok, st))) return r;
     return run_generate(h, h->ids_stage.as<int64_t>(), h->cfg.eos_token, g.d_tok_off, g.max_tok, (double)g.ntok, batch, max_len, out_ids, n_steps, st);
+}
+
+int texocr_preprocess_u8(texocr_handle* h, const uint8_t* pixels, const int32_t* hwc, int32_t batch, int32_t pad_multiple,
+                         float* out_images, int32_t* out_hw, void* stream) {
+    if (!h) return TEXOCR_ERR_ARG;
+    if (!pixels || !hwc || !out_images || !out_hw || batch <= 0 || pad_multiple < 1) return fail(h, TEXOCR_ERR_ARG, "bad argument to texocr_preprocess_u8");
+    CK(cudaSetDevice(h->device));
+    StreamHop hop__(h, stream);
+    cudaStream_t st = hop__.work;
+    // meta block: long in_off[B] | long out_off[B] | int hwc[3B] | int out_hw[2B]
+    std::vector<long> offs((size_t)2 * batch);
+    std::vector<int> ohw((size_t)2 * batch);
+    long in_bytes = 0, out_elems = 0, max_out = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int H = hwc[3 * b], W = hwc[3 * b + 1], C = hwc[3 * b + 2];
+        if (H <= 0 || W <= 0) return fail(h, TEXOCR_ERR_ARG, "image %d: bad size %d x %d", b, H, W);
+        if (C != 1 && C != 3) return fail(h, TEXOCR_ERR_ARG, "image %d: %d channels; Grayscale (torchvision) takes 1 or 3", b, C);
+        const int Hp = (H + pad_multiple - 1) / pad_multiple * pad_multiple, Wp = (W + pad_multiple - 1) / pad_multiple * pad_multiple;
+        offs[b] = in_bytes; offs[batch + b] = out_elems;
+        ohw[2 * b] = Hp; ohw[2 * b + 1] = Wp;
+        in_bytes += (long)H * W * C; out_elems += (long)Hp * Wp;
+        max_out = std::max(max_out, (long)Hp * Wp);
+    }
+    const size_t meta_bytes = (size_t)batch * (2 * sizeof(long) + 5 * sizeof(int));
+    ENSURE(h->prep_meta, meta_bytes);
+    char* mp = (char*)h->prep_meta.p;
+    CK(cudaMemcpyAsync(mp, offs.data(), (size_t)2 * batch * sizeof(long), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mp + (size_t)2 * batch * sizeof(long), hwc, (size_t)3 * batch * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(mp + (size_t)2 * batch * sizeof(long) + (size_t)3 * batch * sizeof(int), ohw.data(), (size_t)2 * batch * sizeof(int), cudaMemcpyHostToDevice, st));
+    int r;
+    const void* d_in = nullptr;
+    if ((r = to_device(h, pixels, (size_t)in_bytes, h->prep_in, &d_in, st))) return r;
+    float* d_out = out_images;
+    const bool out_dev = is_device_ptr(out_images);
+    if (!out_dev) { ENSURE(h->prep_out, (size_t)out_elems * 4); d_out = h->prep_out.as<float>(); }
+    const long* d_off = (const long*)mp;
+    const int* d_hwc = (const int*)(mp + (size_t)2 * batch * sizeof(long));
+    LAUNCH(KC_MISC, 1, (double)in_bytes + (double)out_elems * 4, 0.0,
+           launch_preprocess_u8((const uint8_t*)d_in, d_off, d_hwc, d_off + batch, d_hwc + 3 * batch, d_out, batch, max_out, st));
+    if (!out_dev) { if ((r = from_device(h, out_images, d_out, (size_t)out_elems * 4, st))) return r; }
+    CK(cudaStreamSynchronize(st));        // the host vectors above are staged from pageable memory
+    memcpy(out_hw, ohw.data(), (size_t)2 * batch * sizeof(int));
+    return 0;
 }
 
 int texocr_cross_entropy(texocr_handle* h, const float* logits, const int64_t* targets, int64_t rows, float* loss_out, void* stream) {

@@ -81,6 +81,7 @@ struct texocr_handle {
     DevBuf dec_state;                          // int64 cur_tok[B] | int32 step, done_step, block_counter, pad | int32 seen[B]
     DevBuf out_ids;                            // int64 [B, max_len]
     DevBuf mega_dbg;
+    DevBuf prep_meta, prep_in, prep_out;       // texocr_preprocess_u8 staging
     DevBuf mega_part;                          // cluster-persistent decode kernel: per-CTA argmax partials [B][16] (float | int)
     int* h_poll = nullptr;                     // pinned: done_step polls
     int last_backbone_pixels = 0;

@@ -81,6 +81,11 @@ cudaError_t launch_assemble_tokens(const float* proj /*[P4,256]*/, const float* 
                                    const int* img_off, const int* img_hw, const int* tok_off, int nimg, int total_tok,
                                    cudaStream_t st);
 
+// ---- input side (preprocess.cu): uint8 H x W x C (C = 1 or 3, interleaved) images at in + in_off[b] -> float32 (Hp, Wp) at
+// out + out_off[b]: 1 - gray / 255, zero outside the source image.  hwc = [B][3] (H, W, C), out_hw = [B][2] (Hp, Wp).
+cudaError_t launch_preprocess_u8(const uint8_t* in, const long* in_off, const int* hwc, const long* out_off, const int* out_hw,
+                                 float* out, int nimg, long max_out_pixels, cudaStream_t st);
+
 // ---- row-wise kernels (rowwise.cu)
 struct Ln2Args {
     const float* in; int rows;
