@@ -155,6 +155,58 @@ def run_reference_arm(args, rank: int):
 
 
 # ----------------------------------------------------------------------------- the B200 arm
+def measure_next_rows(model, img_dev, peaks, stream):
+    """SURVEY.md section 8f rows measured next to the headline (not part of the timed region): sampled generate, the
+    GPU image transform against the HBM roofline, the host detokeniser."""
+    import time
+    out = {}
+    B = img_dev.shape[0]
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(lambda: model.generate(img_dev, MAX_LEN, temp=0.3, sample=True, seed=1), 2)
+    out["sampled_generate"] = {"value": B / (ms / 1e3), "unit": UNIT, "ms": ms,
+                               "workload": f"same as the headline with top-k(0.9)/temp 0.3 sampling (model/decoder.py:103-108), batch {B}"}
+    # image transform: 512 RGB uint8 images 64x384 resident on the device -> float32; bytes = 3 read + 4 written per pixel
+    u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=img_dev.device)
+    lst = [u for u in u8]
+    eng = model.engine()
+    ms = timed(lambda: eng.preprocess_u8(lst, 16), 5)
+    eng.profile_enable(True)
+    eng.preprocess_u8(lst, 16)
+    rows = {r["name"]: r for r in eng.profile_read()}
+    eng.profile_enable(False)
+    k_ms = rows.get("misc", {}).get("ms", float("nan"))
+    nbytes = B * H * W * 7
+    out["preprocess"] = {"value": B / (ms / 1e3), "unit": "images/s", "ms_call": ms, "kernel_ms": k_ms,
+                         "kernel_gbs": nbytes / (k_ms / 1e3) / 1e9, "frac_of_hbm_peak": nbytes / (k_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                         "workload": f"{B} RGB uint8 {H}x{W} images on the device -> float32 (ToTensor/Grayscale/Invert); the call "
+                                     "time includes the Python-side concatenation of the image list"}
+    # detokeniser on the host: a synthetic 1k byte-pair vocabulary, (B, MAX_LEN) ids with an EOS per row
+    from texocr_b200.detok import Detokenizer
+    merges = [(i % 256, (i * 7) % 256, 256 + i) for i in range(741)]
+    tok = Detokenizer.from_merges(merges, {"<PAD>": 999, "<BOS>": 998, "<EOS>": 997})
+    ids = torch.randint(32, 997, (B, MAX_LEN))
+    ids[:, MAX_LEN - 8] = 997
+    t0 = time.perf_counter()
+    for _ in range(3):
+        texts = tok.decode_batch(ids, eos_token=997)
+    dt = (time.perf_counter() - t0) / 3
+    out["detokenise"] = {"value": B / dt, "unit": "strings/s", "ms": dt * 1e3, "cores": 1,
+                         "workload": f"{B} rows x {MAX_LEN - 8} tokens -> text + process_output, host Python"}
+    assert len(texts) == B
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -303,8 +355,10 @@ def main():
                    "workload": "BASELINE configs[1]: 256 images, H=64, widths 128..1008 (multiples of 16), one ragged batch",
                    "algorithmic_tflops": enc_flops / (enc_ms / 1e3) / 1e12,
                    "frac_of_bf16_peak": enc_flops / (enc_ms / 1e3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])}
+        next_rows = measure_next_rows(model, img_dev, peaks, stream)
     else:
         encoder = None
+        next_rows = None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -327,7 +381,7 @@ def main():
                    "parallelism": f"dp{world} (independent shards, token-id all_gather)",
                    "l2_policy": "working set (KV cache >= 1 GB, activations >= 3 GB per step) exceeds the 126 MB L2; no explicit flush"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernel_time_shares": shares,
-        "cpu_baseline": cpu_baseline, "encoder": encoder,
+        "cpu_baseline": cpu_baseline, "encoder": encoder, "next_rows": next_rows,
     }
     print(json.dumps(line), flush=True)
 

@@ -320,3 +320,31 @@ def test_preprocess_u8_bit_exact_with_torchvision_pipeline(m32):
     assert out.shape == (4, 8)
     with pytest.raises(RuntimeError, match="channels"):
         eng.preprocess_u8([torch.zeros(16, 16, 4, dtype=torch.uint8)])
+
+
+def test_wrapper_image_to_latex_end_to_end(tmp_path, sd, golden):
+    """TeXOCRWrapper (model/ocr_model.py:69-110): tokenizer file + checkpoint file + uint8 image -> (tokens, LaTeX)."""
+    import json, os
+    from texocr_b200.wrapper import TeXOCRWrapper
+    from texocr_b200.detok import Detokenizer
+    here = os.path.dirname(os.path.abspath(__file__))
+    tk = json.load(open(os.path.join(here, "golden", "golden_tokenizer_v1.json")))
+    merges = {(a, b): t for a, b, t in tk["bp_merges"]}
+    (tmp_path / "tok.txt").write_text(f"{tk['vocab_size']}\n{tk['special_tokens']}\n{merges}\n")
+    torch.save(sd, tmp_path / "model.pth")
+    cfg = spec.default_config(max_length=256)
+    cfg.update(device="cuda:0", tokenizer_path=str(tmp_path / "tok.txt"), model_path=str(tmp_path / "model.pth"))
+    w = TeXOCRWrapper(cfg, precision="fp32")
+    # the float images of the golden greedy run, quantised back to the uint8 the transform would have produced them from
+    img_f = synth.synth_images(8, 64, 384, seed=1234)
+    u8 = torch.round((1.0 - img_f[:, 0]) * 255.0).clamp(0, 255).to(torch.uint8)
+    back = w.model.engine().preprocess_u8([u for u in u8], 16)
+    assert max(float((b.cpu() - f).abs().max()) for b, f in zip(back, img_f)) <= 0.5 / 255 + 1e-6
+    tokens, texts = w.batch([u for u in u8], max_len=24)
+    assert tokens.shape[0] == 8 and len(texts) == 8 and all(isinstance(t, str) for t in texts)
+    d = Detokenizer.load(str(tmp_path / "tok.txt"))
+    assert texts == d.decode_batch(tokens.cpu(), eos_token=997)
+    one_tokens, one_text = w(u8[0].numpy(), max_len=24)
+    assert one_text == texts[0] and one_tokens == [t for t in tokens[0].tolist()][: len(one_tokens)]
+    s_tokens, s_text = w(u8[0], max_len=24, sample=True, seed=4)
+    assert isinstance(s_text, str) and s_tokens != one_tokens
