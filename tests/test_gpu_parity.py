@@ -305,7 +305,9 @@ def test_preprocess_u8_bit_exact_with_torchvision_pipeline(m32):
     imgs = [torch.from_numpy(g[f"img{i}_u8"]) for i in range(4)]
     refs = [torch.from_numpy(g[f"img{i}_f32"]) for i in range(4)]
     eng = m32.engine()
-    for src in (imgs, [t.cuda() for t in imgs]):
+    # second order: the W % 4 == 0 images first, 4-byte aligned in the packed buffer -> the 4-pixels-per-thread path
+    order = [1, 2, 3, 0]
+    for src, refs in ((imgs, refs), ([t.cuda() for t in imgs], refs), ([imgs[i].cuda() for i in order], [refs[i] for i in order])):
         exact = eng.preprocess_u8(src, pad_multiple=1)
         for o, r in zip(exact, refs):
             assert o.shape == r.shape and torch.equal(o.cpu(), r)
