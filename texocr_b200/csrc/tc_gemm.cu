@@ -297,24 +297,46 @@ template <int BN> struct SmemLn {
     static constexpr int TOTAL = NKB * (A_BYTES + W_BYTES) + 1024 + 256;
 };
 
-TX_DEVINL void ln8(float* v, const float* __restrict__ g, const float* __restrict__ b, int col) {
-    float s = 0.f;
+// LayerNorm of 4 rows at once (a row per warp pass, 8 elements per lane); same operation order per row as ln2_kernel
+// (rowwise.cu), so the results are bit-identical; the four shuffle chains are independent and hide each other's latency.
+TX_DEVINL void ln8x4(float (&v)[4][8], const float* g, const float* b) {
+    float s[4], q[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[i];
-    const float mean = warp_sum(s) * (1.0f / 256);
-    float q = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        s[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 256) + 1e-5f);
-    float gg[8], bb[8];
-    ld8(g + col, gg);
-    ld8(b + col, bb);
+        for (int k = 0; k < 8; ++k) s[i] += v[i][k];
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s[i] *= (1.0f / 256);
+        q[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = v[i][k] - s[i]; q[i] = fmaf(d, d, q[i]); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float rstd = 1.0f / sqrtf(q[i] * (1.0f / 256) + 1e-5f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i][k] = (v[i][k] - s[i]) * rstd * g[k] + b[k];
+    }
 }
 
+// LayerNorm-prologue warps of tc_gemm_ln_kernel (warps 2 .. 2 + LN_WARPS - 1; warps 2 .. 5 also run the epilogue).  Measured at
+// B = 512 (8 branch graphs): 4 warps 142 ms, 16 warps 150 ms per generate vs 110 ms with separate ln2_kernel launches -- the
+// big CTAs cannot share an SM with the attention CTAs of other branches, and PDL hides the separate LayerNorm launch anyway.
+constexpr int LN_WARPS = 4;
+
 template <int BN, int EPI, typename TC>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(64 + 32 * LN_WARPS, 1)
 tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmW, const TcParams p, const LnParams ln) {
     using S = SmemLn<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -333,7 +355,7 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmW, const TcParams p, con
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         for (int s = 0; s < S::NKB; ++s) mbar_init(&w_full[s], 1);
-        mbar_init(a_ready, 4);
+        mbar_init(a_ready, LN_WARPS);
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -370,30 +392,63 @@ tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmW, const TcParams p, con
             umma_commit(tmem_full);
         }
     } else {
-        // ---------------- LayerNorm prologue: warp q owns rows 32q..32q+31 of the tile, lane owns 8 consecutive columns
-        const int q = warp & 3;
+        // ---------------- LayerNorm prologue: rows are dealt round-robin to the LN warps (row = 4 W g + W i + q), 4 rows per
+        // warp are normalised at once (independent shuffle chains) while the next 4 are in flight; lane owns 8 columns.
+        // Rows past M are left as they are in shared memory: an output row only depends on its own A row.
+        const int q = warp - 2;
         const int col = lane * 8;
         const int kb = lane >> 3, chunk = lane & 7;
-        for (int i = 0; i < 32; ++i) {
-            const int r = q * 32 + i, m = m0 + r;
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (m < p.M) {
-                ld8(ln.in + (size_t)m * 256 + col, v);
-                if (ln.g1) ln8(v, ln.g1, ln.b1, col);
-                if (ln.x_out && blockIdx.x == 0) {
-                    st4(ln.x_out + (size_t)m * 256 + col, make_float4(v[0], v[1], v[2], v[3]));
-                    st4(ln.x_out + (size_t)m * 256 + col + 4, make_float4(v[4], v[5], v[6], v[7]));
+        const int nrow = p.M - m0 < BM ? p.M - m0 : BM;
+        constexpr int GR = 4 * LN_WARPS;                   // rows per group
+        const int ngrp = (nrow + GR - 1) / GR;
+        float g1[8], b1[8], g2[8], b2[8];
+        if (ln.g1) { ld8(ln.g1 + col, g1); ld8(ln.b1 + col, b1); }
+        if (ln.g2) { ld8(ln.g2 + col, g2); ld8(ln.b2 + col, b2); }
+        float v[4][8], nx[4][8];
+        auto load_group = [&](int g, float (&dst)[4][8]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = GR * g + LN_WARPS * i + q;
+                if (r < nrow) ld8cg(ln.in + (size_t)(m0 + r) * 256 + col, dst[i]);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dst[i][k] = 0.f;
                 }
-                if (ln.g2) ln8(v, ln.g2, ln.b2, col);
             }
-            bf16* dst = reinterpret_cast<bf16*>(smem_a + kb * S::A_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-            st4(dst, make_float4(v[0], v[1], v[2], v[3]));
-            st4(dst + 4, make_float4(v[4], v[5], v[6], v[7]));
+        };
+        load_group(0, v);
+        for (int g = 0; g < ngrp; ++g) {
+            if (g + 1 < ngrp) load_group(g + 1, nx);
+            if (ln.g1) ln8x4(v, g1, b1);
+            if (ln.x_out && blockIdx.x == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = GR * g + LN_WARPS * i + q;
+                    if (r < nrow) {
+                        st4(ln.x_out + (size_t)(m0 + r) * 256 + col, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+                        st4(ln.x_out + (size_t)(m0 + r) * 256 + col + 4, make_float4(v[i][4], v[i][5], v[i][6], v[i][7]));
+                    }
+                }
+            }
+            if (ln.g2) ln8x4(v, g2, b2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = GR * g + LN_WARPS * i + q;
+                if (r < nrow) {
+                    bf16* dst = reinterpret_cast<bf16*>(smem_a + kb * S::A_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+                    st4(dst, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+                    st4(dst + 4, make_float4(v[i][4], v[i][5], v[i][6], v[i][7]));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[i][k] = nx[i][k];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the MMA
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready)) : "memory");
-        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem_a);
+        if (warp < 6) epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem_a);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -524,7 +579,7 @@ cudaError_t launch_ln_cfg(const CUtensorMap& w, const TcParams& p, const LnParam
         attr_set = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    return launch_pdl(PDL_GEMM, kern, grid, dim3(192), (size_t)S::TOTAL, st, w, p, ln);
+    return launch_pdl(PDL_GEMM, kern, grid, dim3(64 + 32 * LN_WARPS), (size_t)S::TOTAL, st, w, p, ln);
 }
 template <int BN>
 cudaError_t launch_ln_epi(const GemmArgs& g, const CUtensorMap& w, const TcParams& p, const LnParams& ln, cudaStream_t st) {
