@@ -10,7 +10,8 @@ namespace {
 constexpr int D = 256;
 constexpr float LN_EPS = 1e-5f;
 
-TX_DEVINL void layer_norm8(float* v, const float* __restrict__ g, const float* __restrict__ b, int col) {
+// gg / bb: the lane's 8 gamma / beta values (weights: the callers fetch them BEFORE griddepcontrol.wait)
+TX_DEVINL void layer_norm8(float* v, const float* gg, const float* bb) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += v[i];
@@ -19,9 +20,6 @@ TX_DEVINL void layer_norm8(float* v, const float* __restrict__ g, const float* _
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
     const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + LN_EPS);
-    float gg[8], bb[8];
-    ld8(g + col, gg);
-    ld8(b + col, bb);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * gg[i] + bb[i];
 }
@@ -34,16 +32,19 @@ template <typename T> TX_DEVINL void store8(T* p, const float* v) {
 template <typename TAct>
 __global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
     if (!a.late_trigger) pdl_launch_dependents();
-    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
+    float g1[8], b1[8], g2[8], b2[8];
+    if (a.g1) { ld8(a.g1 + col, g1); ld8(a.b1 + col, b1); }
+    if (a.g2) { ld8(a.g2 + col, g2); ld8(a.b2 + col, b2); }
+    pdl_wait();
     if (row >= a.rows) { if (a.late_trigger) pdl_launch_dependents(); return; }
     float v[8];
     ld8cg(a.in + (size_t)row * D + col, v);
-    if (a.g1) layer_norm8(v, a.g1, a.b1, col);
+    if (a.g1) layer_norm8(v, g1, b1);
     if (a.o1f) store8(a.o1f + (size_t)row * D + col, v);
     if (a.o1a) store8(reinterpret_cast<TAct*>(a.o1a) + (size_t)row * D + col, v);
     if (a.g2) {
-        layer_norm8(v, a.g2, a.b2, col);
+        layer_norm8(v, g2, b2);
         if (a.o2a) store8(reinterpret_cast<TAct*>(a.o2a) + (size_t)row * D + col, v);
     }
     if (a.late_trigger) pdl_launch_dependents();
@@ -55,8 +56,10 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict
                                                        const float* __restrict__ g, const float* __restrict__ b,
                                                        float* __restrict__ x, TAct* __restrict__ xn) {
     pdl_launch_dependents();
-    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31, col = lane * 8;
+    float gg[8], bb[8];
+    if (g != nullptr) { ld8(g + col, gg); ld8(b + col, bb); }
+    pdl_wait();
     if (row >= rows) return;
     long id = (long)__ldcg(reinterpret_cast<const long long*>(ids) + row);
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int64_t* __restrict
     for (int i = 0; i < 8; ++i) v[i] += pe[i];
     store8(x + (size_t)row * D + col, v);
     if (g == nullptr) return;          // embedding only: the consumer GEMM applies the LayerNorm itself (tc_gemm_ln_kernel)
-    layer_norm8(v, g, b, col);
+    layer_norm8(v, gg, bb);
     store8(xn + (size_t)row * D + col, v);
 }
 

@@ -122,8 +122,6 @@ TX_DEVINL void stage_copy(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int la
 template <int BN, int EPI, typename TC>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
                              uint8_t* smem_idle) {
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
     const int q = warp & 3;
     uint8_t* stg = smem_idle + q * STG_WARP;
     uint8_t* my = stg + lane * STG_STRIDE;                      // this thread's staged row
@@ -133,6 +131,30 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
     constexpr int NOUT = PAIRS ? 16 : 32;
     using TO = typename std::conditional<EPI == EPI_STORE, TC, typename std::conditional<EPI == EPI_GEGLU, bf16, float>::type>::type;
     constexpr int RB = NOUT * (int)sizeof(TO);
+    // Narrow tiles (the latency-bound decode GEMMs): fetch the thread's residual row while the MMAs are still running --
+    // it does not depend on the accumulator, and its L2 round trip would otherwise sit behind the tmem_full wait.
+    constexpr bool PRE_RES = BN == 32 && (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES);
+    float rpre[PRE_RES ? NOUT : 1];
+    if (PRE_RES) {
+        const int ncol = PAIRS ? (n0 >> 1) : n0, nvalid_out = PAIRS ? (min(32, p.N - n0) >> 1) : min(32, p.N - n0);
+        const float* rp = p.res + (size_t)(mrow0 + lane) * p.ldres + ncol;
+#pragma unroll
+        for (int i = 0; i < (PRE_RES ? NOUT : 0); i += 4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < rows_ok && i < nvalid_out) t = __ldcg(reinterpret_cast<const float4*>(rp + i));
+            rpre[i] = t.x; rpre[i + 1] = t.y; rpre[i + 2] = t.z; rpre[i + 3] = t.w;
+        }
+    }
+    // bias of the tile's first 32 columns: a weight, fetched before the wait as well
+    float bpre[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+        bpre[i] = b.x; bpre[i + 1] = b.y; bpre[i + 2] = b.z; bpre[i + 3] = b.w;
+    }
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t raw[32];
@@ -145,16 +167,25 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
         if (p.bias) {
+            if (c0 == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                if (i < nvalid) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                for (int i = 0; i < 32; ++i) v[i] += bpre[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nvalid) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                    }
                 }
             }
         }
         float o[NOUT];
-        if (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES) {
+        if (PRE_RES) {
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i)
+                o[i] = (EPI == EPI_BIAS_RES) ? v[i] + rpre[PRE_RES ? i : 0] : v[2 * i] * sigmoidf_(v[2 * i + 1]) + rpre[PRE_RES ? i : 0];
+        } else if (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES) {
             // residual tile -> staging (coalesced), then every thread picks up its own row
             stage_copy<NOUT * 4, false>(stg, reinterpret_cast<uint8_t*>(const_cast<float*>(p.res) + (size_t)mrow0 * p.ldres + ncol),
                                         (size_t)p.ldres * 4, lane, rows_ok, nvalid_out * 4);
@@ -229,21 +260,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();        // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel
-
+    // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel, and so do the
+    // weight tiles of the first ring round: W never depends on the predecessor, only the activations (A) do.
     if (warp == 0) {
         if (lane == 0) {
+            const int npre = nkb < S::STAGES ? nkb : S::STAGES;
+            for (int kb = 0; kb < npre; ++kb) {
+                uint8_t* st = smem + kb * S::STAGE;
+                mbar_expect_tx(&full[kb], S::STAGE);
+                tma_load_2d(&tmW, &full[kb], st + S::NOPS * S::A_BYTES, kb * BK, n0);
+                if (SPLIT == 3) tma_load_2d(&tmW2, &full[kb], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
+            }
+            pdl_wait();
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % S::STAGES, ph = (kb / S::STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
                 uint8_t* st = smem + s * S::STAGE;
-                mbar_expect_tx(&full[s], S::STAGE);
-                tma_load_2d(&tmA, &full[s], st, kb * BK, m0);
-                tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, kb * BK, n0);
-                if (SPLIT == 3) {
-                    tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, kb * BK, m0);
-                    tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
+                if (kb >= npre) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], S::STAGE);
+                    tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, kb * BK, n0);
+                    if (SPLIT == 3) tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
                 }
+                tma_load_2d(&tmA, &full[s], st, kb * BK, m0);
+                if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, kb * BK, m0);
             }
         }
     } else if (warp == 1) {
@@ -269,6 +308,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(tmem_full);            // accumulator complete
         }
     } else {
+        pdl_wait();        // the epilogue reads the residual stream
         epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem);
     }
     tcgen05_fence_before();
