@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    pdl_wait();
+    // Cross-attention: the producer only reads the encoder-memory K/V and the token offsets, both written before the
+    // generate loop started, so its TMA stream starts while the predecessor (the query GEMM) is still running.
+    if (SELF || warp != 0) pdl_wait();
 
     const int units = a.batch * 4;
     const int t = SELF ? ldcg_i32(a.step) : 0;
