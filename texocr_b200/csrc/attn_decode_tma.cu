@@ -58,10 +58,17 @@ TX_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+// K/V is read exactly once per step: the loads carry an L2 evict-first policy so that the ~1 GB/step stream does not flush
+// the decoder weights and the activations the concurrently running GEMM / LayerNorm kernels of other branches live on.
+TX_DEVINL uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint64_t pol) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
 }
 TX_DEVINL void ldsm_x4(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, uint32_t& d3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(addr));
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
         // ------------------------------------------------------------ producer
         if (lane == 0) {
             int it = 0;
+            const uint64_t pol = l2_evict_first_policy();
             asm volatile("fence.proxy.async.global;" ::: "memory");     // K/V rows were appended by generic-proxy stores of earlier kernels
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int b = u >> 2, hp = u & 3;
@@ -131,18 +139,18 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
                     const int rc = c * CH;
                     if (left >= CH || (a.full_tail & 1)) {
                         mbar_expect_tx(&full[s], STAGE);
-                        tma_load_2d(&tm, &full[s], st, kc0, r0 + rc);
-                        tma_load_2d(&tm, &full[s], st + HTILE, kc1, r1 + rc);
-                        tma_load_2d(&tm, &full[s], st + 2 * HTILE, kc0 + a.v_col, r0 + rc);
-                        tma_load_2d(&tm, &full[s], st + 3 * HTILE, kc1 + a.v_col, r1 + rc);
+                        tma_load_2d(&tm, &full[s], st, kc0, r0 + rc, pol);
+                        tma_load_2d(&tm, &full[s], st + HTILE, kc1, r1 + rc, pol);
+                        tma_load_2d(&tm, &full[s], st + 2 * HTILE, kc0 + a.v_col, r0 + rc, pol);
+                        tma_load_2d(&tm, &full[s], st + 3 * HTILE, kc1 + a.v_col, r1 + rc, pol);
                     } else {               // tail: 4-row boxes, at most 3 rows fetched beyond the sequence
                         const int n4 = (left + 3) >> 2;
                         mbar_expect_tx(&full[s], n4 * 4 * 512);
                         for (int j = 0; j < n4; ++j) {
-                            tma_load_2d(&tm4, &full[s], st + j * 512, kc0, r0 + rc + 4 * j);
-                            tma_load_2d(&tm4, &full[s], st + HTILE + j * 512, kc1, r1 + rc + 4 * j);
-                            tma_load_2d(&tm4, &full[s], st + 2 * HTILE + j * 512, kc0 + a.v_col, r0 + rc + 4 * j);
-                            tma_load_2d(&tm4, &full[s], st + 3 * HTILE + j * 512, kc1 + a.v_col, r1 + rc + 4 * j);
+                            tma_load_2d(&tm4, &full[s], st + j * 512, kc0, r0 + rc + 4 * j, pol);
+                            tma_load_2d(&tm4, &full[s], st + HTILE + j * 512, kc1, r1 + rc + 4 * j, pol);
+                            tma_load_2d(&tm4, &full[s], st + 2 * HTILE + j * 512, kc0 + a.v_col, r0 + rc + 4 * j, pol);
+                            tma_load_2d(&tm4, &full[s], st + 3 * HTILE + j * 512, kc1 + a.v_col, r1 + rc + 4 * j, pol);
                         }
                     }
                 }
