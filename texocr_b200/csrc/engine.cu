@@ -806,14 +806,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
                launch_gemm_tc_ln(ga, sbuf, g1, b1, g2, b2, write_x ? xbuf : nullptr, st));
         return 0;
     };
-    if (fuse) {
-        LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4), 0.0,
-               launch_embed_ln(ds.cur_tok + row0, step, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, nullptr, nullptr, sbuf, nullptr, h->dt, st));
-    } else {
-        LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4 + e), 0.0,
-               launch_embed_ln(ds.cur_tok + row0, step, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b,
-                               xbuf, xnbuf, h->dt, st));
-    }
+    // the step's input (x = embedding, xn = LN(x)) was written by enqueue_first_embed (step 0) or by the previous step's token kernel
     const double tkeys = t_host >= 0 ? (double)(t_host + 1) : 0.0;
     char* qb = (char*)rowa(h, h->qkv, rc, 1536);
     for (int l = 0; l < L; ++l) {
@@ -884,10 +877,31 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
     aa.logits = lg; aa.B = rows; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>() + (size_t)row0 * tcap; aa.out_ld = tcap;
     aa.cur_tok = ds.cur_tok + row0; aa.step = step; aa.seen_eos = ds.seen + row0; aa.done_step = ds.done_step + branch;
     aa.block_counter = ds.block_counter + branch; aa.eos = eos;
+    aa.tok_emb = h->tok_emb; aa.pos_emb = h->pos_emb; aa.emb_dt = h->dt; aa.emb_max_pos = tcap;
+    if (fuse) { aa.emb_x = sbuf; }
+    else { aa.emb_x = xbuf; aa.emb_xn = xnbuf; aa.emb_g = h->dec_ln_g; aa.emb_b = h->dec_ln_b; }
     if (h->samp_temp > 0.0) {
         aa.topk = sampling_k(h); aa.inv_temp = (float)(1.0 / h->samp_temp); aa.seed = h->samp_seed; aa.row_base = row0; aa.call_ctr = ds.call_ctr;
     }
     LAUNCH(KC_DEC_ARGMAX, 1, (double)rows * c.vocab_size * 4, 0.0, launch_argmax_step(aa, st));
+    return 0;
+}
+
+// Input of the first decode step of a branch (later steps get theirs from the token kernel of the step before).
+static int enqueue_first_embed(texocr_handle* h, int B, int row0, int rows, int branch, cudaStream_t st) {
+    const texocr_config& c = h->cfg;
+    DecState ds = dec_state(h, B);
+    RowCtx rc{rows, KC_DEC_GEMM, KC_DEC_ROW, h->dec_ln_g, h->dec_ln_b, row0};
+    const bool fuse = h->fuse_ln && h->dt == DT_BF16 && h->use_tcgen05 && !(h->dbg_skip & 12);
+    if (fuse) {
+        LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4), 0.0,
+               launch_embed_ln(ds.cur_tok + row0, ds.step + branch, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, nullptr, nullptr,
+                               rowf(h->s, rc, 256), nullptr, h->dt, st));
+    } else {
+        LAUNCH(KC_DEC_ROW, 1, (double)rows * 256 * (8 + 4 + h->esz), 0.0,
+               launch_embed_ln(ds.cur_tok + row0, ds.step + branch, 1, rows, h->tok_emb, h->pos_emb, c.vocab_size, h->dec_ln_g, h->dec_ln_b,
+                               rowf(h->x, rc, 256), rowa(h, h->xn, rc, 256), h->dt, st));
+    }
     return 0;
 }
 
@@ -1084,6 +1098,8 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     for (int s2 = 0; s2 < 2; ++s2)
         for (int i = 0; i < bp.n; ++i)
             if (!h->poll_ev[s2][i]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][i], cudaEventDisableTiming));
+    for (int i = 0; i < bp.n; ++i)
+        if ((r = enqueue_first_embed(h, B, bp.row0[i], bp.rows[i], i, bst[i]))) return r;
     // Host runs ahead of the device by at most 2*POLL steps; an early exit costs at most that many extra steps.
     const int POLL = 16;
     int issued = 0, polls = 0;

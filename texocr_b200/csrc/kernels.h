@@ -114,6 +114,11 @@ struct ArgmaxArgs {
     // sampling (model/decoder.py:103-108): topk > 0 replaces the argmax by a draw from softmax(top-k logits / temp);
     // u = Philox4x32-10(key = seed, counter = (row_base + row, step, *call_ctr, 0)); requires V <= 1024
     int topk; float inv_temp; unsigned long long seed; int row_base; const unsigned* call_ctr;
+    // next step's input, produced by the warp that picked the token (saves the embed launch on the step's critical path):
+    // x = tok_emb[token] + pos_emb[step + 1] (fp32), xn = LN(x) in the activation type (skipped when emb_g == nullptr);
+    // nothing is written when step + 1 == emb_max_pos.  emb_x == nullptr disables it.
+    const float* tok_emb; const float* pos_emb; const float* emb_g; const float* emb_b; float* emb_x; void* emb_xn;
+    int emb_dt, emb_max_pos;
 };
 cudaError_t launch_argmax_step(const ArgmaxArgs& a, cudaStream_t st);
 cudaError_t launch_cross_entropy(const float* logits, const int64_t* tgt, int64_t rows, int V, float* row_loss,

@@ -154,12 +154,30 @@ TX_DEVINL int sample_row(const float* __restrict__ l, int V, int k, float inv_te
     return tok;
 }
 
+// x = tok_emb[tok] + pos_emb[pos]; xn = LN(x): the warp of a row prepares the row's input of the next decode step
+TX_DEVINL void embed_next(const ArgmaxArgs& a, int row, int tok, int pos, int lane, const float* gg, const float* bb) {
+    const int col = lane * 8;
+    long id = tok < 0 ? 0 : (tok >= a.V ? a.V - 1 : tok);
+    float v[8], pe[8];
+    ld8(a.tok_emb + (size_t)id * D + col, v);
+    ld8(a.pos_emb + (size_t)pos * D + col, pe);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += pe[i];
+    store8(a.emb_x + (size_t)row * D + col, v);
+    if (a.emb_g == nullptr) return;
+    layer_norm8(v, gg, bb);
+    if (a.emb_dt == DT_F32) store8(reinterpret_cast<float*>(a.emb_xn) + (size_t)row * D + col, v);
+    else store8(reinterpret_cast<bf16*>(a.emb_xn) + (size_t)row * D + col, v);
+}
+
 __global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
     __shared__ int s_last;
     pdl_launch_dependents();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    float egg[8], ebb[8];
+    if (a.emb_x && a.emb_g) { ld8(a.emb_g + lane * 8, egg); ld8(a.emb_b + lane * 8, ebb); }
     pdl_wait();
     const int t = ldcg_i32(a.step);
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row < a.B && a.topk > 0) {
         const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(a.row_base + row), (uint32_t)t, a.call_ctr ? __ldcg(a.call_ctr) : 0u, 0u),
                                         make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
@@ -170,6 +188,7 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
             a.cur_tok[row] = tok;
             if (a.eos >= 0 && tok == a.eos) a.seen_eos[row] = 1;
         }
+        if (a.emb_x && t + 1 < a.emb_max_pos) embed_next(a, row, tok, t + 1, lane, egg, ebb);
     } else if (row < a.B) {
         const float* l = a.logits + (size_t)row * a.V;
         float best = -INFINITY;
@@ -184,12 +203,13 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
+        if (bi == 0x7fffffff) bi = 0;             // every lane holds the row's result after the butterfly
         if (lane == 0) {
-            if (bi == 0x7fffffff) bi = 0;
             a.out_ids[(size_t)row * a.out_ld + t] = bi;
             a.cur_tok[row] = bi;
             if (a.eos >= 0 && bi == a.eos) a.seen_eos[row] = 1;
         }
+        if (a.emb_x && t + 1 < a.emb_max_pos) embed_next(a, row, bi, t + 1, lane, egg, ebb);
     }
     __threadfence();
     __syncthreads();
