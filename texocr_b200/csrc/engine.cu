@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "decode_mega.h"
+extern int g_tc_split_k;
 #include "tc_gemm.h"
 
 static std::string g_create_error;
@@ -1549,6 +1550,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
         h->decode_branches = (int)value;
         return 0;
     }
+    if (!strcmp(name, "gemm_split_k")) { g_tc_split_k = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "decode_mega")) { h->decode_mega = (int)value; return 0; }
     if (!strcmp(name, "mega_steps")) { h->mega_steps = (int)std::max<int64_t>(1, std::min<int64_t>(4096, value)); return 0; }
     if (!strcmp(name, "tcgen05")) {

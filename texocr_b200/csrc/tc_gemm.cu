@@ -21,6 +21,11 @@
 #include "common.cuh"
 #include "tc_gemm.h"
 
+// texocr_set_option("gemm_split_k"): cluster split-K for the long-K decode GEMMs.  Correct (tests/test_gpu_gemm.py) but measured
+// slower in the decode loop (104.5 vs 95.2 ms per generate at B = 512): cluster launch + DSMEM hand-off cost more than the two
+// or three TMA ring rounds they save.  Off by default.
+int g_tc_split_k = 0;
+
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
@@ -56,6 +61,30 @@ TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+TX_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {       // acquire at cluster scope: data written by peer CTAs
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+TX_DEVINL uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+TX_DEVINL void st_cluster_f4(uint32_t raddr, float a, float b, float c, float d) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+TX_DEVINL void mbar_arrive_remote(uint32_t raddr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+TX_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+TX_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 TX_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 TX_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 TX_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -119,9 +148,13 @@ TX_DEVINL void stage_copy(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int la
     }
 }
 
+// split-K partial tiles in the leader CTA's shared memory: [part][128 rows][PSTR floats]
+constexpr int PSTR = 36;
+constexpr int PART_BYTES = BM * PSTR * 4;
+
 template <int BN, int EPI, typename TC>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
-                             uint8_t* smem_idle) {
+                             uint8_t* smem_idle, const float* parts = nullptr, int nparts = 0, uint64_t* part_full = nullptr) {
     const int q = warp & 3;
     uint8_t* stg = smem_idle + q * STG_WARP;
     uint8_t* my = stg + lane * STG_STRIDE;                      // this thread's staged row
@@ -155,6 +188,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
     }
     mbar_wait(tmem_full, 0);
     tcgen05_fence_after();
+    if (nparts) mbar_wait_cluster(part_full, 0);                // split-K: the peers' partial tiles have landed in our shared memory
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t raw[32];
@@ -166,6 +200,14 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        for (int pt = 0; pt < nparts; ++pt) {                   // fixed order: deterministic sums (BN == 32 only)
+            const float* pr = parts + (size_t)pt * (PART_BYTES / 4) + (q * 32 + lane) * PSTR;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(pr + i);
+                v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+            }
+        }
         if (p.bias) {
             if (c0 == 0) {
 #pragma unroll
@@ -225,24 +267,33 @@ template <int BN, int SPLIT, int NSTG = 0> struct Smem {
     static constexpr int NOPS = SPLIT == 3 ? 2 : 1;                 // hi (+ lo) copies per operand
     static constexpr int STAGE = NOPS * (A_BYTES + W_BYTES);
     static constexpr int STAGES = NSTG ? NSTG : ((STAGE * 4 <= 160 * 1024) ? 4 : (STAGE * 3 <= 200 * 1024 ? 3 : 2));
-    static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int BARS = 256;
+    static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BARS;
 };
 
-template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
+// KS > 1: split-K over a cluster of KS CTAs (grid z): CTA kz accumulates k-blocks [kz, kz+1) * nkb / KS in its own TMEM; the
+// peers (kz > 0) ship their fp32 tiles through distributed shared memory to the leader (kz = 0), which adds them in a fixed
+// order and runs the epilogue.  Used for the long-K, latency-bound decode GEMMs (out-projections K = 512, MLP-out K = 1024).
+template <int BN, int EPI, typename TC, int SPLIT, int NSTG, int KS = 1>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
     using S = Smem<BN, SPLIT, NSTG>;
+    static_assert(KS == 1 || (BN == 32 && SPLIT == 1), "split-K is instantiated for the narrow decode tiles only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
     uint64_t* empty = full + S::STAGES;
     uint64_t* tmem_full = empty + S::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* part_full = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_full + 1);
+    float* parts = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE + S::BARS);      // [KS - 1][BM][PSTR] (KS > 1 only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int nkb = p.K / BK;
+    const int kz = KS > 1 ? (int)blockIdx.z : 0;
+    const int nkb = p.K / BK / KS;                  // k-blocks of this CTA
+    const int kb0 = kz * nkb;
 
     if (!p.late_trigger) pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
@@ -250,6 +301,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
+        if (KS > 1) mbar_init(part_full, (KS - 1) * 4);          // one arrival per epilogue warp of every peer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -259,6 +311,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    if (KS > 1) cluster_arrive();       // the leader's part_full barrier is initialised; the matching wait sits off the critical path
     const uint32_t tmem_base = *tmem_slot;
     // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel, and so do the
     // weight tiles of the first ring round: W never depends on the predecessor, only the activations (A) do.
@@ -268,8 +321,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < npre; ++kb) {
                 uint8_t* st = smem + kb * S::STAGE;
                 mbar_expect_tx(&full[kb], S::STAGE);
-                tma_load_2d(&tmW, &full[kb], st + S::NOPS * S::A_BYTES, kb * BK, n0);
-                if (SPLIT == 3) tma_load_2d(&tmW2, &full[kb], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
+                tma_load_2d(&tmW, &full[kb], st + S::NOPS * S::A_BYTES, (kb0 + kb) * BK, n0);
+                if (SPLIT == 3) tma_load_2d(&tmW2, &full[kb], st + S::NOPS * S::A_BYTES + S::W_BYTES, (kb0 + kb) * BK, n0);
             }
             pdl_wait();
             for (int kb = 0; kb < nkb; ++kb) {
@@ -278,11 +331,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (kb >= npre) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], S::STAGE);
-                    tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, kb * BK, n0);
-                    if (SPLIT == 3) tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
+                    tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, (kb0 + kb) * BK, n0);
+                    if (SPLIT == 3) tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, (kb0 + kb) * BK, n0);
                 }
-                tma_load_2d(&tmA, &full[s], st, kb * BK, m0);
-                if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, kb * BK, m0);
+                tma_load_2d(&tmA, &full[s], st, (kb0 + kb) * BK, m0);
+                if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, (kb0 + kb) * BK, m0);
             }
         }
     } else if (warp == 1) {
@@ -307,10 +360,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             umma_commit(tmem_full);            // accumulator complete
         }
+    } else if (KS > 1 && kz > 0) {
+        // split-K peer: accumulator tile -> the leader's shared memory (thread = row, 32 columns), then one arrival per warp
+        cluster_wait();                                           // leader's barrier initialised (arrived long ago)
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), raw);
+        const uint32_t row_local = smem_u32(parts) + (uint32_t)(kz - 1) * PART_BYTES + (uint32_t)(q * 32 + lane) * (PSTR * 4);
+        const uint32_t row_remote = mapa_rank(row_local, 0);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            st_cluster_f4(row_remote + i * 4, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]), __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(part_full), 0));
     } else {
         pdl_wait();        // the epilogue reads the residual stream
-        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem);
+        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem, parts, KS - 1, part_full);
     }
+    if (KS > 1 && !(kz > 0 && warp >= 2)) cluster_wait();         // pairs with the arrive above (peer epilogue warps waited already)
     tcgen05_fence_before();
     __syncthreads();
     if (p.late_trigger) pdl_launch_dependents();
@@ -582,12 +651,43 @@ cudaError_t launch_cfg2(const CUtensorMap& a, const CUtensorMap& w, const CUtens
     return launch_pdl(PDL_GEMM, kern, grid, dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
 }
 
+// split-K launch: grid z = cluster of KS CTAs; programmatic dependent launch like every other decode kernel
+template <int EPI, typename TC, int KS>
+cudaError_t launch_cfg_ks(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                          cudaStream_t st) {
+    using S = Smem<32, 1, 0>;
+    constexpr int SMEM = S::TOTAL + (KS - 1) * PART_BYTES;
+    static bool attr_set = false;
+    auto kern = tc_gemm_kernel<32, EPI, TC, 1, 0, KS>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((p.N + 31) / 32, (p.M + BM - 1) / BM, KS); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = KS;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = ((g_texocr_pdl >> PDL_GEMM) & 1) ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, a, w, a2, w2, p);
+}
+
 template <int BN, int EPI, typename TC, int SPLIT>
 cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
                        cudaStream_t st) {
     // many tiles (encoder / teacher-forced sizes): shallow pipeline, several CTAs per SM; few tiles: deep pipeline
     const long tiles = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
     if (SPLIT == 1 && BN >= 64 && tiles >= 592) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
+    if constexpr (SPLIT == 1 && BN == 32 && (EPI == EPI_GLU_RES || EPI == EPI_BIAS_RES)) {
+        // latency-bound decode GEMMs with a long K loop: split K over a 2- / 4-CTA cluster (4 k-blocks per CTA = one ring round)
+        if (g_tc_split_k && tiles < 120) {
+            if (p.K == 1024) return launch_cfg_ks<EPI, TC, 4>(a, w, a2, w2, p, st);
+            if (p.K == 512) return launch_cfg_ks<EPI, TC, 2>(a, w, a2, w2, p, st);
+        }
+    }
     return launch_cfg2<BN, EPI, TC, SPLIT, 0>(a, w, a2, w2, p, st);
 }
 
