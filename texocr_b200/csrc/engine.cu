@@ -391,6 +391,7 @@ struct EncGeom {
     std::vector<int> img_off, tok_off;
     long P[5] = {0, 0, 0, 0, 0};
     int ntok = 0, max_tok = 0;
+    int uni_h = 0, uni_w = 0;          // > 0: every image has this size (enables the TMA im2col convolutions)
     const int* d_img_off = nullptr; const int* d_img_hw = nullptr; const int* d_tok_off = nullptr;
 };
 
@@ -398,8 +399,10 @@ static int plan_geometry(texocr_handle* h, const int32_t* hw, int B, EncGeom& g,
     if (B <= 0) return fail(h, TEXOCR_ERR_ARG, "batch must be positive");
     g.B = B;
     g.img_off.assign(B + 1, 0); g.tok_off.assign(B + 1, 0);
+    g.uni_h = hw[0]; g.uni_w = hw[1];
     for (int b = 0; b < B; ++b) {
         const int H = hw[2 * b], W = hw[2 * b + 1];
+        if (H != g.uni_h || W != g.uni_w) g.uni_h = g.uni_w = 0;
         if (H <= 0 || W <= 0 || H % 16 || W % 16 || H > 160 || W > 1008)
             return fail(h, TEXOCR_ERR_ARG, "image %d is %dx%d: height and width must be multiples of 16 with H <= 160 and "
                         "W <= 1008 (10x63 position grid, model/encoder.py:137-143)", b, H, W);
@@ -565,14 +568,21 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
         const long M = g.P[lout];
         const int K = cw.k * cw.k * cw.cin;
         const void *a_hi = in.hi, *a_lo = in.lo;
-        if (!(cw.k == 1 && cw.stride == 1)) {
-            ConvGather cg{g.d_img_off, g.d_img_hw, B, lin, lout, cw.k, cw.stride, (cw.k == 3 && cw.stride == 1) ? 1 : 0, cw.cin};
+        const int pad_lo = (cw.k == 3 && cw.stride == 1) ? 1 : 0;
+        // same-size batch: the GEMM fetches its A tiles straight from the NHWC activation with TMA im2col loads
+        const bool implicit = h->use_im2col_tma && g.uni_h > 0 && cw.cin % 64 == 0 && !(cw.k == 1 && cw.stride == 1);
+        if (!(cw.k == 1 && cw.stride == 1) && !implicit) {
+            ConvGather cg{g.d_img_off, g.d_img_hw, B, lin, lout, cw.k, cw.stride, pad_lo, cw.cin};
             Pair c = pair_of(h->col, (size_t)M * K);
             LAUNCH(KC_GN_APPLY, 1, (double)M * K * 8, 0.0, launch_im2col_split(in.hi, in.lo, c.hi, c.lo, cg, M, st));
             a_hi = c.hi; a_lo = c.lo;
         }
         GemmArgs ga = mk_gemm(a_hi, K, cw.w_hi, K, out, cw.cout, (int)M, cw.cout, K, EPI_STORE, DT_BF16, DT_F32, nullptr, nullptr, 0);
         ga.A2 = a_lo; ga.W2 = cw.w_lo;
+        if (implicit) {
+            ga.lda = cw.cin;
+            ga.im2col = {cw.k, cw.stride, pad_lo, cw.cin, g.uni_w >> lin, g.uni_h >> lin, B, g.uni_w >> lout, g.uni_h >> lout};
+        }
         if (!tc_gemm_supported(ga)) return fail(h, TEXOCR_ERR_ARG, "backbone conv %s not supported by the tcgen05 GEMM", cw.name.c_str());
         LAUNCH(KC_CONV, 1, gemm_bytes(ga, 4), gemm_flops(ga), launch_gemm_tc(ga, st));
         return 0;
@@ -1551,6 +1561,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "gemm_split_k")) { g_tc_split_k = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "im2col_tma")) { h->use_im2col_tma = value != 0; return 0; }
     if (!strcmp(name, "decode_mega")) { h->decode_mega = (int)value; return 0; }
     if (!strcmp(name, "mega_steps")) { h->mega_steps = (int)std::max<int64_t>(1, std::min<int64_t>(4096, value)); return 0; }
     if (!strcmp(name, "tcgen05")) {

@@ -49,6 +49,10 @@ struct GemmArgs {
     int epi;
     const ConvGather* conv;   // non-null: A(m,k) gathered from NHWC input (fp32 only)
     const void* A2; const void* W2;   // tcgen05 bf16x3 mode: low-order bf16 parts of A and W (same shapes / strides)
+    // tcgen05 path, implicit GEMM of a ksz x ksz convolution over a batch of N same-size NHWC images [N][H][W][C] (A = the
+    // activation, K = ksz*ksz*C, k order (ky, kx, c)): the A tiles are fetched with TMA im2col loads, no im2col buffer.
+    // pad_lo = padding before (TF-SAME, utils.py:93-123); M = N * Ho * Wo output pixels.  ksz == 0: plain GEMM.
+    struct Im2col { int ksz, stride, pad_lo, C, W, H, N, Wo, Ho; } im2col;
 };
 cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 

@@ -34,6 +34,8 @@ struct TcParams {
     void* C; int M, N, K, ldc;
     const float* bias; const float* res; int ldres;
     int late_trigger;
+    // implicit-GEMM convolution (TMA im2col loads of A): cpk = 64-channel chunks per filter tap (0 = plain GEMM)
+    int cv_cpk, cv_ksz, cv_stride, cv_lower, cv_Wo, cv_Ho;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -60,6 +62,14 @@ TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// im2col-mode TMA load: 128 consecutive output pixels (w fastest, then h, then n, stepping by the map's traversal stride and
+// wrapping inside its bounding box) x 64 channels of the input pixel at (base + filter offset); out-of-image taps are zero
+TX_DEVINL void tma_load_im2col(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h, int n, int off_w, int off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
+        : "memory");
 }
 TX_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {       // acquire at cluster scope: data written by peer CTAs
     asm volatile(
@@ -325,6 +335,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (SPLIT == 3) tma_load_2d(&tmW2, &full[kb], st + S::NOPS * S::A_BYTES + S::W_BYTES, (kb0 + kb) * BK, n0);
             }
             pdl_wait();
+            // convolution: base input pixel of the tile's first output pixel m0 = (n, oh, ow)
+            int cv_w = 0, cv_h = 0, cv_n = 0;
+            if (p.cv_cpk) {
+                const int per = p.cv_Wo * p.cv_Ho;
+                cv_n = m0 / per;
+                const int rem = m0 - cv_n * per, oh = rem / p.cv_Wo;
+                cv_h = oh * p.cv_stride + p.cv_lower;
+                cv_w = (rem - oh * p.cv_Wo) * p.cv_stride + p.cv_lower;
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % S::STAGES, ph = (kb / S::STAGES) & 1;
                 uint8_t* st = smem + s * S::STAGE;
@@ -334,8 +353,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, (kb0 + kb) * BK, n0);
                     if (SPLIT == 3) tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, (kb0 + kb) * BK, n0);
                 }
-                tma_load_2d(&tmA, &full[s], st, (kb0 + kb) * BK, m0);
-                if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, (kb0 + kb) * BK, m0);
+                if (p.cv_cpk) {
+                    const int kg = kb0 + kb, tap = kg / p.cv_cpk, cc = (kg - tap * p.cv_cpk) * BK;
+                    const int ky = tap / p.cv_ksz, kx = tap - ky * p.cv_ksz;
+                    tma_load_im2col(&tmA, &full[s], st, cc, cv_w, cv_h, cv_n, kx, ky);
+                    if (SPLIT == 3) tma_load_im2col(&tmA2, &full[s], st + S::A_BYTES, cc, cv_w, cv_h, cv_n, kx, ky);
+                } else {
+                    tma_load_2d(&tmA, &full[s], st, (kb0 + kb) * BK, m0);
+                    if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, (kb0 + kb) * BK, m0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -634,6 +660,35 @@ cudaError_t tma_map_3d_bf16(const void* ptr, int d0, long d1, long d2, long stri
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// im2col-mode map of an NHWC bf16 activation [N][H][W][C]: box = 128 output pixels x 64 channels, 128-byte swizzle
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static cudaError_t tma_map_im2col_bf16(const void* ptr, const GemmArgs::Im2col& c, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_encode_im2col) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        g_encode_im2col = (EncodeIm2colFn)fn;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+    cuuint64_t strides[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+    // fprop corners (see CUTLASS conv/collective/detail.hpp): lower = -pad_before, upper = pad_after - (ksz - 1)
+    const int pad_total = std::max((c.Wo - 1) * c.stride + c.ksz - c.W, 0);
+    const int pad_total_h = std::max((c.Ho - 1) * c.stride + c.ksz - c.H, 0);
+    int lower[2] = {-c.pad_lo, -c.pad_lo};
+    int upper[2] = {(pad_total - c.pad_lo) - (c.ksz - 1), (pad_total_h - c.pad_lo) - (c.ksz - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+    CUresult r = g_encode_im2col(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, BK, BM, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 namespace {
 
 template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
@@ -755,6 +810,7 @@ cudaError_t launch_gemm_tc_ln(const GemmArgs& g, const float* s_in, const float*
 bool tc_gemm_supported(const GemmArgs& g) {
     if (g.dt_a != DT_BF16 || g.conv) return false;
     if (g.K % BK != 0 || g.N % 8 != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0) return false;
+    if (g.im2col.ksz > 0 && (g.im2col.C % BK != 0 || g.im2col.ksz > 7)) return false;
     if (((uintptr_t)g.A | (uintptr_t)g.W) & 15) return false;
     if (g.epi == EPI_STORE) { if (g.ldc % 8 != 0) return false; }
     else if (g.ldc % 4 != 0) return false;
@@ -771,14 +827,21 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
     const bool split = g.A2 != nullptr;
     if (split) bn = g.N <= 64 ? 64 : 128;
-    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1};
+    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1, 0, 0, 0, 0, 0, 0};
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
-    if ((e = get_map(g.A, g.M, g.K, g.lda, BM, &a)) != cudaSuccess) return e;
+    const bool conv = g.im2col.ksz > 0;
+    if (conv) {
+        const GemmArgs::Im2col& c = g.im2col;
+        if (c.C % BK != 0 || g.K != c.ksz * c.ksz * c.C || (long)c.N * c.Wo * c.Ho != g.M) return cudaErrorInvalidValue;
+        p.cv_cpk = c.C / BK; p.cv_ksz = c.ksz; p.cv_stride = c.stride; p.cv_lower = -c.pad_lo; p.cv_Wo = c.Wo; p.cv_Ho = c.Ho;
+        if ((e = tma_map_im2col_bf16(g.A, c, &a)) != cudaSuccess) return e;
+    } else if ((e = get_map(g.A, g.M, g.K, g.lda, BM, &a)) != cudaSuccess) return e;
     if ((e = get_map(g.W, g.N, g.K, g.ldw, bn, &w)) != cudaSuccess) return e;
     a2 = a; w2 = w;
     if (split) {
-        if ((e = get_map(g.A2, g.M, g.K, g.lda, BM, &a2)) != cudaSuccess) return e;
+        if (conv) { if ((e = tma_map_im2col_bf16(g.A2, g.im2col, &a2)) != cudaSuccess) return e; }
+        else if ((e = get_map(g.A2, g.M, g.K, g.lda, BM, &a2)) != cudaSuccess) return e;
         if ((e = get_map(g.W2, g.N, g.K, g.ldw, bn, &w2)) != cudaSuccess) return e;
         if (bn == 64) return launch_epi<64, 3>(g, a, w, a2, w2, p, st);
         return launch_epi<128, 3>(g, a, w, a2, w2, p, st);
