@@ -20,6 +20,7 @@
 
 #include "decode_mega.h"
 extern int g_tc_split_k;
+extern int g_tc_persistent;
 #include "tc_gemm.h"
 
 static std::string g_create_error;
@@ -1560,6 +1561,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
         h->decode_branches = (int)value;
         return 0;
     }
+    if (!strcmp(name, "gemm_persistent")) { g_tc_persistent = (int)value; return 0; }
     if (!strcmp(name, "gemm_split_k")) { g_tc_split_k = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "im2col_tma")) { h->use_im2col_tma = value != 0; return 0; }
     if (!strcmp(name, "decode_mega")) { h->decode_mega = (int)value; return 0; }

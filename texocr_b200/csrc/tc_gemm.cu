@@ -25,6 +25,7 @@
 // slower in the decode loop (104.5 vs 95.2 ms per generate at B = 512): cluster launch + DSMEM hand-off cost more than the two
 // or three TMA ring rounds they save.  Off by default.
 int g_tc_split_k = 0;
+int g_tc_persistent = 1;     // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
 
 namespace {
 
@@ -70,6 +71,9 @@ TX_DEVINL void tma_load_im2col(const CUtensorMap* map, uint64_t* bar, void* dst,
         "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
         : "memory");
+}
+TX_DEVINL void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 TX_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {       // acquire at cluster scope: data written by peer CTAs
     asm volatile(
@@ -164,7 +168,8 @@ constexpr int PART_BYTES = BM * PSTR * 4;
 
 template <int BN, int EPI, typename TC>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
-                             uint8_t* smem_idle, const float* parts = nullptr, int nparts = 0, uint64_t* part_full = nullptr) {
+                             uint8_t* smem_idle, const float* parts = nullptr, int nparts = 0, uint64_t* part_full = nullptr,
+                             uint32_t parity = 0) {
     const int q = warp & 3;
     uint8_t* stg = smem_idle + q * STG_WARP;
     uint8_t* my = stg + lane * STG_STRIDE;                      // this thread's staged row
@@ -196,7 +201,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         if (p.bias && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
         bpre[i] = b.x; bpre[i + 1] = b.y; bpre[i + 2] = b.z; bpre[i + 3] = b.w;
     }
-    mbar_wait(tmem_full, 0);
+    mbar_wait(tmem_full, parity);
     tcgen05_fence_after();
     if (nparts) mbar_wait_cluster(part_full, 0);                // split-K: the peers' partial tiles have landed in our shared memory
 #pragma unroll 1
@@ -412,6 +417,140 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ persistent GEMM
+// Large-M GEMMs (backbone convolutions, encoder blocks, cross-K/V): one CTA per SM walks the output tiles (n fastest, so
+// neighbouring CTAs share an A tile in L2) with TWO accumulator buffers in TMEM: the MMA warp fills buffer (i + 1) & 1
+// while the four epilogue warps drain buffer i & 1, and the TMA ring keeps running across tile boundaries.  In the
+// one-tile-per-CTA kernel above the tensor pipe sat idle during every epilogue (ncu: 20 % tensor-pipe active on the conv
+// GEMMs); here the epilogue is off the critical path as long as it is shorter than a tile's MMA loop.
+template <int BN, int SPLIT> struct SmemP {
+    static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+    static constexpr int NOPS = SPLIT == 3 ? 2 : 1;
+    static constexpr int STAGE = NOPS * (A_BYTES + W_BYTES);
+    static constexpr int STG = 4 * STG_WARP;                                   // dedicated epilogue staging (the ring never idles)
+    static constexpr int STAGES = (200 * 1024 - STG) / STAGE > 8 ? 8 : (200 * 1024 - STG) / STAGE;
+    static constexpr int BARS = 256;
+    static constexpr int TOTAL = STAGES * STAGE + STG + 1024 + BARS;
+};
+
+template <int BN, int EPI, typename TC, int SPLIT>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
+    using S = SmemP<BN, SPLIT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stg = smem + S::STAGES * S::STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stg + S::STG);
+    uint64_t* empty = full + S::STAGES;
+    uint64_t* tmem_full = empty + S::STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.K / BK;
+    const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM - 1) / BM;
+    const int tiles = n_tiles * m_tiles;
+
+    pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                int cv_w = 0, cv_h = 0, cv_n = 0;
+                if (p.cv_cpk) {
+                    const int per = p.cv_Wo * p.cv_Ho;
+                    cv_n = m0 / per;
+                    const int rem = m0 - cv_n * per, oh = rem / p.cv_Wo;
+                    cv_h = oh * p.cv_stride + p.cv_lower;
+                    cv_w = (rem - oh * p.cv_Wo) * p.cv_stride + p.cv_lower;
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % S::STAGES, ph = (it / S::STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * S::STAGE;
+                    mbar_expect_tx(&full[s], S::STAGE);
+                    if (p.cv_cpk) {
+                        const int tap = kb / p.cv_cpk, cc = (kb - tap * p.cv_cpk) * BK;
+                        const int ky = tap / p.cv_ksz, kx = tap - ky * p.cv_ksz;
+                        tma_load_im2col(&tmA, &full[s], st, cc, cv_w, cv_h, cv_n, kx, ky);
+                        if (SPLIT == 3) tma_load_im2col(&tmA2, &full[s], st + S::A_BYTES, cc, cv_w, cv_h, cv_n, kx, ky);
+                    } else {
+                        tma_load_2d(&tmA, &full[s], st, kb * BK, m0);
+                        if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, kb * BK, m0);
+                    }
+                    tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, kb * BK, n0);
+                    if (SPLIT == 3) tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int it = 0, i = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);        // the epilogue has drained this buffer (first use passes)
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % S::STAGES, ph = (it / S::STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * S::STAGE);
+                    const uint32_t w_hi = a_hi + S::NOPS * S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 2;
+                        umma_bf16(acc, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, (kb | k) != 0);
+                        if (SPLIT == 3) {
+                            umma_bf16(acc, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + S::W_BYTES + koff), idesc, 1);
+                            umma_bf16(acc, make_smem_desc(a_hi + S::A_BYTES + koff), make_smem_desc(w_hi + koff), idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        int i = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            epilogue_tile<BN, EPI, TC>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, nullptr, 0, nullptr,
+                                       (uint32_t)((i >> 1) & 1));
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);              // all of this warp's tcgen05.ld of the buffer have completed
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
     }
 }
 
@@ -731,10 +870,32 @@ cudaError_t launch_cfg_ks(const CUtensorMap& a, const CUtensorMap& w, const CUte
 }
 
 template <int BN, int EPI, typename TC, int SPLIT>
+cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                              long tiles, cudaStream_t st) {
+    using S = SmemP<BN, SPLIT>;
+    static bool attr_set = false;
+    static int sms = 0;
+    auto kern = tc_gemm_persistent_kernel<BN, EPI, TC, SPLIT>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)std::min<long>(tiles, sms);
+    return launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
+}
+
+template <int BN, int EPI, typename TC, int SPLIT>
 cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
                        cudaStream_t st) {
     // many tiles (encoder / teacher-forced sizes): shallow pipeline, several CTAs per SM; few tiles: deep pipeline
     const long tiles = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
+    if constexpr (BN >= 64) {
+        if (g_tc_persistent && tiles >= 296) return launch_persistent<BN, EPI, TC, SPLIT>(a, w, a2, w2, p, tiles, st);
+    }
     if (SPLIT == 1 && BN >= 64 && tiles >= 592) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
     if constexpr (SPLIT == 1 && BN == 32 && (EPI == EPI_GLU_RES || EPI == EPI_BIAS_RES)) {
         // latency-bound decode GEMMs with a long K loop: split K over a 2- / 4-CTA cluster (4 k-blocks per CTA = one ring round)
