@@ -18,8 +18,12 @@ for o in opts:
     for kv in o.split(","):
         k, v = kv.split("=")
         eng.set_option(k, int(v))
-    for _ in range(2):
-        out = m.generate(img, T)
+    try:
+        for _ in range(2):
+            out = m.generate(img, T)
+    except RuntimeError as ex:
+        print("%-40s FAILED: %s" % (o, ex), flush=True)
+        continue
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     n = 4

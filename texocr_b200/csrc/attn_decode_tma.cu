@@ -35,7 +35,9 @@ struct Args {
     int batch;
     int ld, col0, col_h, v_col, row_h, row_b;           // KvLayout (kernels.h)
     int full_tail;                                      // debug: fetch the last, partial stage with full 16-row boxes
+    unsigned long long* trace; const int* trace_step; int trace_k;     // debug timeline: [3][256 steps][8 launches] of this branch
 };
+TX_DEVINL unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 TX_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 TX_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     pdl_launch_dependents();
+    const unsigned long long t_entry = a.trace ? gtime() : 0ull;
     // Rows past the end of a sequence (fetched by the last box or stale in a partially filled stage) may hold anything:
     // their scores are replaced by -inf and their V fragments are cleared below, so the ring needs no initialisation.
     if (threadIdx.x == 0) {
@@ -115,6 +118,13 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
 
     const int units = a.batch * 4;
     const int t = SELF ? ldcg_i32(a.step) : 0;
+    unsigned long long* tr = nullptr;
+    if (a.trace && threadIdx.x == 32) {
+        const int ts = min(ldcg_i32(a.trace_step), 255);
+        tr = a.trace + (size_t)ts * 8 + a.trace_k;
+        atomicMin(tr, t_entry);
+        atomicMin(tr + 2048, gtime());
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer
@@ -311,6 +321,7 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
             for (int nt = 0; nt < 8; ++nt) op[4 * nt + tq] = pack_bf16x2(o[nt][0] * inv, o[nt][1] * inv);
         }
     }
+    if (tr) atomicMax(tr + 4096, gtime());
 }
 
 int g_smem_set = 0;
@@ -339,6 +350,7 @@ cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const KvLayout& lay,
     k.q = (const bf16*)a.q; k.ldq = a.ldq; k.knew = (const bf16*)a.knew; k.vnew = (const bf16*)a.vnew; k.ldnew = a.ldnew;
     k.cache = (bf16*)const_cast<void*>(lay.map_base); k.k_off = a.k_off; k.step = a.step; k.o = (bf16*)a.o; k.ldo = a.ldo;
     k.full_tail = g_attn_full_tail;
+    k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k;
     k.batch = a.batch; k.ld = lay.ld; k.col0 = lay.col0; k.col_h = lay.col_h; k.v_col = lay.v_col; k.row_h = lay.row_h; k.row_b = lay.row_b;
     const int units = a.batch * 4;
     const int grid = units < max_ctas ? units : max_ctas;

@@ -78,6 +78,10 @@ static void drop_graphs(texocr_handle* h) {
         if (h->bgraph[i]) { cudaGraphDestroy(h->bgraph[i]); h->bgraph[i] = nullptr; }
     }
     h->graph_exec = nullptr; h->graph = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (h->cgraph_exec[i]) { cudaGraphExecDestroy(h->cgraph_exec[i]); h->cgraph_exec[i] = nullptr; }
+        if (h->cgraph[i]) { cudaGraphDestroy(h->cgraph[i]); h->cgraph[i] = nullptr; }
+    }
 }
 
 static int ensure(texocr_handle* h, DevBuf& b, size_t bytes) {
@@ -776,6 +780,7 @@ static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_t
 
 // ------------------------------------------------------------------------------------------------ decode step
 constexpr int MAX_BRANCH = 16;
+constexpr int FIFO_STRIDE = 32;      // events per (step, branch) of the coupled graph: 2 attention launches per decoder layer
 static int sampling_k(const texocr_handle* h);
 struct DecState {
     int64_t* cur_tok; int* step; int* done_step; int* block_counter; unsigned* call_ctr; int* seen;     // step/done/counter: [MAX_BRANCH]
@@ -818,6 +823,20 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
                launch_gemm_tc_ln(ga, sbuf, g1, b1, g2, b2, write_x ? xbuf : nullptr, st));
         return 0;
     };
+    // Coupled capture (run_generate, attn_fifo > 0): attention launch k of this branch waits for the attention launch the
+    // FIFO names and records its own completion for the branch behind it.
+    struct PdlGuard { int saved; PdlGuard() : saved(g_texocr_pdl) {} ~PdlGuard() { g_texocr_pdl = saved; } };
+    auto fifo_before = [&](int k) -> int {
+        if (h->fifo_wait && h->fifo_wait[k]) {
+            CK(cudaStreamWaitEvent(st, h->fifo_wait[k], 0));
+            if (!h->fifo_pdl) g_texocr_pdl &= ~((1 << PDL_ATTN_TMA) | (1 << PDL_ATTN_SIMPLE));
+        }
+        return 0;
+    };
+    auto fifo_after = [&](int k) -> int {
+        if (h->fifo_rec) CK(cudaEventRecord(h->fifo_rec[k], st));
+        return 0;
+    };
     // the step's input (x = embedding, xn = LN(x)) was written by enqueue_first_embed (step 0) or by the previous step's token kernel
     const double tkeys = t_host >= 0 ? (double)(t_host + 1) : 0.0;
     char* qb = (char*)rowa(h, h->qkv, rc, 1536);
@@ -837,12 +856,20 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
         ad.kcache = kv; ad.vcache = kv + 64 * e; ad.ldkv = 128; ad.batch_stride = (int64_t)tcap * 1024; ad.head_stride = (int64_t)tcap * 128;
         ad.step = step; ad.o = rowa(h, h->o, rc, 512); ad.ldo = 512; ad.batch = rows; ad.dt = h->dt;
         const KvLayout lay_self{kv, (long)rows * 8 * tcap, 128, 128, 0, 0, 64, tcap, 8 * tcap};
-        if (h->dbg_skip & 1) {}
-        else if ((h->use_tma_attn == 1 || h->use_tma_attn == 2) && attn_decode_tma_supported(ad))
-            LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512,
-                   launch_attn_decode_tma(ad, lay_self, h->num_sms * h->attn_ctas_per_sm, st));
-        else
-            LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512, launch_attn_decode(ad, tcap, st));
+        if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
+            ad.trace = h->attn_trace.as<unsigned long long>() + (size_t)branch * 3 * 2048; ad.trace_step = step; ad.trace_k = 2 * l;
+        }
+        {
+            PdlGuard guard;
+            if ((r = fifo_before(2 * l))) return r;
+            if (h->dbg_skip & 1) {}
+            else if ((h->use_tma_attn == 1 || h->use_tma_attn == 2) && attn_decode_tma_supported(ad))
+                LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512,
+                       launch_attn_decode_tma(ad, lay_self, h->num_sms * h->attn_ctas_per_sm, st));
+            else
+                LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 1024 * e, 4.0 * rows * tkeys * 512, launch_attn_decode(ad, tcap, st));
+        }
+        if ((r = fifo_after(2 * l))) return r;
         if ((r = sub_attn_out(h, rc, h->dec_self[l], st))) return r;
         // ---- cross-attention over the (pre-projected) encoder memory; q goes to the first 512 columns of this branch's qkv rows
         if (fuse) {
@@ -859,12 +886,20 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
         ac.q = qb; ac.ldq = 512; ac.kcache = ckv; ac.vcache = ckv + 64 * e; ac.ldkv = 128; ac.head_stride = ntok_all * 128;
         ac.k_off = d_enc_off + row0; ac.o = rowa(h, h->o, rc, 512); ac.ldo = 512; ac.batch = rows; ac.dt = h->dt;
         const KvLayout lay_cross{ckv, 8 * ntok_all, 128, 128, 0, 0, 64, (int)ntok_all, 0};
-        if (h->dbg_skip & 2) {}
-        else if ((h->use_tma_attn == 1 || h->use_tma_attn == 3) && attn_decode_tma_supported(ac))
-            LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512,
-                   launch_attn_decode_tma(ac, lay_cross, h->num_sms * h->attn_ctas_per_sm, st));
-        else
-            LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512, launch_attn_decode(ac, max_s, st));
+        if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
+            ac.trace = h->attn_trace.as<unsigned long long>() + (size_t)branch * 3 * 2048; ac.trace_step = step; ac.trace_k = 2 * l + 1;
+        }
+        {
+            PdlGuard guard;
+            if ((r = fifo_before(2 * l + 1))) return r;
+            if (h->dbg_skip & 2) {}
+            else if ((h->use_tma_attn == 1 || h->use_tma_attn == 3) && attn_decode_tma_supported(ac))
+                LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512,
+                       launch_attn_decode_tma(ac, lay_cross, h->num_sms * h->attn_ctas_per_sm, st));
+            else
+                LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 1024 * e, 4.0 * sum_s * rows / B * 512, launch_attn_decode(ac, max_s, st));
+        }
+        if ((r = fifo_after(2 * l + 1))) return r;
         if ((r = sub_attn_out(h, rc, h->dec_cross[l], st))) return r;
         // ---- GeGLU MLP
         if (fuse) {
@@ -1049,6 +1084,14 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     ENSURE(h->kvcache, (size_t)c.dec_layers * B * tcap * 1024 * h->esz);
     ENSURE(h->dec_state, dec_state_bytes(B));
     ENSURE(h->out_ids, (size_t)B * tcap * 8);
+    if (h->attn_trace_on) {
+        ENSURE(h->attn_trace, (size_t)MAX_BRANCH * 3 * 2048 * 8);
+        for (int i = 0; i < MAX_BRANCH; ++i) {
+            char* base = (char*)h->attn_trace.p + (size_t)i * 3 * 2048 * 8;
+            CK(cudaMemsetAsync(base, 0xff, 2 * 2048 * 8, st));
+            CK(cudaMemsetAsync(base + 2 * 2048 * 8, 0, 2048 * 8, st));
+        }
+    }
     if (!h->h_poll) CK(cudaMallocHost(&h->h_poll, 4 * MAX_BRANCH * 4));
     DecState ds = dec_state(h, B);
     CK(cudaMemsetAsync((char*)h->dec_state.p + (size_t)B * 8, 0, dec_state_bytes(B) - (size_t)B * 8, st));
@@ -1078,7 +1121,88 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     // branches run as independent, phase-shifted pipelines that only meet again at the end of the call.
     cudaStream_t bst[MAX_BRANCH];
     for (int i = 0; i < bp.n; ++i) bst[i] = (bp.n == 1 || !graph_ok) ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
-    if (graph_ok) {
+    const int samp_key = h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0;
+    // ---- coupled mode: one graph holds all branches of `spg` steps; attention launches are chained across branches (FIFO of
+    // depth `fifo`), everything else of a branch only depends on the branch itself
+    const int fifo = (graph_ok && bp.n > 1 && h->attn_fifo > 0 && 2 * c.dec_layers <= FIFO_STRIDE) ? std::min(h->attn_fifo, bp.n) : 0;
+    if (fifo > 0) {
+        cudaStream_t cs = h->own_stream2;
+        const int spg = std::max(1, std::min(h->steps_per_graph, 16));
+        const bool hit = h->cgraph_exec[0] && h->cgraph_exec[1] && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos &&
+                         h->gkey.max_s == max_s && h->gkey.samp == samp_key && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p &&
+                         h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n && h->gkey.fifo == fifo && h->gkey.spg == spg;
+        if (!hit) {
+            drop_graphs(h);
+            while (h->fifo_ev.size() < (size_t)spg * bp.n * FIFO_STRIDE) {
+                cudaEvent_t ev = nullptr;
+                CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                h->fifo_ev.push_back(ev);
+            }
+            for (int slot = 0; slot < 2; ++slot) {
+                const int ns = slot == 0 ? 1 : spg;
+                const int64_t before = h->launches;
+                CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+                cudaError_t ce = cudaEventRecord(h->fork_ev, cs);
+                for (int i = 1; i < bp.n && ce == cudaSuccess; ++i) ce = cudaStreamWaitEvent(h->branch_stream[i], h->fork_ev, 0);
+                r = 0;
+                for (int s2 = 0; s2 < ns && !r && ce == cudaSuccess; ++s2)
+                    for (int i = 0; i < bp.n && !r; ++i) {
+                        const int j = s2 * bp.n + i;                 // position in the FIFO order (step-major, then branch)
+                        h->fifo_rec = h->fifo_ev.data() + (size_t)j * FIFO_STRIDE;
+                        h->fifo_wait = j >= fifo ? h->fifo_ev.data() + (size_t)(j - fifo) * FIFO_STRIDE : nullptr;
+                        r = enqueue_decode_step(h, B, bp.row0[i], bp.rows[i], i, tcap, eos, d_enc_off, max_s, sum_s, -1,
+                                                i == 0 ? cs : h->branch_stream[i]);
+                    }
+                h->fifo_rec = nullptr; h->fifo_wait = nullptr;
+                for (int i = 1; i < bp.n && ce == cudaSuccess && !r; ++i) {
+                    ce = cudaEventRecord(h->join_ev[i], h->branch_stream[i]);
+                    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs, h->join_ev[i], 0);
+                }
+                cudaError_t ee = cudaStreamEndCapture(cs, &h->cgraph[slot]);
+                if (r) return r;
+                CK(ce);
+                CK(ee);
+                CK(cudaGraphInstantiate(&h->cgraph_exec[slot], h->cgraph[slot], 0));
+                h->cgraph_kernels[slot] = (int)(h->launches - before);
+                h->launches = before;
+            }
+            h->gkey.samp = samp_key; h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
+            h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv_hm.p; h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
+            h->gkey.fifo = fifo; h->gkey.spg = spg;
+        }
+        CK(cudaEventRecord(h->fork_ev, st));
+        CK(cudaStreamWaitEvent(cs, h->fork_ev, 0));
+        for (int s2 = 0; s2 < 2; ++s2)
+            if (!h->poll_ev[s2][0]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][0], cudaEventDisableTiming));
+        for (int i = 0; i < bp.n; ++i)
+            if ((r = enqueue_first_embed(h, B, bp.row0[i], bp.rows[i], i, cs))) return r;
+        const int POLL = 16;
+        int polls = 0, next_poll = POLL;
+        bool stop = false;
+        for (int t = 0; t < max_len && !stop;) {
+            const int slot = (max_len - t >= spg && spg > 1) ? 1 : 0;
+            CK(cudaGraphLaunch(h->cgraph_exec[slot], cs));
+            h->launches += h->cgraph_kernels[slot];
+            t += slot ? spg : 1;
+            if (eos >= 0 && t >= next_poll && t < max_len) {
+                next_poll += POLL;
+                const int ps = polls & 1;
+                if (polls >= 1) {
+                    CK(cudaEventSynchronize(h->poll_ev[ps ^ 1][0]));
+                    bool all = true;
+                    for (int i = 0; i < bp.n; ++i) all = all && h->h_poll[(ps ^ 1) * MAX_BRANCH + i] > 0;
+                    if (all) stop = true;
+                }
+                CK(cudaMemcpyAsync(&h->h_poll[ps * MAX_BRANCH], ds.done_step, (size_t)bp.n * 4, cudaMemcpyDeviceToHost, cs));
+                CK(cudaEventRecord(h->poll_ev[ps][0], cs));
+                ++polls;
+            }
+        }
+        CK(cudaEventRecord(h->join_ev[0], cs));
+        CK(cudaStreamWaitEvent(st, h->join_ev[0], 0));
+    }
+    if (fifo > 0) {
+    } else if (graph_ok) {
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
                          h->gkey.samp == (h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0) && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
@@ -1110,12 +1234,12 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     for (int s2 = 0; s2 < 2; ++s2)
         for (int i = 0; i < bp.n; ++i)
             if (!h->poll_ev[s2][i]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][i], cudaEventDisableTiming));
-    for (int i = 0; i < bp.n; ++i)
+    for (int i = 0; i < bp.n && fifo == 0; ++i)
         if ((r = enqueue_first_embed(h, B, bp.row0[i], bp.rows[i], i, bst[i]))) return r;
     // Host runs ahead of the device by at most 2*POLL steps; an early exit costs at most that many extra steps.
     const int POLL = 16;
     int issued = 0, polls = 0;
-    bool stop = false;
+    bool stop = fifo > 0;
     for (int t = 0; t < max_len && !stop; ++t) {
         if (graph_ok) {
             for (int i = 0; i < bp.n; ++i) { CK(cudaGraphLaunch(h->bgraph_exec[i], bst[i])); h->launches += h->gkey.kernels; }
@@ -1138,7 +1262,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
             ++polls;
         }
     }
-    if (graph_ok && bp.n > 1) {      // join
+    if (graph_ok && bp.n > 1 && fifo == 0) {      // join
         for (int i = 0; i < bp.n; ++i) {
             CK(cudaEventRecord(h->join_ev[i], bst[i]));
             CK(cudaStreamWaitEvent(st, h->join_ev[i], 0));
@@ -1541,6 +1665,10 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "attn_trace")) { h->attn_trace_on = value != 0; drop_graphs(h); return 0; }
+    if (!strcmp(name, "attn_fifo")) { h->attn_fifo = (int)std::max<int64_t>(0, std::min<int64_t>(MAX_BRANCH, value)); return 0; }
+    if (!strcmp(name, "steps_per_graph")) { h->steps_per_graph = (int)std::max<int64_t>(1, std::min<int64_t>(16, value)); return 0; }
+    if (!strcmp(name, "fifo_pdl")) { h->fifo_pdl = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_full_tail")) { g_attn_full_tail = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "fuse_ln")) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "poison")) { h->poison = value != 0; return 0; }
@@ -1590,7 +1718,7 @@ int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_
     {   // raw workspace taps (byte-exact copies reinterpreted as float32 words): name -> buffer
         struct { const char* n; DevBuf* b; } taps[] = {{"logits", &h->logits}, {"kvcache", &h->kvcache}, {"x", &h->x}, {"s", &h->s},
                                                        {"xn", &h->xn}, {"qkv", &h->qkv}, {"o", &h->o}, {"hid", &h->hid},
-                                                       {"crosskv_hm", &h->crosskv_hm}, {"enc_out", &h->enc_out}};
+                                                       {"crosskv_hm", &h->crosskv_hm}, {"enc_out", &h->enc_out}, {"attn_trace", &h->attn_trace}};
         for (auto& t : taps)
             if (!strcmp(name, t.n)) {
                 if (!t.b->p) return fail(h, TEXOCR_ERR_STATE, "buffer '%s' not allocated", name);

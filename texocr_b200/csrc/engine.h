@@ -81,6 +81,7 @@ struct texocr_handle {
     DevBuf dec_state;                          // int64 cur_tok[B] | int32 step, done_step, block_counter, pad | int32 seen[B]
     DevBuf out_ids;                            // int64 [B, max_len]
     DevBuf mega_dbg;
+    DevBuf attn_trace; bool attn_trace_on = false;   // debug timeline of the decode attention launches: [branch][3][256 steps][8] u64 ns
     DevBuf prep_meta, prep_in, prep_out;       // texocr_preprocess_u8 staging
     DevBuf mega_part;                          // cluster-persistent decode kernel: per-CTA argmax partials [B][16] (float | int)
     int* h_poll = nullptr;                     // pinned: done_step polls
@@ -93,7 +94,16 @@ struct texocr_handle {
     cudaGraph_t bgraph[16] = {nullptr}; cudaGraphExec_t bgraph_exec[16] = {nullptr};   // one single-step graph per branch
     cudaEvent_t poll_ev[2][16] = {{nullptr}};
     int stagger_us = 30;                        // start offset between consecutive branches
-    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; } gkey;
+    // Coupled mode (attn_fifo = m > 0): all branches of `steps_per_graph` decode steps are captured into ONE graph in which
+    // attention launch k of branch i additionally depends on attention launch k of branch i - m, so that at most m branches
+    // stream K/V at a time and the others run their GEMM / LayerNorm chains meanwhile.
+    int attn_fifo = 0;
+    int steps_per_graph = 4;
+    int fifo_pdl = 1;                           // attention launches that carry a cross-branch dependency keep their programmatic edge
+    cudaGraph_t cgraph[2] = {nullptr, nullptr}; cudaGraphExec_t cgraph_exec[2] = {nullptr, nullptr}; int cgraph_kernels[2] = {0, 0};
+    std::vector<cudaEvent_t> fifo_ev;           // [step in graph][branch][8 attention launches]
+    cudaEvent_t* fifo_wait = nullptr; cudaEvent_t* fifo_rec = nullptr;     // set around enqueue_decode_step while capturing
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; int fifo = 0; int spg = 0; } gkey;
 
     // ---- instrumentation
     int64_t launches = 0;

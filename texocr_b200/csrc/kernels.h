@@ -157,6 +157,8 @@ struct AttnDecodeArgs {
     const int* step;                   // self: number of cached keys before this step = *step
     void* o; int ldo;
     int batch, dt;
+    // debug timeline (TMA kernel only; null = off): entry / ready / end globaltimer stamps of launch `trace_k` of step *trace_step
+    unsigned long long* trace; const int* trace_step; int trace_k;
 };
 // nk_cap >= the largest key count any row can have (sizes the per-head score buffer in shared memory)
 cudaError_t launch_attn_decode(const AttnDecodeArgs& a, int nk_cap, cudaStream_t st);
