@@ -6,7 +6,10 @@ greedy, max_len 256).
     python bench.py --impl reference ...                            # the reference's CPU algorithm (oracle port)
 
 A step = one pass of the hot path over one batch: encoder -> cross-K/V -> 256 greedy decode steps for
-B=512 synthetic 64x384 images per GPU (BASELINE.json configs[2]).  N>1: one process per GPU (torchrun), the image
+B=512 synthetic 64x384 images per GPU (BASELINE.json configs[2]).  The K timed steps are K independent batches; up to
+--in-flight of them are decoded concurrently on the GPU (texocr_b200/pipeline.py: one engine handle, host thread and
+stream per batch in flight -- one batch alone is bound by the latency of its kernel chain, not by the machine); the
+one-batch-at-a-time number is reported next to it.  N>1: one process per GPU (torchrun), the image
 list is sharded contiguously, every rank decodes its shard independently and the token ids are gathered
 with one NCCL all_gather per step ("scaling": "weak").  One JSON line is printed by rank 0.
 """
@@ -20,6 +23,8 @@ import subprocess
 import sys
 import threading
 import time
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # one hardware queue per stream (branches x batches in flight)
 
 import torch
 
@@ -210,11 +215,13 @@ def measure_next_rows(model, img_dev, peaks, stream):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="equations per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--in-flight", type=int, default=6, help="batches decoded concurrently per GPU (1 = one at a time)")
+    ap.add_argument("--branches", type=int, default=1, help="decode branches per batch when several batches are in flight")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -251,18 +258,27 @@ def main():
     img_dev = img_host.cuda()
     out_host = torch.empty((hi - lo, MAX_LEN), dtype=torch.int64).pin_memory()
     stream = torch.cuda.current_stream()
+    n_fly = max(1, min(args.in_flight, args.steps))
+    pipe = None
+    if n_fly > 1:
+        from texocr_b200.pipeline import GeneratePipeline
+        pipe = GeneratePipeline(model, in_flight=n_fly, branches=args.branches)
+        outs_host = [torch.empty((hi - lo, MAX_LEN), dtype=torch.int64).pin_memory() for _ in range(args.steps)]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, whole=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
-            fn()
+        if whole:
+            fn(steps)          # runs all `steps` batches (several in flight); returns after the last one has completed
+        else:
+            for _ in range(steps):
+                fn()
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -280,22 +296,50 @@ def main():
             gather_tokens(tok.cuda(non_blocking=True), world)
         return tok
 
+    def steps_device(k):       # k batches resident in HBM through the pipeline (public API: GeneratePipeline.generate_batches)
+        for tok in pipe.generate_batches([img_dev] * k, MAX_LEN):
+            gather_tokens(tok, world)
+
+    def steps_e2e(k):          # k batches from pinned HOST memory, token ids back to pinned host memory
+        for tok in pipe.generate_batches([img_host] * k, MAX_LEN, outs=outs_host[:k]):
+            if world > 1:
+                gather_tokens(tok.cuda(non_blocking=True), world)
+
     for _ in range(args.warmup):
         step_device()
+    if pipe is not None:
+        pipe.warm_up(img_dev, MAX_LEN)
+        for _ in range(args.warmup):
+            steps_device(n_fly)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    l0 = eng.kernel_launches()
-    ms = timed(step_device, args.steps)
-    launches = eng.kernel_launches() - l0
+    serial = None
+    if pipe is None:
+        l0 = eng.kernel_launches()
+        ms = timed(step_device, args.steps)
+        launches = eng.kernel_launches() - l0
+    else:
+        l0 = pipe.kernel_launches()
+        ms = timed(steps_device, args.steps, whole=True)
+        launches = pipe.kernel_launches() - l0
+        ms_1 = timed(step_device, args.steps)
+        serial = {"value": world * B * args.steps / (ms_1 / 1e3), "unit": UNIT, "ms_per_step": ms_1 / args.steps,
+                  "note": "the same K batches, one model.generate call at a time (6 decode branches per batch)"}
     clk = clocks.stop()
     value = world * B * args.steps / (ms / 1e3)
 
     e2e = None
     if not args.no_e2e:
-        step_e2e()
-        ms_e = timed(step_e2e, args.steps)
+        if pipe is None:
+            step_e2e()
+            ms_e = timed(step_e2e, args.steps)
+        else:
+            steps_e2e(n_fly)
+            ms_e = timed(steps_e2e, args.steps, whole=True)
         e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(img_host.numel() * 4 * world), "d2h_bytes_per_step": int(out_host.numel() * 8 * world)}
+    if pipe is not None:
+        pipe.close()
 
     # ---- roofline of the dominant kernel.  One extra step is launched eagerly (no CUDA graph, one decode branch so that every
     # kernel sees the full batch) with CUDA events around every launch on the launching stream (texocr_profile_*); the
@@ -379,8 +423,9 @@ def main():
                                f"max_len {MAX_LEN}, default config.yml model (ResNetV2-hybrid ViT encoder + 4-layer decoder), random-init weights",
                    "batch_per_gpu": B, "max_len": MAX_LEN, "image": [H, W], "precision": args.precision,
                    "parallelism": f"dp{world} (independent shards, token-id all_gather)",
+                   "batches_in_flight": n_fly, "decode_branches_per_batch": args.branches if n_fly > 1 else 6,
                    "l2_policy": "working set (KV cache >= 1 GB, activations >= 3 GB per step) exceeds the 126 MB L2; no explicit flush"},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernel_time_shares": shares,
+        "e2e": e2e, "one_batch_at_a_time": serial, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernel_time_shares": shares,
         "cpu_baseline": cpu_baseline, "encoder": encoder, "next_rows": next_rows,
     }
     print(json.dumps(line), flush=True)

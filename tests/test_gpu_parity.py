@@ -192,6 +192,46 @@ def test_decode_branches_do_not_change_tokens(m16, golden):
     assert res[0].shape == res[1].shape and torch.equal(res[0], res[1])
 
 
+def test_coupled_step_graph_does_not_change_tokens(m16):
+    """Opt-in coupled mode: all branches of several decode steps in one graph, attention launches chained across branches
+    (attn_fifo).  Same kernels, same tokens; early exit keeps its contract with multi-step graphs."""
+    img = synth.synth_images(64, 32, 128, seed=12).cuda()
+    eng = m16.engine()
+    eng.set_option("decode_branches", 4)
+    ref = m16.generate(img, 37)
+    enc = m16.encoder(img)
+    start = torch.full((64, 1), m16.dims.bos, dtype=torch.long, device="cuda")
+    eos = int(ref[0, 9])
+    ref_e = m16.decoder.generate(start_tokens=start, eos_tok=eos, max_len=37, enc=enc)
+    try:
+        for fifo, spg in ((1, 4), (2, 1), (4, 8)):
+            eng.set_option("attn_fifo", fifo)
+            eng.set_option("steps_per_graph", spg)
+            assert torch.equal(m16.generate(img, 37), ref), (fifo, spg)
+            out_e = m16.decoder.generate(start_tokens=start, eos_tok=eos, max_len=37, enc=enc)
+            assert out_e.shape == ref_e.shape and torch.equal(out_e, ref_e), (fifo, spg)
+    finally:
+        eng.set_option("attn_fifo", 0)
+        eng.set_option("decode_branches", 0)
+
+
+def test_pipeline_of_batches_in_flight_matches_generate(m16):
+    """GeneratePipeline (several batches decoded concurrently by replica handles on their own host threads / streams):
+    every batch gets exactly the tokens model.generate gives it, for device and for host (pinned) buffers."""
+    from texocr_b200.pipeline import GeneratePipeline
+    batches = [synth.synth_images(40 + 8 * i, 32, 128 + 64 * (i % 2), seed=30 + i) for i in range(5)]
+    ref = [m16.generate(b.cuda(), 24).cpu() for b in batches]
+    with GeneratePipeline(m16, in_flight=3, branches=2) as pipe:
+        pipe.warm_up(batches[0].cuda(), 24)
+        got = [t.cpu() for t in pipe.generate_batches([b.cuda() for b in batches], 24)]
+        outs = [torch.empty((b.shape[0], 24), dtype=torch.int64).pin_memory() for b in batches]
+        got_h = list(pipe.generate_batches([b.pin_memory() for b in batches], 24, outs=outs))
+        assert pipe.kernel_launches() > 0
+    for r, g, gh, o in zip(ref, got, got_h, outs):
+        assert torch.equal(r, g)
+        assert not gh.is_cuda and torch.equal(r, gh) and gh.data_ptr() == o.data_ptr()
+
+
 def test_tma_attention_matches_simple_kernel(m16):
     """The persistent TMA-fed decode attention and the simple per-sequence kernel compute the same attention."""
     img = synth.synth_images(40, 64, 384, seed=21).cuda()

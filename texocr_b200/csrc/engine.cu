@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "decode_mega.h"
 extern int g_tc_split_k;
@@ -24,6 +25,10 @@ extern int g_tc_persistent;
 #include "tc_gemm.h"
 
 static std::string g_create_error;
+// Several handles may be driven from different host threads (texocr_b200/pipeline.py).  Stream capture and device-wide
+// operations do not mix across threads (a cudaDeviceSynchronize / cudaFree in one thread invalidates a capture in
+// another), so graph capture and (re)allocation take this process-wide lock.  Steady-state calls never hold it.
+static std::recursive_mutex g_dev_mu;
 // bits 0..5: programmatic dependent launch per kernel family (kernels.h); bit 8 / 9: LayerNorm / GEMM kernels release their
 // dependents only after their stores (experiment switches; the default is an early trigger everywhere).
 int g_texocr_pdl = 0x3f;
@@ -86,6 +91,7 @@ static void drop_graphs(texocr_handle* h) {
 
 static int ensure(texocr_handle* h, DevBuf& b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return 0;
+    std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
     if (b.p) { CK(cudaDeviceSynchronize()); CK(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
     size_t want = std::max(bytes, (size_t)256);
     want = (want + 255) & ~(size_t)255;
@@ -1132,6 +1138,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
                          h->gkey.max_s == max_s && h->gkey.samp == samp_key && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p &&
                          h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n && h->gkey.fifo == fifo && h->gkey.spg == spg;
         if (!hit) {
+            std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
             drop_graphs(h);
             while (h->fifo_ev.size() < (size_t)spg * bp.n * FIFO_STRIDE) {
                 cudaEvent_t ev = nullptr;
@@ -1206,6 +1213,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
                          h->gkey.samp == (h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0) && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
+            std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
             drop_graphs(h);
             const int64_t before = h->launches;
             for (int i = 0; i < bp.n; ++i) {
@@ -1321,6 +1329,7 @@ int texocr_create(const texocr_config* cfg, int device, texocr_handle** out) {
 
 void texocr_destroy(texocr_handle* h) {
     if (!h) return;
+    std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     drop_graphs(h);
@@ -1330,7 +1339,7 @@ void texocr_destroy(texocr_handle* h) {
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
                       &h->proj_out, &h->patch_cols, &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
                       &h->enc_out, &h->enc_a, &h->crosskv, &h->crosskv_hm, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
-                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg, &h->prep_meta, &h->prep_in, &h->prep_out};
+                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg, &h->attn_trace, &h->prep_meta, &h->prep_in, &h->prep_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);
