@@ -15,7 +15,8 @@
  *    on `stream`.  Device pointers must belong to the handle's device.
  *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work is
  *    enqueued on it; calls that return host-visible results synchronise that stream.
- *  - one handle per process per GPU; a handle is not thread-safe.
+ *  - a handle is not thread-safe; different handles (also on the same GPU) are independent and may be driven from different
+ *    host threads concurrently -- that is how several batches are kept in flight (texocr_b200/pipeline.py).
  *  - hw, enc_len and n_steps are always HOST arrays (they drive the host-side launch plan).
  *  - images: float32, single channel, row-major, ink = 1 on a 0 background
  *    (data_wrangling/dataset.py:365-371).  A batch is RAGGED: image i is hw[2*i] x hw[2*i+1],
