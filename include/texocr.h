@@ -174,6 +174,14 @@ TEXOCR_API int texocr_debug_attn_decode(texocr_handle* h, int32_t self, const vo
                              const int32_t* k_off_dev, const int32_t* step_dev, void* out, int32_t batch, int32_t max_keys,
                              int32_t use_tma, void* stream);
 
+/* Test hook: one launch of the absorbed decode-attention kernel of the bf16 generate loop: q bf16
+ * [batch, 8 x 256] absorbed queries; out bf16 [batch, 8 x 256] = softmax(q_h . Z^T / 8) . Z per head over the sequence's latent rows Z.
+ * Cross (znew == NULL): latent bf16 [latent_rows, 256] = encoder memory, k_off_dev int32 [batch + 1] token ranges (device).
+ * Self (znew != NULL): latent = cache bf16 [batch][tcap][256] with *step_dev valid rows per sequence; znew bf16 [batch, 256] is this
+ * step's own row: used as key *step_dev and appended to the cache. */
+TEXOCR_API int texocr_debug_attn_abs(texocr_handle* h, const void* q, void* latent, int64_t latent_rows, const int32_t* k_off_dev,
+                          const void* znew, int32_t tcap, const int32_t* step_dev, void* out, int32_t batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

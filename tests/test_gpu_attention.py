@@ -68,3 +68,50 @@ def test_cross_attention_decode_ragged(eng, use_tma):
             ref = _ref(q[b].float().reshape(8, 64), rows[:, :, :64].permute(1, 0, 2), rows[:, :, 64:].permute(1, 0, 2))
             err = (out[b].float() - ref).abs().max() / ref.abs().max()
             assert err < 2e-2, (layer, b, lens[b], float(err))
+
+
+def test_cross_attention_absorbed_ragged(eng):
+    """attn_abs_kernel<cross>: per head softmax(q'_h . enc^T * 0.125) . enc over the sequence's own memory tokens, all 8 heads
+    sharing the [S, 256] bf16 memory; ragged lengths incl. 1 token, non-multiples of 4 / 16 and the 631-token maximum."""
+    lens = [17, 97, 100, 253, 1, 16, 33, 631, 97, 97, 64, 2, 3, 15] * 12
+    B = len(lens)
+    off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    ntok = int(off[-1])
+    g = torch.Generator(device="cuda").manual_seed(9)
+    enc = torch.randn(ntok, 256, device="cuda", generator=g).to(torch.bfloat16)
+    q = (torch.randn(B, 2048, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    out = eng.debug_attn_abs(q, enc, k_off=off)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    for b in range(B):
+        mem = enc[int(off[b]):int(off[b + 1])].float()
+        s = (q[b].float().reshape(8, 256) @ mem.T) * 0.125
+        ref = (torch.softmax(s, dim=-1) @ mem).reshape(-1)
+        err = (out[b].float() - ref).abs().max() / ref.abs().max()
+        assert err < 2e-2, (b, lens[b], float(err))
+    assert torch.equal(out, eng.debug_attn_abs(q, enc, k_off=off))
+
+
+@pytest.mark.parametrize("B", [37, 300])
+@pytest.mark.parametrize("t", [0, 1, 3, 4, 5, 12, 15, 16, 17, 31, 32, 33, 100, 255])
+def test_self_attention_absorbed(eng, t, B):
+    """attn_abs_kernel<self>: keys = the t cached latent rows + this step's own row (appended to the cache by the kernel)."""
+    tcap = 256
+    g = torch.Generator(device="cuda").manual_seed(100 + t)
+    cache = torch.randn(B * tcap, 256, device="cuda", generator=g).to(torch.bfloat16)
+    cache.view(B, tcap, 256)[:, t:] = float("nan")            # rows not yet written must never matter
+    znew = torch.randn(B, 256, device="cuda", generator=g).to(torch.bfloat16)
+    q = (torch.randn(B, 2048, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    step = torch.tensor([t], dtype=torch.int32, device="cuda")
+    out = eng.debug_attn_abs(q, cache, znew=znew, tcap=tcap, step=step)
+    torch.cuda.synchronize()
+    assert torch.equal(cache.view(B, tcap, 256)[:, t], znew)                      # appended
+    if t + 1 < tcap:
+        assert torch.isnan(cache.view(B, tcap, 256)[:, t + 1:].float()).all()     # nothing else touched
+    z = cache.view(B, tcap, 256)[:, : t + 1].float()
+    s = torch.einsum("bhc,bjc->bhj", q.float().view(B, 8, 256), z) * 0.125
+    ref = torch.einsum("bhj,bjc->bhc", torch.softmax(s, dim=-1), z).reshape(B, 2048)
+    err = (out.float() - ref).abs().amax(1) / ref.abs().amax(1)
+    assert torch.isfinite(out.float()).all() and float(err.max()) < 2e-2, float(err.max())
+    cache.view(B, tcap, 256)[:, t] = float("nan")
+    assert torch.equal(out, eng.debug_attn_abs(q, cache, znew=znew, tcap=tcap, step=step))      # run-to-run reproducible

@@ -39,6 +39,12 @@ def m16(sd):
     return _model(sd, "bf16")
 
 
+def _absorb(eng, on, self_on=None):
+    """bf16 generate loop: absorbed (latent) attention for cross / self-attention on or off (off = projected K/V caches)."""
+    eng.set_option("cross_absorb", int(on))
+    eng.set_option("self_absorb", int(on if self_on is None else self_on))
+
+
 def _img(golden, name):
     B, H, W, dense, seed = [int(v) for v in golden[f"enc_{name}_shape"]]
     return synth.synth_images(B, H, W, seed=seed, dense=bool(dense))
@@ -239,10 +245,12 @@ def test_tma_attention_matches_simple_kernel(m16):
     enc = m16.encoder(img)
     trg = synth.synth_labels(40, 40, m16.dims, seed=5).cuda()
     outs = []
+    _absorb(eng, 0)         # compare the two kernels on the same (projected K/V) formulation
     for tma in (1, 0):
         eng.set_option("tma_attention", tma)
         outs.append(m16.generate(img, 40))
     eng.set_option("tma_attention", 1)
+    _absorb(eng, 1)
     same = (outs[0] == outs[1]).float().mean().item()
     assert same > 0.90, same          # same math up to bf16 rounding of the softmax weights: only near-ties may flip
     # teacher-forced logits of the generated prefix agree with the decode loop's choices (KV cache == full recompute)
@@ -257,11 +265,50 @@ def test_layernorm_fused_gemm_is_bit_identical(m16):
     img = synth.synth_images(300, 64, 384, seed=31).cuda()
     eng = m16.engine()
     outs = []
+    _absorb(eng, 0)         # the fused-LayerNorm path keeps the projected K/V formulation
     for fuse in (1, 0):
         eng.set_option("fuse_ln", fuse)
         outs.append(m16.generate(img, 40))
     eng.set_option("fuse_ln", 0)
+    _absorb(eng, 1)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_absorbed_attention_matches_projected_kv(m16, m32):
+    """bf16 generate loop: attention with the K / V projections absorbed into the query / output projections (the decode loop
+    streams 256-wide latent rows -- encoder memory / cached LayerNorm'd inputs -- instead of per-head K/V) is the same function:
+    first-step logits within the bf16 tolerance of the fp32 parity tier, the same tokens as the projected-K/V path up to
+    near-ties, and agreement with the teacher-forced decoder on its own prefix."""
+    widths = synth.synth_widths(48, seed=3)
+    src = [synth.synth_images(1, 64, int(w), seed=700 + i)[0].cuda() for i, w in enumerate(widths)]      # ragged memory lengths
+    eng = m16.engine()
+    B, V = len(src), m16.dims.vocab
+
+    def first_logits(model):
+        model.generate(src, 1)
+        return model.engine().debug_read("logits", B * V).reshape(B, V).cpu()
+
+    ref32 = first_logits(m32)
+    modes = ((1, 1), (0, 0), (1, 0), (0, 1))          # (cross, self)
+    try:
+        lg, toks = {}, {}
+        for mode in modes:
+            _absorb(eng, mode[0], mode[1])
+            lg[mode] = first_logits(m16)
+            toks[mode] = m16.generate(src, 40)
+            assert torch.equal(toks[mode], m16.generate(src, 40)), mode          # deterministic
+    finally:
+        _absorb(eng, 1)
+    assert not torch.equal(lg[(0, 0)], lg[(1, 1)])                               # the formulations really differ in rounding
+    for mode in modes:
+        assert rel_max(lg[mode].numpy(), ref32.numpy()) < BF16_TOL, mode
+        assert (toks[mode] == toks[(0, 0)]).float().mean().item() > 0.9, mode
+    img = synth.synth_images(32, 64, 384, seed=41).cuda()
+    out = m16.generate(img, 40)
+    enc = m16.encoder(img)
+    ids = torch.cat((torch.full((32, 1), m16.dims.bos, device="cuda"), out[:, :-1]), 1)
+    agree = (m16.decoder.net(ids, enc=enc).argmax(-1) == out).float().mean().item()
+    assert agree > 0.97, agree
 
 
 def test_cluster_persistent_decode_kernel_matches_branch_path(m16):
@@ -275,7 +322,9 @@ def test_cluster_persistent_decode_kernel_matches_branch_path(m16):
             imgs = [synth.synth_images(1, 64, int(w), seed=1000 * B + i)[0] for i, w in enumerate(widths)]
             src = [im.cuda() for im in imgs]
             eng.set_option("decode_mega", 0)
+            _absorb(eng, 0)                  # the cluster kernel implements the projected-K/V formulation
             ref = m16.generate(src, T)
+            _absorb(eng, 1)
             eng.set_option("decode_mega", 1)
             out = m16.generate(src, T)
             eng.set_option("mega_steps", 5)

@@ -23,7 +23,7 @@ EXPORTS = (
     "texocr_create", "texocr_destroy", "texocr_last_error", "texocr_set_weight", "texocr_finalize_weights",
     "texocr_encode", "texocr_decoder_logits", "texocr_decoder_generate", "texocr_generate", "texocr_cross_entropy",
     "texocr_kernel_launches", "texocr_profile_enable", "texocr_profile_read", "texocr_set_option", "texocr_debug_read",
-    "texocr_debug_gemm", "texocr_debug_attn_decode", "texocr_set_sampling", "texocr_debug_sample_step", "texocr_preprocess_u8",
+    "texocr_debug_gemm", "texocr_debug_attn_decode", "texocr_debug_attn_abs", "texocr_set_sampling", "texocr_debug_sample_step", "texocr_preprocess_u8",
 )
 
 
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     lib.texocr_debug_read.restype = i64
     lib.texocr_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]
     lib.texocr_debug_attn_decode.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i64, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
+    lib.texocr_debug_attn_abs.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp, vp, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib
@@ -287,6 +288,16 @@ class Engine:
             self.h, 1 if self_attn else 0, q.data_ptr(), q.stride(0), ptr(knew), ptr(vnew), 0 if knew is None else knew.stride(0),
             kv.data_ptr(), kv.shape[0], kv.stride(0), col0, tcap, ptr(k_off), ptr(step), out.data_ptr(), batch, max_keys,
             1 if use_tma else 0, self._stream()))
+        return out
+
+    def debug_attn_abs(self, q: torch.Tensor, latent: torch.Tensor, k_off: Optional[torch.Tensor] = None,
+                       znew: Optional[torch.Tensor] = None, tcap: int = 0, step: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Test hook: absorbed decode attention; q bf16 [B, 2048], latent bf16 [rows, 256]; cross: k_off int32 [B+1] (device);
+        self: znew bf16 [B, 256], tcap, step int32 [1] (device) -> bf16 [B, 2048]."""
+        out = torch.zeros((q.shape[0], 2048), dtype=torch.bfloat16, device=self.device)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        self._check(self.lib.texocr_debug_attn_abs(self.h, q.data_ptr(), latent.data_ptr(), latent.shape[0], ptr(k_off), ptr(znew),
+                                                   int(tcap), ptr(step), out.data_ptr(), q.shape[0], self._stream()))
         return out
 
     def debug_read(self, name: str, numel: int) -> torch.Tensor:

@@ -72,6 +72,11 @@ TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol) : "memory");
 }
+TX_DEVINL void tma_load_2d_nohint(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 TX_DEVINL void ldsm_x4(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, uint32_t& d3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(addr));
 }
@@ -324,6 +329,216 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
     if (tr) atomicMax(tr + 4096, gtime());
 }
 
+
+// ------------------------------------------------------------------------------------------------ absorbed ("latent") attention
+// Decode-step attention of the bf16 generate loop with the key / value projections absorbed into the query and output
+// projections.  For a head h with key / value weights Wk_h, Wv_h [64 x 256] and latent rows z_j [256] (cross-attention:
+// z_j = encoder memory token j; self-attention: z_j = the layer's LayerNorm'd input at position j, i.e. what the reference
+// feeds to to_k / to_v, model/attention.py:114-126):
+//   q_h . K_h[j] = q_h . (Wk_h z_j) = (q_h Wk_h) . z_j                   Q'_h = q_h Wk_h       (256 wide; folded query GEMM)
+//   sum_j p_h[j] V_h[j] = (sum_j p_h[j] z_j) Wv_h^T                      C_h = P_h . Z         (256 wide; folded out-projection)
+// so all 8 heads of a sequence stream the SAME [n, 256] bf16 latent rows instead of their own [n, 64 | 64] K/V slices:
+// 512 bytes per key and layer instead of 2,048 -- 4x less HBM traffic for the loop's dominant stream, and the self-attention
+// cache holds 256 instead of 1,024 values per position (model/attention.py:148-173 computes the left-hand sides).
+// Work unit = sequence.  The 8 heads are rows 0..7 of the 16-row mma.sync A operand.  Stage = 16 latent rows x 256 columns as
+// four 64-column TMA boxes (128B swizzle), 8 KB.  Four consumer warps, warp w owns column block w: it computes the partial
+// scores Q'[:, 64w..64w+63] . Z[:, 64w..]^T (8 MMAs, k = 64), the partials are summed through shared memory (one named barrier per
+// stage, double-buffered), every warp runs the identical online softmax, and accumulates C[:, 64w..64w+63] += P . Z[:, 64w..] (8 MMAs).
+// Self-attention: this step's own latent row (position t) is written into the last stage by the consumers (it is key t of
+// that stage) and appended to the cache for the following steps.
+constexpr int AW = 4;                       // consumer warps = 64-column blocks of a latent row
+struct AbsArgs {
+    const bf16* q; int ldq;            // [batch, ldq]: head h at h*256 (absorbed query, unscaled)
+    const int* k_off;                  // cross: token offsets [batch + 1] into the latent matrix the tensor maps cover
+    const bf16* znew; int ldz;         // self: this step's latent rows [batch, ldz]
+    bf16* cache; int tcap;             // self: latent cache [batch][tcap][256] (row b*tcap + j); the tensor maps cover it
+    const int* step;                   // self: positions already cached (= index of this step's row)
+    bf16* o; int ldo;                  // [batch, ldo]: head h at h*256
+    int batch;
+    unsigned long long* trace; const int* trace_step; int trace_k;
+};
+
+template <bool SELF>
+__global__ void __launch_bounds__(32 * (AW + 1), 4) attn_abs_kernel(const __grid_constant__ CUtensorMap tm,
+                                                                 const __grid_constant__ CUtensorMap tm4, const AbsArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    float* xbuf = reinterpret_cast<float*>(ring + NS * STAGE);            // [2][AW][8 heads][16 keys] partial scores
+    uint64_t* full = reinterpret_cast<uint64_t*>(xbuf + 2 * AW * 8 * CH);
+    uint64_t* empty = full + NS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    pdl_launch_dependents();
+    const unsigned long long t_entry = a.trace ? gtime() : 0ull;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm4) : "memory");
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // cross: the producer only reads the encoder memory and the token offsets, both written before the generate loop started
+    if (SELF || warp != 0) pdl_wait();
+    const int units = a.batch;
+    const int t = SELF ? ldcg_i32(a.step) : 0;
+    unsigned long long* tr = nullptr;
+    if (a.trace && threadIdx.x == 32) {
+        const int ts = min(ldcg_i32(a.trace_step), 255);
+        tr = a.trace + (size_t)ts * 8 + a.trace_k;
+        atomicMin(tr, t_entry);
+        atomicMin(tr + 2048, gtime());
+    }
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            if (SELF) asm volatile("fence.proxy.async.global;" ::: "memory");     // cache rows were appended by generic-proxy stores of earlier steps
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                int row0, nc;      // nc = rows to fetch; self: the t cached rows (this step's own row is added by the consumers)
+                if (SELF) { row0 = u * a.tcap; nc = t; }
+                else { row0 = ldcg_i32(a.k_off + u); nc = ldcg_i32(a.k_off + u + 1) - row0; }
+                const int nchunk = ((SELF ? nc + 1 : nc) + CH - 1) / CH;
+                for (int c = 0; c < nchunk; ++c, ++it) {
+                    const int s = it % NS, ph = (it / NS) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = ring + s * STAGE;
+                    const int left = nc - c * CH, r = row0 + c * CH;
+                    if (left >= CH) {
+                        mbar_expect_tx(&full[s], STAGE);
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) tma_load_2d_nohint(&tm, &full[s], st + cb * HTILE, 64 * cb, r);
+                    } else {               // tail: 4-row boxes (none at all when only this step's own row is left)
+                        const int n4 = left > 0 ? (left + 3) >> 2 : 0;
+                        mbar_expect_tx(&full[s], n4 * 4 * 512);
+                        for (int j = 0; j < n4; ++j)
+#pragma unroll
+                            for (int cb = 0; cb < 4; ++cb) tma_load_2d_nohint(&tm4, &full[s], st + cb * HTILE + j * 512, 64 * cb, r + 4 * j);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------- consumers: warp w+1 owns column block w
+    const int cw = warp - 1;
+    const int g = lane >> 2, tq = lane & 3;               // fragment row (= head) / thread-in-group
+    const int lm_r = lane & 7, lm_m = lane >> 3;
+    int it = 0;
+    uint32_t qn[8];
+    auto load_header = [&](int u) {       // words of row g, columns 64cw..: k-step s holds dims 16s+2t,+1 and 16s+8+2t,+1
+        const uint32_t* qp = reinterpret_cast<const uint32_t*>(a.q + (size_t)u * a.ldq + g * 256 + cw * 64);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { qn[2 * s] = ldcg_u32(qp + 8 * s + tq); qn[2 * s + 1] = ldcg_u32(qp + 8 * s + 4 + tq); }
+    };
+    if ((int)blockIdx.x < units) load_header(blockIdx.x);
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        uint32_t qa[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 f = unpack_bf16x2(qn[i]);
+            qa[i] = pack_bf16x2(f.x * SCALE, f.y * SCALE);          // exact: a power of two
+        }
+        uint4 zrow = make_uint4(0u, 0u, 0u, 0u);
+        if (SELF && lane < 8) {      // this step's latent row, columns 64cw + 8*lane .. +7: append to the cache, keep for the last stage
+            zrow = ldcg_u4(a.znew + (size_t)u * a.ldz + cw * 64 + lane * 8);
+            *reinterpret_cast<uint4*>(a.cache + ((size_t)u * a.tcap + t) * 256 + cw * 64 + lane * 8) = zrow;
+            asm volatile("fence.proxy.async.global;" ::: "memory");      // later steps read the row through the async proxy (TMA)
+        }
+        const int un = u + gridDim.x;
+        if (un < units) load_header(un);
+        int nk;
+        if (SELF) nk = t + 1; else nk = ldcg_i32(a.k_off + u + 1) - ldcg_i32(a.k_off + u);
+        const int nchunk = (nk + CH - 1) / CH;
+        float m = -INFINITY, l = 0.f;
+        float o[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+        for (int c = 0; c < nchunk; ++c, ++it) {
+            const int s = it % NS, ph = (it / NS) & 1;
+            mbar_wait(&full[s], ph);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t kt = smem_u32(ring + s * STAGE + cw * HTILE);
+            if (SELF && c == nchunk - 1) {      // key t of the sequence = this step's own row, row t % 16 of the last stage
+                const int r = t & (CH - 1);
+                if (lane < 8) *reinterpret_cast<uint4*>(ring + s * STAGE + cw * HTILE + r * 128 + ((lane ^ (r & 7)) << 4)) = zrow;
+                __syncwarp();
+            }
+            // ---- partial S = Q'[:, block] . Z[:, block]^T : rows = heads, 2 n-tiles of 8 keys, 4 k-steps of 16 columns
+            float sc[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+                const int r = 8 * j + lm_r;
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(kt + r * 128 + (((4 * s2 + lm_m) ^ (r & 7)) << 4), b0, b1, b2, b3);
+                    mma_bf16(sc[j], qa[4 * s2], 0u, qa[4 * s2 + 1], 0u, b0, b1);
+                    mma_bf16(sc[j], qa[4 * s2 + 2], 0u, qa[4 * s2 + 3], 0u, b2, b3);
+                }
+            }
+            // exchange: row g (= head g), lane tq holds keys 8j+2tq, 8j+2tq+1
+            float* xb = xbuf + (c & 1) * (AW * 8 * CH);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                *reinterpret_cast<float2*>(xb + (cw * 8 + g) * CH + 8 * j + 2 * tq) = make_float2(sc[j][0], sc[j][1]);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * AW) : "memory");
+            const int kbase = c * CH + 2 * tq;
+            float p[2][2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float2 acc = *reinterpret_cast<const float2*>(xb + (0 * 8 + g) * CH + 8 * j + 2 * tq);
+#pragma unroll
+                for (int w2 = 1; w2 < AW; ++w2) {
+                    const float2 v = *reinterpret_cast<const float2*>(xb + (w2 * 8 + g) * CH + 8 * j + 2 * tq);
+                    acc.x += v.x; acc.y += v.y;
+                }
+                p[j][0] = (kbase + 8 * j < nk) ? acc.x : -INFINITY;
+                p[j][1] = (kbase + 8 * j + 1 < nk) ? acc.y : -INFINITY;
+            }
+            float cm = fmaxf(fmaxf(p[0][0], p[0][1]), fmaxf(p[1][0], p[1][1]));
+            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+            const float mn = fmaxf(m, cm);                 // finite: every stage holds at least one valid key
+            const float corr = __expf(m - mn);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { p[j][0] = __expf(p[j][0] - mn); p[j][1] = __expf(p[j][1] - mn); }
+            l = l * corr + (p[0][0] + p[0][1]) + (p[1][0] + p[1][1]);
+            m = mn;
+            const uint32_t pa0 = pack_bf16x2(p[0][0], p[0][1]);     // keys 2t, 2t+1
+            const uint32_t pa2 = pack_bf16x2(p[1][0], p[1][1]);     // keys 8+2t, 9+2t
+            // ---- C[:, block] = C*corr + P . Z[:, block] : 8 n-tiles of 8 columns, one k-step of 16 keys
+            const int vr = (lane & 7) + 8 * ((lane >> 3) & 1);
+            uint32_t vm_lo = 0xffffffffu, vm_hi = 0xffffffffu;     // rows past the sequence carry p = 0, but 0 * NaN = NaN
+            if (nk - c * CH < CH) {
+                const int k0 = c * CH + 2 * tq;
+                vm_lo = (k0 < nk ? 0x0000ffffu : 0u) | (k0 + 1 < nk ? 0xffff0000u : 0u);
+                vm_hi = (k0 + 8 < nk ? 0x0000ffffu : 0u) | (k0 + 9 < nk ? 0xffff0000u : 0u);
+            }
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(kt + vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4), b0, b1, b2, b3);
+                b0 &= vm_lo; b2 &= vm_lo; b1 &= vm_hi; b3 &= vm_hi;
+                o[2 * np][0] *= corr; o[2 * np][1] *= corr;
+                o[2 * np + 1][0] *= corr; o[2 * np + 1][1] *= corr;
+                mma_bf16(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
+                mma_bf16(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const float inv = 1.0f / l;
+        uint32_t* op = reinterpret_cast<uint32_t*>(a.o + (size_t)u * a.ldo + g * 256 + cw * 64);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) op[4 * nt + tq] = pack_bf16x2(o[nt][0] * inv, o[nt][1] * inv);
+    }
+    if (tr) atomicMax(tr + 4096, gtime());
+}
+
 int g_smem_set = 0;
 
 }  // namespace
@@ -356,4 +571,29 @@ cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const KvLayout& lay,
     const int grid = units < max_ctas ? units : max_ctas;
     if (a.knew) return launch_pdl(PDL_ATTN_TMA, attn_decode_tma_kernel<true>, dim3(grid), dim3(96), smem, st, tm, tm4, k);
     return launch_pdl(PDL_ATTN_TMA, attn_decode_tma_kernel<false>, dim3(grid), dim3(96), smem, st, tm, tm4, k);
+}
+
+
+cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st) {
+    if (a.batch <= 0) return cudaSuccess;
+    if (a.ldq % 8 != 0 || a.ldo % 8 != 0 || (a.znew && a.ldz % 8 != 0)) return cudaErrorInvalidValue;
+    CUtensorMap tm, tm4;
+    cudaError_t e = tma_map_2d_bf16(a.latent, a.latent_rows, 256, 256, CH, 64, 1, &tm);
+    if (e != cudaSuccess) return e;
+    if ((e = tma_map_2d_bf16(a.latent, a.latent_rows, 256, 256, 4, 64, 1, &tm4)) != cudaSuccess) return e;
+    const size_t smem = (size_t)NS * STAGE + 1024 + 2 * AW * 8 * CH * 4 + 2 * NS * 8 + 64;
+    static int smem_set = 0;
+    if (!smem_set) {
+        if ((e = cudaFuncSetAttribute(attn_abs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_abs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        smem_set = 1;
+    }
+    AbsArgs k{};
+    k.q = (const bf16*)a.q; k.ldq = a.ldq; k.k_off = a.k_off; k.o = (bf16*)a.o; k.ldo = a.ldo; k.batch = a.batch;
+    k.znew = (const bf16*)a.znew; k.ldz = a.ldz; k.cache = (bf16*)const_cast<void*>(a.latent); k.tcap = a.tcap; k.step = a.step;
+    k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k;
+    const int grid = a.batch < max_ctas ? a.batch : max_ctas;
+    const dim3 block(32 * (AW + 1));
+    if (a.znew) return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<true>, dim3(grid), block, smem, st, tm, tm4, k);
+    return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<false>, dim3(grid), block, smem, st, tm, tm4, k);
 }

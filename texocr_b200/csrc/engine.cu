@@ -22,6 +22,8 @@
 #include "decode_mega.h"
 extern int g_tc_split_k;
 extern int g_tc_persistent;
+extern int g_tc_persistent_stages;
+extern int g_tc_min_ctas;
 #include "tc_gemm.h"
 
 static std::string g_create_error;
@@ -205,7 +207,39 @@ static void interleave_rows(const std::vector<float>& w, int rows, int cols, std
     }
 }
 
-static int pack_attn(texocr_handle* h, const std::string& p, bool cross, AttnW& out) {
+// Absorbed K / V projections (attn_abs_kernel), per head h:
+//   Wqk[h*256 + c][i] = sum_d Wk[h*64+d][c] * Wq[h*64+d][i]      Q'_h = xn . Wqk_h^T = (xn Wq_h^T) Wk_h
+//   Wvo[o][h*256 + c] = sum_d Wo[o][h*64+d] * Wv[h*64+d][c]      y = sum_h C_h . Wvo_h^T = sum_h (C_h Wv_h^T) Wo_h^T
+// (fp64 accumulation; Wvo rows interleaved like Wo for the GLU epilogue)
+static void fold_absorbed(const HostTensor& q, const HostTensor& k, const HostTensor& v, const HostTensor& wo, std::vector<float>& wqk,
+                          std::vector<float>& wvoi) {
+    wqk.assign((size_t)2048 * 256, 0.f);
+    std::vector<float> wvo((size_t)512 * 2048);
+    std::vector<double> acc(256);
+    for (int hh = 0; hh < 8; ++hh)
+        for (int cc = 0; cc < 256; ++cc) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            for (int d = 0; d < 64; ++d) {
+                const double kv = k.data[(size_t)(hh * 64 + d) * 256 + cc];
+                const float* qr = &q.data[(size_t)(hh * 64 + d) * 256];
+                for (int i = 0; i < 256; ++i) acc[i] += kv * qr[i];
+            }
+            for (int i = 0; i < 256; ++i) wqk[(size_t)(hh * 256 + cc) * 256 + i] = (float)acc[i];
+        }
+    for (int o2 = 0; o2 < 512; ++o2)
+        for (int hh = 0; hh < 8; ++hh) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            for (int d = 0; d < 64; ++d) {
+                const double ov = wo.data[(size_t)o2 * 512 + hh * 64 + d];
+                const float* vr = &v.data[(size_t)(hh * 64 + d) * 256];
+                for (int cc = 0; cc < 256; ++cc) acc[cc] += ov * vr[cc];
+            }
+            for (int cc = 0; cc < 256; ++cc) wvo[(size_t)o2 * 2048 + hh * 256 + cc] = (float)acc[cc];
+        }
+    interleave_rows(wvo, 512, 2048, wvoi);
+}
+
+static int pack_attn(texocr_handle* h, const std::string& p, bool cross, AttnW& out, bool decoder = false) {
     GETW(q, p + ".q.weight", 512, 256);
     GETW(k, p + ".k.weight", 512, 256);
     GETW(v, p + ".v.weight", 512, 256);
@@ -220,6 +254,12 @@ static int pack_attn(texocr_handle* h, const std::string& p, bool cross, AttnW& 
         if ((r = upload_act(h, qkv, &out.wqkv))) return r;
     } else {
         if ((r = upload_act(h, q->data, &out.wq))) return r;
+    }
+    if (decoder && h->dt != DT_F32) {
+        std::vector<float> wqk, wvoi;
+        fold_absorbed(*q, *k, *v, *wo, wqk, wvoi);
+        if ((r = upload_act(h, wqk, &out.wqk))) return r;
+        if ((r = upload_act(h, wvoi, &out.wvo))) return r;
     }
     std::vector<float> woi, boi;
     interleave_rows(wo->data, 512, 512, woi);
@@ -359,8 +399,8 @@ static int finalize_weights(texocr_handle* h) {
     std::vector<float> ckv;
     for (int l = 0; l < c.dec_layers; ++l) {
         const std::string base = Dn + "attn_layers.layers.";
-        if ((r = pack_attn(h, base + std::to_string(3 * l) + ".1", false, h->dec_self[l]))) return r;
-        if ((r = pack_attn(h, base + std::to_string(3 * l + 1) + ".1", true, h->dec_cross[l]))) return r;
+        if ((r = pack_attn(h, base + std::to_string(3 * l) + ".1", false, h->dec_self[l], true))) return r;
+        if ((r = pack_attn(h, base + std::to_string(3 * l + 1) + ".1", true, h->dec_cross[l], true))) return r;
         if ((r = pack_mlp(h, base + std::to_string(3 * l + 2) + ".1", h->dec_mlp[l]))) return r;
         GETW(k, base + std::to_string(3 * l + 1) + ".1.k.weight", 512, 256);
         GETW(v, base + std::to_string(3 * l + 1) + ".1.v.weight", 512, 256);
@@ -766,8 +806,26 @@ static int run_encoder(texocr_handle* h, const float* d_img, const EncGeom& g, c
 }
 
 // memory (device fp32 or already-typed copy) -> h->crosskv [ntok, L*1024]   (K/V of every cross-attention layer, once)
-static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_typed, int ntok, cudaStream_t st) {
+// generate loop, bf16 tier: absorbed cross-attention (needs the TMA attention path and the per-branch kernel graphs)
+static bool use_absorb(const texocr_handle* h) {
+    return h->dt == DT_BF16 && h->use_tcgen05 && (h->use_tma_attn == 1 || h->use_tma_attn == 3) && !h->decode_mega &&
+           !h->fuse_ln;
+}
+
+static int run_crosskv(texocr_handle* h, const float* enc_f32, const void* enc_typed, int ntok, cudaStream_t st, bool for_generate = false) {
     const int L = h->cfg.dec_layers;
+    h->self_abs_active = for_generate && h->self_absorb && use_absorb(h);
+    if (for_generate && h->cross_absorb && use_absorb(h)) {      // no K/V projection at all: the decode loop streams the bf16 encoder memory itself
+        if (!enc_typed) {
+            ENSURE(h->enc_a, (size_t)ntok * 256 * h->esz);
+            LAUNCH(KC_MISC, 1, (double)ntok * 256 * 6, 0.0, launch_cast_f32_to(enc_f32, h->enc_a.p, (int64_t)ntok * 256, h->dt, st));
+            enc_typed = h->enc_a.p;
+        }
+        h->dec_enc = enc_typed;
+        h->crosskv_rows = ntok;
+        return 0;
+    }
+    h->dec_enc = nullptr;
     ENSURE(h->crosskv, (size_t)ntok * L * 1024 * h->esz);
     h->crosskv_rows = ntok;
     const void* a_ptr = enc_f32;
@@ -847,6 +905,30 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
     const double tkeys = t_host >= 0 ? (double)(t_host + 1) : 0.0;
     char* qb = (char*)rowa(h, h->qkv, rc, 1536);
     for (int l = 0; l < L; ++l) {
+        // ---- causal self-attention, absorbed form: the cache holds this layer's LayerNorm'd inputs (256 per position), Q' = xn . Wqk^T,
+        // C_h = softmax(Q'_h . Z^T / 8) . Z over positions 0..t (t = this step's own row), y = C . Wvo^T + bo -> GLU -> + residual
+        if (h->self_abs_active && !fuse) {
+            void* qa = rowa(h, h->qabs, rc, 2048);
+            void* ca = rowa(h, h->cabs, rc, 2048);
+            GemmArgs gq = mk_gemm(xnbuf, 256, h->dec_self[l].wqk, 256, qa, 2048, rows, 2048, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gq, e), gemm_flops(gq), run_gemm(h, gq, st));
+            AttnAbsArgs ab{};
+            ab.q = qa; ab.ldq = 2048; ab.latent = (char*)h->latcache.p + ((size_t)l * B + row0) * tcap * 256 * e; ab.latent_rows = (long)rows * tcap;
+            ab.znew = xnbuf; ab.ldz = 256; ab.tcap = tcap; ab.step = step; ab.o = ca; ab.ldo = 2048; ab.batch = rows;
+            if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
+                ab.trace = h->attn_trace.as<unsigned long long>() + (size_t)branch * 3 * 2048; ab.trace_step = step; ab.trace_k = 2 * l;
+            }
+            {
+                PdlGuard guard;
+                if ((r = fifo_before(2 * l))) return r;
+                if (!(h->dbg_skip & 1))
+                    LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 256 * e, 4.0 * rows * tkeys * 2048,
+                           launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
+            }
+            if ((r = fifo_after(2 * l))) return r;
+            GemmArgs go = mk_gemm(ca, 2048, h->dec_self[l].wvo, 2048, sbuf, 256, rows, 512, 2048, EPI_GLU_RES, h->dt, DT_F32, h->dec_self[l].bo, xbuf, 256);
+            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(go, e), gemm_flops(go), run_gemm(h, go, st));
+        } else {
         // ---- causal self-attention over the KV cache
         if (fuse) {
             // layer 0: x = embedding (no LayerNorm before the first block input's residual); later layers: x = LN(s)
@@ -877,6 +959,31 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
         }
         if ((r = fifo_after(2 * l))) return r;
         if ((r = sub_attn_out(h, rc, h->dec_self[l], st))) return r;
+        }
+        // ---- cross-attention, absorbed form: Q' = LN.LN(s) . Wqk^T (8 x 256 per row), C_h = softmax(Q'_h . enc^T / 8) . enc over the
+        // bf16 encoder memory itself, y = C . Wvo^T + bo -> GLU -> + residual
+        if (h->dec_enc && !fuse) {
+            if ((r = sub_norm(h, rc, false, nullptr, nullptr, nullptr, nullptr, st))) return r;
+            void* qa = rowa(h, h->qabs, rc, 2048);
+            void* ca = rowa(h, h->cabs, rc, 2048);
+            GemmArgs gc = mk_gemm(xnbuf, 256, h->dec_cross[l].wqk, 256, qa, 2048, rows, 2048, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gc, e), gemm_flops(gc), run_gemm(h, gc, st));
+            AttnAbsArgs ab{};
+            ab.q = qa; ab.ldq = 2048; ab.latent = h->dec_enc; ab.latent_rows = h->crosskv_rows; ab.k_off = d_enc_off + row0; ab.o = ca; ab.ldo = 2048; ab.batch = rows;
+            if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
+                ab.trace = h->attn_trace.as<unsigned long long>() + (size_t)branch * 3 * 2048; ab.trace_step = step; ab.trace_k = 2 * l + 1;
+            }
+            {
+                PdlGuard guard;
+                if ((r = fifo_before(2 * l + 1))) return r;
+                if (!(h->dbg_skip & 2))
+                    LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 256 * e, 4.0 * sum_s * rows / B * 2048,
+                           launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
+            }
+            if ((r = fifo_after(2 * l + 1))) return r;
+            GemmArgs go = mk_gemm(ca, 2048, h->dec_cross[l].wvo, 2048, sbuf, 256, rows, 512, 2048, EPI_GLU_RES, h->dt, DT_F32, h->dec_cross[l].bo, xbuf, 256);
+            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(go, e), gemm_flops(go), run_gemm(h, go, st));
+        } else {
         // ---- cross-attention over the (pre-projected) encoder memory; q goes to the first 512 columns of this branch's qkv rows
         if (fuse) {
             if ((r = gemm_ln(h->dec_cross[l].wq, 512, qb, 512, EPI_STORE, h->dt, nullptr, true, true, nullptr, nullptr))) return r;
@@ -907,6 +1014,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
         }
         if ((r = fifo_after(2 * l + 1))) return r;
         if ((r = sub_attn_out(h, rc, h->dec_cross[l], st))) return r;
+        }
         // ---- GeGLU MLP
         if (fuse) {
             if ((r = gemm_ln(h->dec_mlp[l].w1, 2048, rowa(h, h->hid, rc, 1024), 1024, EPI_GEGLU, h->dt, h->dec_mlp[l].b1, true, true, nullptr, nullptr))) return r;
@@ -1080,14 +1188,21 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     const int tcap = max_len;
     int r;
     if ((r = ensure_rows(h, B))) return r;
-    {   // the decode loop streams the memory K/V per (sequence, head): re-lay the GEMM output head-major, once
+    const bool absorb = h->dec_enc != nullptr;
+    if (absorb || h->self_abs_active) {
+        ENSURE(h->qabs, (size_t)B * 2048 * h->esz);
+        ENSURE(h->cabs, (size_t)B * 2048 * h->esz);
+    }
+    if (!absorb) {   // the decode loop streams the memory K/V per (sequence, head): re-lay the GEMM output head-major, once
         const int ntok = h->crosskv_rows;
         ENSURE(h->crosskv_hm, (size_t)ntok * c.dec_layers * 1024 * h->esz);
         LAUNCH(KC_MISC, 1, (double)ntok * c.dec_layers * 1024 * h->esz * 2, 0.0,
                launch_crosskv_head_major(h->crosskv.p, h->crosskv_hm.p, ntok, c.dec_layers, h->dt, st));
     }
     ENSURE(h->logits, (size_t)B * c.vocab_size * 4);
-    ENSURE(h->kvcache, (size_t)c.dec_layers * B * tcap * 1024 * h->esz);
+    if (h->self_abs_active) ENSURE(h->latcache, (size_t)c.dec_layers * B * tcap * 256 * h->esz);
+    else ENSURE(h->kvcache, (size_t)c.dec_layers * B * tcap * 1024 * h->esz);
+    const void* kv_key = h->self_abs_active ? h->latcache.p : h->kvcache.p;
     ENSURE(h->dec_state, dec_state_bytes(B));
     ENSURE(h->out_ids, (size_t)B * tcap * 8);
     if (h->attn_trace_on) {
@@ -1127,6 +1242,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     // branches run as independent, phase-shifted pipelines that only meet again at the end of the call.
     cudaStream_t bst[MAX_BRANCH];
     for (int i = 0; i < bp.n; ++i) bst[i] = (bp.n == 1 || !graph_ok) ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
+    const void* ckv_key = absorb ? h->dec_enc : h->crosskv_hm.p;
     const int samp_key = h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0;
     // ---- coupled mode: one graph holds all branches of `spg` steps; attention launches are chained across branches (FIFO of
     // depth `fifo`), everything else of a branch only depends on the branch itself
@@ -1135,8 +1251,8 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
         cudaStream_t cs = h->own_stream2;
         const int spg = std::max(1, std::min(h->steps_per_graph, 16));
         const bool hit = h->cgraph_exec[0] && h->cgraph_exec[1] && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos &&
-                         h->gkey.max_s == max_s && h->gkey.samp == samp_key && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p &&
-                         h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n && h->gkey.fifo == fifo && h->gkey.spg == spg;
+                         h->gkey.max_s == max_s && h->gkey.samp == samp_key && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == kv_key &&
+                         h->gkey.ckv == ckv_key && h->gkey.x == h->x.p && h->gkey.nb == bp.n && h->gkey.fifo == fifo && h->gkey.spg == spg;
         if (!hit) {
             std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
             drop_graphs(h);
@@ -1174,7 +1290,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
                 h->launches = before;
             }
             h->gkey.samp = samp_key; h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
-            h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv_hm.p; h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
+            h->gkey.kv = const_cast<void*>(kv_key); h->gkey.ckv = const_cast<void*>(ckv_key); h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
             h->gkey.fifo = fifo; h->gkey.spg = spg;
         }
         CK(cudaEventRecord(h->fork_ev, st));
@@ -1211,7 +1327,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     if (fifo > 0) {
     } else if (graph_ok) {
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
-                         h->gkey.samp == (h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0) && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == h->kvcache.p && h->gkey.ckv == h->crosskv_hm.p && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
+                         h->gkey.samp == (h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0) && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == kv_key && h->gkey.ckv == ckv_key && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
             std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
             drop_graphs(h);
@@ -1229,7 +1345,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
             h->launches = before;        // capture does not execute
             h->gkey.samp = h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0;
             h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
-            h->gkey.kv = h->kvcache.p; h->gkey.ckv = h->crosskv_hm.p; h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
+            h->gkey.kv = const_cast<void*>(kv_key); h->gkey.ckv = const_cast<void*>(ckv_key); h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
         }
         if (bp.n > 1) {      // fork: every branch stream waits for the work already queued on st, then starts with its phase shift
             CK(cudaEventRecord(h->fork_ev, st));
@@ -1339,7 +1455,7 @@ void texocr_destroy(texocr_handle* h) {
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
                       &h->proj_out, &h->patch_cols, &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
                       &h->enc_out, &h->enc_a, &h->crosskv, &h->crosskv_hm, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
-                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg, &h->attn_trace, &h->prep_meta, &h->prep_in, &h->prep_out};
+                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg, &h->attn_trace, &h->qabs, &h->cabs, &h->latcache, &h->prep_meta, &h->prep_in, &h->prep_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);
@@ -1514,7 +1630,7 @@ int texocr_decoder_generate(texocr_handle* h, const int64_t* start_tokens, int32
     const void *d_enc, *d_start;
     if ((r = to_device(h, enc, (size_t)ntok * 256 * 4, h->enc_stage, &d_enc, st))) return r;
     if ((r = to_device(h, start_tokens, (size_t)batch * 8, h->ids_stage, &d_start, st))) return r;
-    if ((r = run_crosskv(h, (const float*)d_enc, nullptr, ntok, st))) return r;
+    if ((r = run_crosskv(h, (const float*)d_enc, nullptr, ntok, st, true))) return r;
     return run_generate(h, (const int64_t*)d_start, eos_tok, h->geom.as<int>(), max_s, (double)ntok, batch, max_len, out_ids, n_steps, st);
 }
 
@@ -1532,7 +1648,7 @@ int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, in
     ENSURE(h->ids_stage, (size_t)batch * 8);
     CK(cudaMemcpy(h->ids_stage.p, start.data(), (size_t)batch * 8, cudaMemcpyHostToDevice));
     if ((r = run_encoder(h, (const float*)d_img, g, st))) return r;
-    if ((r = run_crosskv(h, h->enc_out.as<float>(), h->dt == DT_F32 ? nullptr : h->enc_a.p, g.ntok, st))) return r;
+    if ((r = run_crosskv(h, h->enc_out.as<float>(), h->dt == DT_F32 ? nullptr : h->enc_a.p, g.ntok, st, true))) return r;
     return run_generate(h, h->ids_stage.as<int64_t>(), h->cfg.eos_token, g.d_tok_off, g.max_tok, (double)g.ntok, batch, max_len, out_ids, n_steps, st);
 }
 
@@ -1674,6 +1790,8 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "self_absorb")) { h->self_absorb = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "cross_absorb")) { h->cross_absorb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_trace")) { h->attn_trace_on = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_fifo")) { h->attn_fifo = (int)std::max<int64_t>(0, std::min<int64_t>(MAX_BRANCH, value)); return 0; }
     if (!strcmp(name, "steps_per_graph")) { h->steps_per_graph = (int)std::max<int64_t>(1, std::min<int64_t>(16, value)); return 0; }
@@ -1699,6 +1817,8 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "gemm_persistent")) { g_tc_persistent = (int)value; return 0; }
+    if (!strcmp(name, "gemm_min_ctas")) { g_tc_min_ctas = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "gemm_persistent_stages")) { g_tc_persistent_stages = (int)value; return 0; }
     if (!strcmp(name, "gemm_split_k")) { g_tc_split_k = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "im2col_tma")) { h->use_im2col_tma = value != 0; return 0; }
     if (!strcmp(name, "decode_mega")) { h->decode_mega = (int)value; return 0; }
@@ -1727,7 +1847,7 @@ int64_t texocr_debug_read(texocr_handle* h, const char* name, float* out, int64_
     {   // raw workspace taps (byte-exact copies reinterpreted as float32 words): name -> buffer
         struct { const char* n; DevBuf* b; } taps[] = {{"logits", &h->logits}, {"kvcache", &h->kvcache}, {"x", &h->x}, {"s", &h->s},
                                                        {"xn", &h->xn}, {"qkv", &h->qkv}, {"o", &h->o}, {"hid", &h->hid},
-                                                       {"crosskv_hm", &h->crosskv_hm}, {"enc_out", &h->enc_out}, {"attn_trace", &h->attn_trace}};
+                                                       {"crosskv_hm", &h->crosskv_hm}, {"enc_out", &h->enc_out}, {"attn_trace", &h->attn_trace}, {"latcache", &h->latcache}};
         for (auto& t : taps)
             if (!strcmp(name, t.n)) {
                 if (!t.b->p) return fail(h, TEXOCR_ERR_STATE, "buffer '%s' not allocated", name);
@@ -1786,4 +1906,17 @@ int texocr_debug_attn_decode(texocr_handle* h, int32_t self, const void* q, int3
     return 0;
 }
 
+
+int texocr_debug_attn_abs(texocr_handle* h, const void* q, void* latent, int64_t latent_rows, const int32_t* k_off_dev, const void* znew,
+                          int32_t tcap, const int32_t* step_dev, void* out, int32_t batch, void* stream) {
+    if (!h || !q || !latent || !out || batch <= 0 || latent_rows <= 0 || (!k_off_dev && !znew)) return TEXOCR_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    AttnAbsArgs ab{};
+    ab.q = q; ab.ldq = 2048; ab.latent = latent; ab.latent_rows = (long)latent_rows; ab.k_off = k_off_dev; ab.o = out; ab.ldo = 2048; ab.batch = batch;
+    if (znew) { ab.znew = znew; ab.ldz = 256; ab.tcap = tcap; ab.step = step_dev; }
+    CK(launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
 }  // extern "C"

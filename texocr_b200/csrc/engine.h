@@ -30,7 +30,8 @@ struct ConvW {           // one weight-standardised convolution + its GroupNorm
     float* gamma = nullptr; float* beta = nullptr;
 };
 
-struct AttnW { void* wqkv = nullptr; void* wq = nullptr; void* wo = nullptr; float* bo = nullptr; };
+struct AttnW { void* wqkv = nullptr; void* wq = nullptr; void* wo = nullptr; float* bo = nullptr;
+               void* wqk = nullptr; void* wvo = nullptr; };    // cross, bf16 tier: Wq^T.Wk per head [2048,256] and Wo.Wv per head [512,2048] (absorbed K / V projections)
 struct MlpW { void* w1 = nullptr; float* b1 = nullptr; void* w2 = nullptr; float* b2 = nullptr; };
 
 enum KClass {
@@ -76,6 +77,7 @@ struct texocr_handle {
     DevBuf gn_partial, gn_stats[4];
     DevBuf proj_out, patch_cols, backbone_a, col;
     DevBuf x, s, xn, qkv, o, hid, logits;
+    DevBuf qabs, cabs;                         // absorbed cross-attention: queries / memory averages [rows, 8 x 256]
     DevBuf enc_out, enc_a, crosskv, crosskv_hm, kvcache;      // crosskv: GEMM output [tok][L*1024]; crosskv_hm: head-major copy for decoding
     DevBuf ids_stage, mask_stage, enc_stage, tgt_stage, row_loss, scalars;
     DevBuf dec_state;                          // int64 cur_tok[B] | int32 step, done_step, block_counter, pad | int32 seen[B]
@@ -103,7 +105,7 @@ struct texocr_handle {
     cudaGraph_t cgraph[2] = {nullptr, nullptr}; cudaGraphExec_t cgraph_exec[2] = {nullptr, nullptr}; int cgraph_kernels[2] = {0, 0};
     std::vector<cudaEvent_t> fifo_ev;           // [step in graph][branch][8 attention launches]
     cudaEvent_t* fifo_wait = nullptr; cudaEvent_t* fifo_rec = nullptr;     // set around enqueue_decode_step while capturing
-    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; int fifo = 0; int spg = 0; } gkey;
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; int fifo = 0; int spg = 0; int absorb = 0; } gkey;
 
     // ---- instrumentation
     int64_t launches = 0;
@@ -117,6 +119,13 @@ struct texocr_handle {
     int decode_mega = 0;      // bf16 tier: 1 = experimental cluster-persistent decode kernel (decode_mega.cu), 0 = per-branch kernel graphs.
                               // Token-identical to the branch path but ~1.8x slower at B = 512 (issue-bound at 8 warps per SM)
     int mega_steps = 16;      // decode steps per launch of that kernel (also the early-exit polling interval)
+    // bf16 tier generate loop: cross-attention streams the [S,256] encoder memory once for all heads instead of per-head K/V
+    // (K / V projections folded into the query / output projections).  0 = projected K/V cache.
+    int cross_absorb = 1;
+    int self_absorb = 1;                       // same for the self-attention: the cache holds the layer's 256-wide LayerNorm'd inputs
+    bool self_abs_active = false;              // decided per generate call (run_crosskv)
+    DevBuf latcache;                           // [layer][sequence][position][256] bf16 latent cache of the absorbed self-attention
+    const void* dec_enc = nullptr;             // bf16 encoder memory of the current generate call [crosskv_rows, 256]
     int use_tma_attn = 1;     // 0 = simple kernel, 1 = TMA kernel for self + cross, 2 = self only, 3 = cross only
     bool fuse_ln = false;    // decode step: LayerNorms computed inside the consuming tcgen05 GEMM (bf16 tier)
     bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate

@@ -174,6 +174,22 @@ struct KvLayout {
     int col0, col_h, v_col, row_h, row_b;
 };
 bool attn_decode_tma_supported(const AttnDecodeArgs& a);
+// bf16 tier: decode attention with the K / V projections absorbed into the query / output projections (attn_decode_tma.cu).
+// q [batch, ldq] holds 8 absorbed queries of 256 per row; `latent` is the bf16 matrix [latent_rows, 256] the keys live in:
+//   cross (znew == null): the encoder memory, k_off[batch + 1] = token range of every sequence;
+//   self  (znew != null): the layer's latent cache [batch][tcap][256] (*step rows valid per sequence); znew [batch, ldz] is this
+//   step's own latent row, which the kernel uses as key *step and appends to the cache.
+// o [batch, ldo] receives 8 x 256 softmax-weighted latent averages per row.
+struct AttnAbsArgs {
+    const void* q; int ldq;
+    const void* latent; long latent_rows;
+    const int* k_off;
+    const void* znew; int ldz; int tcap; const int* step;
+    void* o; int ldo;
+    int batch;
+    unsigned long long* trace; const int* trace_step; int trace_k;
+};
+cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st);
 cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const KvLayout& lay, int max_ctas, cudaStream_t st);
 // [tok][L*1024] (per layer: K 512 | V 512, heads side by side; the cross-K/V GEMM output) -> [L][8][tok][K 64 | V 64]
 cudaError_t launch_crosskv_head_major(const void* in, void* out, int ntok, int layers, int dt, cudaStream_t st);

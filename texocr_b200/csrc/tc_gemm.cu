@@ -25,7 +25,9 @@
 // slower in the decode loop (104.5 vs 95.2 ms per generate at B = 512): cluster launch + DSMEM hand-off cost more than the two
 // or three TMA ring rounds they save.  Off by default.
 int g_tc_split_k = 0;
-int g_tc_persistent = 1;     // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
+int g_tc_persistent = 1;
+int g_tc_min_ctas = 120;          // tile width rule: narrow the N tile (128 -> 64 -> 32) while the grid would have fewer CTAs than this
+int g_tc_persistent_stages = 0;   // 0 = as many ring stages as fit in 200 KB; n > 0 caps them (leaves shared memory to co-resident kernels)     // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
 
 namespace {
 
@@ -37,6 +39,7 @@ struct TcParams {
     int late_trigger;
     // implicit-GEMM convolution (TMA im2col loads of A): cpk = 64-channel chunks per filter tap (0 = plain GEMM)
     int cv_cpk, cv_ksz, cv_stride, cv_lower, cv_Wo, cv_Ho;
+    int stages;       // persistent kernel: ring stages actually used (<= SmemP::STAGES)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -443,7 +446,8 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     using S = SmemP<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* stg = smem + S::STAGES * S::STAGE;
+    const int nst = p.stages;
+    uint8_t* stg = smem + nst * S::STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(stg + S::STG);
     uint64_t* empty = full + S::STAGES;
     uint64_t* tmem_full = empty + S::STAGES;       // [2]
@@ -459,7 +463,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-        for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -487,7 +491,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                     cv_w = (rem - oh * p.cv_Wo) * p.cv_stride + p.cv_lower;
                 }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % S::STAGES, ph = (it / S::STAGES) & 1;
+                    const int s = it % nst, ph = (it / nst) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * S::STAGE;
                     mbar_expect_tx(&full[s], S::STAGE);
@@ -515,7 +519,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                 tcgen05_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % S::STAGES, ph = (it / S::STAGES) & 1;
+                    const int s = it % nst, ph = (it / nst) & 1;
                     mbar_wait(&full[s], ph);
                     tcgen05_fence_after();
                     const uint32_t a_hi = smem_u32(smem + s * S::STAGE);
@@ -885,7 +889,10 @@ cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const 
         attr_set = true;
     }
     const unsigned grid = (unsigned)std::min<long>(tiles, sms);
-    return launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
+    TcParams pp = p;
+    pp.stages = g_tc_persistent_stages > 0 ? std::max(2, std::min(g_tc_persistent_stages, S::STAGES)) : S::STAGES;
+    const size_t smem = (size_t)S::TOTAL - (size_t)(S::STAGES - pp.stages) * S::STAGE;
+    return launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(192), smem, st, a, w, a2, w2, pp);
 }
 
 template <int BN, int EPI, typename TC, int SPLIT>
@@ -956,8 +963,8 @@ cudaError_t launch_gemm_tc_ln(const GemmArgs& g, const float* s_in, const float*
     if (g.K != 256 || g.N % 8 != 0 || g.ldw % 8 != 0 || (g.epi != EPI_STORE && g.epi != EPI_GEGLU)) return cudaErrorInvalidValue;
     const long mt = (g.M + BM - 1) / BM;
     int bn = 128;
-    if (mt * ((g.N + 127) / 128) < 120) bn = 64;
-    if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
+    if (mt * ((g.N + 127) / 128) < g_tc_min_ctas) bn = 64;
+    if (mt * ((g.N + 63) / 64) < g_tc_min_ctas && g.N >= 64) bn = 32;
     TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1};
     LnParams ln{s_in, g1, b1, g2, b2, x_out};
     CUtensorMap w;

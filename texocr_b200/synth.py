@@ -94,6 +94,8 @@ def encoder_flops(height: int, width: int, kind: str = "hybrid") -> float:
     return first + 11534336.0 * n + 8192.0 * n * n
 
 
-def decode_step_bytes(batch: int, t: int, s: int, w_step: int = 15222736, kv_row: int = 8192) -> float:
-    """Algorithmic bytes of decode step t (1-based) with a bf16 KV cache."""
-    return float(w_step + batch * (kv_row * t + kv_row * s + kv_row))
+def decode_step_bytes(batch: int, t: int, s: int, w_step: int = 15222736, kv_row: int = 8192, mem_row: int = 8192) -> float:
+    """Algorithmic bytes of decode step t (1-based) with a bf16 KV cache.  kv_row = self-attention bytes
+    per cached key (4 layers x K,V x 512 x bf16); mem_row = cross-attention bytes per memory token: 8192 with projected K/V,
+    2048 when the K / V projections are absorbed and the [S, 256] bf16 memory itself is streamed (4 layers x 256 x bf16)."""
+    return float(w_step + batch * (kv_row * t + mem_row * s + kv_row))
