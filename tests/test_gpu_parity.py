@@ -300,15 +300,16 @@ def test_absorbed_attention_matches_projected_kv(m16, m32):
     finally:
         _absorb(eng, 1)
     assert not torch.equal(lg[(0, 0)], lg[(1, 1)])                               # the formulations really differ in rounding
+    enc = m16.encoder(src)                                  # ragged: list of (N_i, 256)
+    bos = torch.full((B, 1), m16.dims.bos, device="cuda")
     for mode in modes:
         assert rel_max(lg[mode].numpy(), ref32.numpy()) < BF16_TOL, mode
-        assert (toks[mode] == toks[(0, 0)]).float().mean().item() > 0.9, mode
-    img = synth.synth_images(32, 64, 384, seed=41).cuda()
-    out = m16.generate(img, 40)
-    enc = m16.encoder(img)
-    ids = torch.cat((torch.full((32, 1), m16.dims.bos, device="cuda"), out[:, :-1]), 1)
-    agree = (m16.decoder.net(ids, enc=enc).argmax(-1) == out).float().mean().item()
-    assert agree > 0.97, agree
+        # greedy decoding of random-init weights is chaotic (one flipped near-tie changes the rest of the row), so the formulations
+        # are compared through the teacher-forced decoder on each one's own prefix, and only loosely token by token
+        ids = torch.cat((bos, toks[mode][:, :-1]), 1)
+        agree = (m16.decoder.net(ids, enc=enc).argmax(-1) == toks[mode]).float().mean().item()
+        assert agree > 0.97, (mode, agree)
+        assert (toks[mode][:, :8] == toks[(0, 0)][:, :8]).float().mean().item() > 0.9, mode
 
 
 def test_cluster_persistent_decode_kernel_matches_branch_path(m16):

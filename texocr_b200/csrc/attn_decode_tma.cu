@@ -16,6 +16,7 @@
 #include "tc_gemm.h"
 
 int g_attn_full_tail = 0;
+int g_attn_abs_minb = 4;     // attn_abs_kernel: 4 = 96 registers (small spills), 4 CTAs per SM; 3 = 128 registers, no spills
 
 namespace {
 
@@ -86,6 +87,22 @@ TX_DEVINL void ldsm_x4_t(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2
 TX_DEVINL void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// m16n8k16 with only rows 0..7 of A in use (a1 = a3 = 0): rows 8..15 of the accumulator stay zero, so they are fed as constants
+// and their results land in two scratch registers instead of occupying two live registers per n-tile
+TX_DEVINL void mma_bf16_top(float& c0, float& c1, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    float j0, j1;
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %5}, {%7, %8}, {%0, %1, %9, %9};"
+                 : "+f"(c0), "+f"(c1), "=f"(j0), "=f"(j1) : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1), "f"(0.f));
+}
+TX_DEVINL void sts_f2(uint32_t addr, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory"); }
+TX_DEVINL float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+TX_DEVINL void sts_u4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 TX_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -358,8 +375,8 @@ struct AbsArgs {
     unsigned long long* trace; const int* trace_step; int trace_k;
 };
 
-template <bool SELF>
-__global__ void __launch_bounds__(32 * (AW + 1), 4) attn_abs_kernel(const __grid_constant__ CUtensorMap tm,
+template <bool SELF, int MINB>
+__global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __grid_constant__ CUtensorMap tm,
                                                                  const __grid_constant__ CUtensorMap tm4, const AbsArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -423,6 +440,14 @@ __global__ void __launch_bounds__(32 * (AW + 1), 4) attn_abs_kernel(const __grid
     const int cw = warp - 1;
     const int g = lane >> 2, tq = lane & 3;               // fragment row (= head) / thread-in-group
     const int lm_r = lane & 7, lm_m = lane >> 3;
+    const uint32_t ring_u32 = smem_u32(ring), xbuf_u32 = smem_u32(xbuf);
+    uint32_t off_qk[2][2], off_pv[4];         // swizzled ldmatrix offsets inside a 16 x 64 tile: the same for every stage
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) { const int r = 8 * j + lm_r; off_qk[j][s2] = r * 128 + (((4 * s2 + lm_m) ^ (r & 7)) << 4); }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) { const int vr = (lane & 7) + 8 * ((lane >> 3) & 1); off_pv[np] = vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4); }
     int it = 0;
     uint32_t qn[8];
     auto load_header = [&](int u) {       // words of row g, columns 64cw..: k-step s holds dims 16s+2t,+1 and 16s+8+2t,+1
@@ -450,51 +475,58 @@ __global__ void __launch_bounds__(32 * (AW + 1), 4) attn_abs_kernel(const __grid
         if (SELF) nk = t + 1; else nk = ldcg_i32(a.k_off + u + 1) - ldcg_i32(a.k_off + u);
         const int nchunk = (nk + CH - 1) / CH;
         float m = -INFINITY, l = 0.f;
-        float o[8][4];
+        float o[8][2];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = 0.f; }
         for (int c = 0; c < nchunk; ++c, ++it) {
             const int s = it % NS, ph = (it / NS) & 1;
             mbar_wait(&full[s], ph);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t kt = smem_u32(ring + s * STAGE + cw * HTILE);
-            if (SELF && c == nchunk - 1) {      // key t of the sequence = this step's own row, row t % 16 of the last stage
+            const uint32_t kt = ring_u32 + s * STAGE + cw * HTILE;
+            const bool last = c == nchunk - 1;
+            if (SELF && last) {      // key t of the sequence = this step's own row, row t % 16 of the last stage
                 const int r = t & (CH - 1);
-                if (lane < 8) *reinterpret_cast<uint4*>(ring + s * STAGE + cw * HTILE + r * 128 + ((lane ^ (r & 7)) << 4)) = zrow;
+                if (lane < 8) sts_u4(kt + r * 128 + ((lane ^ (r & 7)) << 4), zrow);
                 __syncwarp();
             }
             // ---- partial S = Q'[:, block] . Z[:, block]^T : rows = heads, 2 n-tiles of 8 keys, 4 k-steps of 16 columns
-            float sc[2][4];
+            float sc[2][2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-                const int r = 8 * j + lm_r;
+                sc[j][0] = sc[j][1] = 0.f;
 #pragma unroll
                 for (int s2 = 0; s2 < 2; ++s2) {
                     uint32_t b0, b1, b2, b3;
-                    ldsm_x4(kt + r * 128 + (((4 * s2 + lm_m) ^ (r & 7)) << 4), b0, b1, b2, b3);
-                    mma_bf16(sc[j], qa[4 * s2], 0u, qa[4 * s2 + 1], 0u, b0, b1);
-                    mma_bf16(sc[j], qa[4 * s2 + 2], 0u, qa[4 * s2 + 3], 0u, b2, b3);
+                    ldsm_x4(kt + off_qk[j][s2], b0, b1, b2, b3);
+                    mma_bf16_top(sc[j][0], sc[j][1], qa[4 * s2], qa[4 * s2 + 1], b0, b1);
+                    mma_bf16_top(sc[j][0], sc[j][1], qa[4 * s2 + 2], qa[4 * s2 + 3], b2, b3);
                 }
             }
             // exchange: row g (= head g), lane tq holds keys 8j+2tq, 8j+2tq+1
-            float* xb = xbuf + (c & 1) * (AW * 8 * CH);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-                *reinterpret_cast<float2*>(xb + (cw * 8 + g) * CH + 8 * j + 2 * tq) = make_float2(sc[j][0], sc[j][1]);
+            const uint32_t xb = xbuf_u32 + (c & 1) * (AW * 8 * CH * 4) + (g * CH + 2 * tq) * 4;
+            sts_f2(xb + cw * (8 * CH * 4), sc[0][0], sc[0][1]);
+            sts_f2(xb + cw * (8 * CH * 4) + 32, sc[1][0], sc[1][1]);
             asm volatile("bar.sync 1, %0;" ::"n"(32 * AW) : "memory");
-            const int kbase = c * CH + 2 * tq;
             float p[2][2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                float2 acc = *reinterpret_cast<const float2*>(xb + (0 * 8 + g) * CH + 8 * j + 2 * tq);
+                float2 acc = lds_f2(xb + 32 * j);
 #pragma unroll
                 for (int w2 = 1; w2 < AW; ++w2) {
-                    const float2 v = *reinterpret_cast<const float2*>(xb + (w2 * 8 + g) * CH + 8 * j + 2 * tq);
+                    const float2 v = lds_f2(xb + w2 * (8 * CH * 4) + 32 * j);
                     acc.x += v.x; acc.y += v.y;
                 }
-                p[j][0] = (kbase + 8 * j < nk) ? acc.x : -INFINITY;
-                p[j][1] = (kbase + 8 * j + 1 < nk) ? acc.y : -INFINITY;
+                p[j][0] = acc.x; p[j][1] = acc.y;
+            }
+            uint32_t vm_lo = 0xffffffffu, vm_hi = 0xffffffffu;
+            if (last) {      // keys past the end of the sequence: score -> -inf; their Z rows carry p = 0, but 0 * NaN = NaN -> cleared below
+                const int k0 = c * CH + 2 * tq;
+                if (k0 >= nk) p[0][0] = -INFINITY;
+                if (k0 + 1 >= nk) p[0][1] = -INFINITY;
+                if (k0 + 8 >= nk) p[1][0] = -INFINITY;
+                if (k0 + 9 >= nk) p[1][1] = -INFINITY;
+                vm_lo = (k0 < nk ? 0x0000ffffu : 0u) | (k0 + 1 < nk ? 0xffff0000u : 0u);
+                vm_hi = (k0 + 8 < nk ? 0x0000ffffu : 0u) | (k0 + 9 < nk ? 0xffff0000u : 0u);
             }
             float cm = fmaxf(fmaxf(p[0][0], p[0][1]), fmaxf(p[1][0], p[1][1]));
             cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
@@ -508,22 +540,15 @@ __global__ void __launch_bounds__(32 * (AW + 1), 4) attn_abs_kernel(const __grid
             const uint32_t pa0 = pack_bf16x2(p[0][0], p[0][1]);     // keys 2t, 2t+1
             const uint32_t pa2 = pack_bf16x2(p[1][0], p[1][1]);     // keys 8+2t, 9+2t
             // ---- C[:, block] = C*corr + P . Z[:, block] : 8 n-tiles of 8 columns, one k-step of 16 keys
-            const int vr = (lane & 7) + 8 * ((lane >> 3) & 1);
-            uint32_t vm_lo = 0xffffffffu, vm_hi = 0xffffffffu;     // rows past the sequence carry p = 0, but 0 * NaN = NaN
-            if (nk - c * CH < CH) {
-                const int k0 = c * CH + 2 * tq;
-                vm_lo = (k0 < nk ? 0x0000ffffu : 0u) | (k0 + 1 < nk ? 0xffff0000u : 0u);
-                vm_hi = (k0 + 8 < nk ? 0x0000ffffu : 0u) | (k0 + 9 < nk ? 0xffff0000u : 0u);
-            }
 #pragma unroll
             for (int np = 0; np < 4; ++np) {
                 uint32_t b0, b1, b2, b3;
-                ldsm_x4_t(kt + vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4), b0, b1, b2, b3);
-                b0 &= vm_lo; b2 &= vm_lo; b1 &= vm_hi; b3 &= vm_hi;
+                ldsm_x4_t(kt + off_pv[np], b0, b1, b2, b3);
+                if (last) { b0 &= vm_lo; b2 &= vm_lo; b1 &= vm_hi; b3 &= vm_hi; }
                 o[2 * np][0] *= corr; o[2 * np][1] *= corr;
                 o[2 * np + 1][0] *= corr; o[2 * np + 1][1] *= corr;
-                mma_bf16(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
-                mma_bf16(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
+                mma_bf16_top(o[2 * np][0], o[2 * np][1], pa0, pa2, b0, b1);
+                mma_bf16_top(o[2 * np + 1][0], o[2 * np + 1][1], pa0, pa2, b2, b3);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -584,8 +609,10 @@ cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     const size_t smem = (size_t)NS * STAGE + 1024 + 2 * AW * 8 * CH * 4 + 2 * NS * 8 + 64;
     static int smem_set = 0;
     if (!smem_set) {
-        if ((e = cudaFuncSetAttribute(attn_abs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(attn_abs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_abs_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_abs_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_abs_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(attn_abs_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         smem_set = 1;
     }
     AbsArgs k{};
@@ -594,6 +621,10 @@ cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k;
     const int grid = a.batch < max_ctas ? a.batch : max_ctas;
     const dim3 block(32 * (AW + 1));
-    if (a.znew) return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<true>, dim3(grid), block, smem, st, tm, tm4, k);
-    return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<false>, dim3(grid), block, smem, st, tm, tm4, k);
+    if (g_attn_abs_minb == 3) {
+        if (a.znew) return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<true, 3>, dim3(grid), block, smem, st, tm, tm4, k);
+        return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<false, 3>, dim3(grid), block, smem, st, tm, tm4, k);
+    }
+    if (a.znew) return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<true, 4>, dim3(grid), block, smem, st, tm, tm4, k);
+    return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<false, 4>, dim3(grid), block, smem, st, tm, tm4, k);
 }

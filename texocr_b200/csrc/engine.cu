@@ -35,6 +35,7 @@ static std::recursive_mutex g_dev_mu;
 // dependents only after their stores (experiment switches; the default is an early trigger everywhere).
 int g_texocr_pdl = 0x3f;
 extern int g_attn_full_tail;
+extern int g_attn_abs_minb;
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -236,8 +237,13 @@ static void fold_absorbed(const HostTensor& q, const HostTensor& k, const HostTe
     if (g_fold_cache.size() >= 64) g_fold_cache.clear();
     g_fold_cache[key] = std::make_pair(wqk, wvoi);
 }
-static void fold_absorbed_compute(const HostTensor& q, const HostTensor& k, const HostTensor& v, const HostTensor& wo, std::vector<float>& wqk,
+static void fold_absorbed_compute(const HostTensor& q0, const HostTensor& k0, const HostTensor& v0, const HostTensor& wo0, std::vector<float>& wqk,
                                   std::vector<float>& wvoi) {
+    // The bf16 tier's weights ARE their bf16 roundings (what the projected path multiplies with, and what a 'mixed' weight blob
+    // stores): fold those, so that a model built from fp32 weights and one built from the blob stay bit-identical.
+    HostTensor q = q0, k = k0, v = v0, wo = wo0;
+    for (HostTensor* t : {&q, &k, &v, &wo})
+        for (float& x : t->data) x = bf2f(f2bf(x));
     wqk.assign((size_t)2048 * 256, 0.f);
     std::vector<float> wvo((size_t)512 * 2048);
     std::vector<double> acc(256);
@@ -1815,6 +1821,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "attn_abs_minb")) { g_attn_abs_minb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "self_absorb")) { h->self_absorb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "cross_absorb")) { h->cross_absorb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_trace")) { h->attn_trace_on = value != 0; drop_graphs(h); return 0; }

@@ -906,10 +906,13 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     if (SPLIT == 1 && BN >= 64 && tiles >= 592) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
     if constexpr (SPLIT == 1 && BN == 32 && (EPI == EPI_GLU_RES || EPI == EPI_BIAS_RES)) {
         // latency-bound decode GEMMs with a long K loop: split K over a 2- / 4-CTA cluster (4 k-blocks per CTA = one ring round)
-        if (g_tc_split_k && tiles < 120) {
+        // g_tc_split_k bit 0: K = 512 / 1024 (measured slower than the plain kernel); bit 1: K = 2048 (the folded out-projection of the
+        // absorbed attention: 32 k-blocks in one CTA are 14 us, 4 x 8 k-blocks over a cluster with a DSMEM reduction are shorter)
+        if ((g_tc_split_k & 1) && tiles < 120) {
             if (p.K == 1024) return launch_cfg_ks<EPI, TC, 4>(a, w, a2, w2, p, st);
             if (p.K == 512) return launch_cfg_ks<EPI, TC, 2>(a, w, a2, w2, p, st);
         }
+        if ((g_tc_split_k & 2) && tiles < 120 && p.K == 2048) return launch_cfg_ks<EPI, TC, 4>(a, w, a2, w2, p, st);
     }
     return launch_cfg2<BN, EPI, TC, SPLIT, 0>(a, w, a2, w2, p, st);
 }
