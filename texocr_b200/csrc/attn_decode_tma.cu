@@ -16,7 +16,7 @@
 #include "tc_gemm.h"
 
 int g_attn_full_tail = 0;
-int g_attn_abs_minb = 4;     // attn_abs_kernel: 4 = 96 registers (small spills), 4 CTAs per SM; 3 = 128 registers, no spills
+int g_attn_abs_minb = 3;     // attn_abs_kernel: 3 = 128 registers, no spills (default: 1-3 % better with batches in flight); 4 = 96 registers (small spills), 4 CTAs per SM
 
 namespace {
 
@@ -364,6 +364,8 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
 // Self-attention: this step's own latent row (position t) is written into the last stage by the consumers (it is key t of
 // that stage) and appended to the cache for the following steps.
 constexpr int AW = 4;                       // consumer warps = 64-column blocks of a latent row
+constexpr int ANS = 5;                      // ring stages of the absorbed kernel (40 KB)
+constexpr int XROW = 40;                    // floats per (warp, head) row of the score exchange: 32 keys, padded so that a half-warp's float2 accesses hit 32 distinct banks
 struct AbsArgs {
     const bf16* q; int ldq;            // [batch, ldq]: head h at h*256 (absorbed query, unscaled)
     const int* k_off;                  // cross: token offsets [batch + 1] into the latent matrix the tensor maps cover
@@ -373,6 +375,7 @@ struct AbsArgs {
     bf16* o; int ldo;                  // [batch, ldo]: head h at h*256
     int batch;
     unsigned long long* trace; const int* trace_step; int trace_k;
+    unsigned long long* dbg;           // debug: sums over CTAs of [wait for predecessor, first data, stage loop, epilogue] ns + count
 };
 
 template <bool SELF, int MINB>
@@ -380,17 +383,18 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
                                                                  const __grid_constant__ CUtensorMap tm4, const AbsArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float* xbuf = reinterpret_cast<float*>(ring + NS * STAGE);            // [2][AW][8 heads][16 keys] partial scores
-    uint64_t* full = reinterpret_cast<uint64_t*>(xbuf + 2 * AW * 8 * CH);
-    uint64_t* empty = full + NS;
+    float* xbuf = reinterpret_cast<float*>(ring + ANS * STAGE);           // [2][AW][8 heads][XROW] partial scores of two stages (32 keys)
+    uint64_t* full = reinterpret_cast<uint64_t*>(xbuf + 2 * AW * 8 * XROW);
+    uint64_t* empty = full + ANS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     pdl_launch_dependents();
     const unsigned long long t_entry = a.trace ? gtime() : 0ull;
+    const unsigned long long t_entry0 = a.dbg ? gtime() : 0ull;
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm4) : "memory");
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AW); }
+        for (int s = 0; s < ANS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
                 else { row0 = ldcg_i32(a.k_off + u); nc = ldcg_i32(a.k_off + u + 1) - row0; }
                 const int nchunk = ((SELF ? nc + 1 : nc) + CH - 1) / CH;
                 for (int c = 0; c < nchunk; ++c, ++it) {
-                    const int s = it % NS, ph = (it / NS) & 1;
+                    const int s = it % ANS, ph = (it / ANS) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = ring + s * STAGE;
                     const int left = nc - c * CH, r = row0 + c * CH;
@@ -456,6 +460,8 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         for (int s = 0; s < 4; ++s) { qn[2 * s] = ldcg_u32(qp + 8 * s + tq); qn[2 * s + 1] = ldcg_u32(qp + 8 * s + 4 + tq); }
     };
     if ((int)blockIdx.x < units) load_header(blockIdx.x);
+    const unsigned long long t_ready = a.dbg ? gtime() : 0ull;
+    unsigned long long t_first = 0ull;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
         uint32_t qa[8];
 #pragma unroll
@@ -478,88 +484,128 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         float o[8][2];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = 0.f; }
-        for (int c = 0; c < nchunk; ++c, ++it) {
-            const int s = it % NS, ph = (it / NS) & 1;
-            mbar_wait(&full[s], ph);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t kt = ring_u32 + s * STAGE + cw * HTILE;
-            const bool last = c == nchunk - 1;
+        // Two stages (32 keys) per iteration: one score exchange / barrier / softmax update for both, two independent MMA chains.
+        for (int c = 0; c < nchunk; c += 2) {
+            const bool two = c + 1 < nchunk;
+            const bool last = c + 2 >= nchunk;
+            uint32_t kts[2];
+            int sidx[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q == 0 || two) {
+                    const int iq = it + q;
+                    sidx[q] = iq % ANS;
+                    mbar_wait(&full[sidx[q]], (iq / ANS) & 1);
+                    kts[q] = ring_u32 + sidx[q] * STAGE + cw * HTILE;
+                } else { sidx[q] = 0; kts[q] = 0; }
+            }
+            // (no proxy fence here: observing the mbarrier phase makes the TMA writes of the stage visible to this thread's ldmatrix)
+            if (a.dbg && t_first == 0ull) t_first = gtime();
             if (SELF && last) {      // key t of the sequence = this step's own row, row t % 16 of the last stage
                 const int r = t & (CH - 1);
-                if (lane < 8) sts_u4(kt + r * 128 + ((lane ^ (r & 7)) << 4), zrow);
+                if (lane < 8) sts_u4(kts[two ? 1 : 0] + r * 128 + ((lane ^ (r & 7)) << 4), zrow);
                 __syncwarp();
             }
-            // ---- partial S = Q'[:, block] . Z[:, block]^T : rows = heads, 2 n-tiles of 8 keys, 4 k-steps of 16 columns
-            float sc[2][2];
+            // ---- partial S = Q'[:, block] . Z[:, block]^T : rows = heads; per stage 2 n-tiles of 8 keys, 4 k-steps of 16 columns
+            float sc[2][2][2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                sc[j][0] = sc[j][1] = 0.f;
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    uint32_t b0, b1, b2, b3;
-                    ldsm_x4(kt + off_qk[j][s2], b0, b1, b2, b3);
-                    mma_bf16_top(sc[j][0], sc[j][1], qa[4 * s2], qa[4 * s2 + 1], b0, b1);
-                    mma_bf16_top(sc[j][0], sc[j][1], qa[4 * s2 + 2], qa[4 * s2 + 3], b2, b3);
+                for (int j = 0; j < 2; ++j) {
+                    sc[q][j][0] = sc[q][j][1] = 0.f;
+                    if (q == 0 || two) {
+#pragma unroll
+                        for (int s2 = 0; s2 < 2; ++s2) {
+                            uint32_t b0, b1, b2, b3;
+                            ldsm_x4(kts[q] + off_qk[j][s2], b0, b1, b2, b3);
+                            mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2], qa[4 * s2 + 1], b0, b1);
+                            mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2 + 2], qa[4 * s2 + 3], b2, b3);
+                        }
+                    }
                 }
-            }
-            // exchange: row g (= head g), lane tq holds keys 8j+2tq, 8j+2tq+1
-            const uint32_t xb = xbuf_u32 + (c & 1) * (AW * 8 * CH * 4) + (g * CH + 2 * tq) * 4;
-            sts_f2(xb + cw * (8 * CH * 4), sc[0][0], sc[0][1]);
-            sts_f2(xb + cw * (8 * CH * 4) + 32, sc[1][0], sc[1][1]);
+            // exchange: row g (= head g), lane tq holds keys 16q+8j+2tq, +1
+            const uint32_t xb = xbuf_u32 + ((c >> 1) & 1) * (AW * 8 * XROW * 4) + (g * XROW + 2 * tq) * 4;
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) sts_f2(xb + cw * (8 * XROW * 4) + (16 * q + 8 * j) * 4, sc[q][j][0], sc[q][j][1]);
             asm volatile("bar.sync 1, %0;" ::"n"(32 * AW) : "memory");
-            float p[2][2];
+            float p[2][2][2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                float2 acc = lds_f2(xb + 32 * j);
+            for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int w2 = 1; w2 < AW; ++w2) {
-                    const float2 v = lds_f2(xb + w2 * (8 * CH * 4) + 32 * j);
-                    acc.x += v.x; acc.y += v.y;
+                for (int j = 0; j < 2; ++j) {
+                    float2 acc = lds_f2(xb + (16 * q + 8 * j) * 4);
+#pragma unroll
+                    for (int w2 = 1; w2 < AW; ++w2) {
+                        const float2 v = lds_f2(xb + w2 * (8 * XROW * 4) + (16 * q + 8 * j) * 4);
+                        acc.x += v.x; acc.y += v.y;
+                    }
+                    p[q][j][0] = acc.x; p[q][j][1] = acc.y;
                 }
-                p[j][0] = acc.x; p[j][1] = acc.y;
-            }
-            uint32_t vm_lo = 0xffffffffu, vm_hi = 0xffffffffu;
+            uint32_t vm_lo[2] = {0xffffffffu, 0xffffffffu}, vm_hi[2] = {0xffffffffu, 0xffffffffu};
             if (last) {      // keys past the end of the sequence: score -> -inf; their Z rows carry p = 0, but 0 * NaN = NaN -> cleared below
-                const int k0 = c * CH + 2 * tq;
-                if (k0 >= nk) p[0][0] = -INFINITY;
-                if (k0 + 1 >= nk) p[0][1] = -INFINITY;
-                if (k0 + 8 >= nk) p[1][0] = -INFINITY;
-                if (k0 + 9 >= nk) p[1][1] = -INFINITY;
-                vm_lo = (k0 < nk ? 0x0000ffffu : 0u) | (k0 + 1 < nk ? 0xffff0000u : 0u);
-                vm_hi = (k0 + 8 < nk ? 0x0000ffffu : 0u) | (k0 + 9 < nk ? 0xffff0000u : 0u);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int k0 = (c + q) * CH + 2 * tq;
+                    if (k0 >= nk) p[q][0][0] = -INFINITY;
+                    if (k0 + 1 >= nk) p[q][0][1] = -INFINITY;
+                    if (k0 + 8 >= nk) p[q][1][0] = -INFINITY;
+                    if (k0 + 9 >= nk) p[q][1][1] = -INFINITY;
+                    vm_lo[q] = (k0 < nk ? 0x0000ffffu : 0u) | (k0 + 1 < nk ? 0xffff0000u : 0u);
+                    vm_hi[q] = (k0 + 8 < nk ? 0x0000ffffu : 0u) | (k0 + 9 < nk ? 0xffff0000u : 0u);
+                }
             }
-            float cm = fmaxf(fmaxf(p[0][0], p[0][1]), fmaxf(p[1][0], p[1][1]));
+            float cm = fmaxf(fmaxf(fmaxf(p[0][0][0], p[0][0][1]), fmaxf(p[0][1][0], p[0][1][1])),
+                             fmaxf(fmaxf(p[1][0][0], p[1][0][1]), fmaxf(p[1][1][0], p[1][1][1])));
             cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
             cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-            const float mn = fmaxf(m, cm);                 // finite: every stage holds at least one valid key
+            const float mn = fmaxf(m, cm);                 // finite: the first stage of an iteration holds at least one valid key
             const float corr = __expf(m - mn);
+            float ps = 0.f;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { p[j][0] = __expf(p[j][0] - mn); p[j][1] = __expf(p[j][1] - mn); }
-            l = l * corr + (p[0][0] + p[0][1]) + (p[1][0] + p[1][1]);
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    p[q][j][0] = __expf(p[q][j][0] - mn); p[q][j][1] = __expf(p[q][j][1] - mn);
+                    ps += p[q][j][0] + p[q][j][1];
+                }
+            l = l * corr + ps;
             m = mn;
-            const uint32_t pa0 = pack_bf16x2(p[0][0], p[0][1]);     // keys 2t, 2t+1
-            const uint32_t pa2 = pack_bf16x2(p[1][0], p[1][1]);     // keys 8+2t, 9+2t
-            // ---- C[:, block] = C*corr + P . Z[:, block] : 8 n-tiles of 8 columns, one k-step of 16 keys
 #pragma unroll
-            for (int np = 0; np < 4; ++np) {
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4_t(kt + off_pv[np], b0, b1, b2, b3);
-                if (last) { b0 &= vm_lo; b2 &= vm_lo; b1 &= vm_hi; b3 &= vm_hi; }
-                o[2 * np][0] *= corr; o[2 * np][1] *= corr;
-                o[2 * np + 1][0] *= corr; o[2 * np + 1][1] *= corr;
-                mma_bf16_top(o[2 * np][0], o[2 * np][1], pa0, pa2, b0, b1);
-                mma_bf16_top(o[2 * np + 1][0], o[2 * np + 1][1], pa0, pa2, b2, b3);
+            for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= corr; o[nt][1] *= corr; }
+            // ---- C[:, block] += P . Z[:, block] : per stage 8 n-tiles of 8 columns, one k-step of 16 keys
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (q == 0 || two) {
+                    const uint32_t pa0 = pack_bf16x2(p[q][0][0], p[q][0][1]);     // keys 2t, 2t+1 of the stage
+                    const uint32_t pa2 = pack_bf16x2(p[q][1][0], p[q][1][1]);     // keys 8+2t, 9+2t
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_t(kts[q] + off_pv[np], b0, b1, b2, b3);
+                        if (last) { b0 &= vm_lo[q]; b2 &= vm_lo[q]; b1 &= vm_hi[q]; b3 &= vm_hi[q]; }
+                        mma_bf16_top(o[2 * np][0], o[2 * np][1], pa0, pa2, b0, b1);
+                        mma_bf16_top(o[2 * np + 1][0], o[2 * np + 1][1], pa0, pa2, b2, b3);
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) { mbar_arrive(&empty[sidx[0]]); if (two) mbar_arrive(&empty[sidx[1]]); }
+            it += two ? 2 : 1;
         }
+        const unsigned long long t_loop = a.dbg ? gtime() : 0ull;
         l += __shfl_xor_sync(0xffffffffu, l, 1);
         l += __shfl_xor_sync(0xffffffffu, l, 2);
         const float inv = 1.0f / l;
         uint32_t* op = reinterpret_cast<uint32_t*>(a.o + (size_t)u * a.ldo + g * 256 + cw * 64);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) op[4 * nt + tq] = pack_bf16x2(o[nt][0] * inv, o[nt][1] * inv);
+        if (a.dbg && threadIdx.x == 32 && u == (int)blockIdx.x) {
+            atomicAdd(a.dbg + 0, t_ready - t_entry0); atomicAdd(a.dbg + 1, t_first - t_ready); atomicAdd(a.dbg + 2, t_loop - t_first);
+            atomicAdd(a.dbg + 3, gtime() - t_loop); atomicAdd(a.dbg + 4, 1ull);
+        }
     }
     if (tr) atomicMax(tr + 4096, gtime());
 }
@@ -606,7 +652,7 @@ cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     cudaError_t e = tma_map_2d_bf16(a.latent, a.latent_rows, 256, 256, CH, 64, 1, &tm);
     if (e != cudaSuccess) return e;
     if ((e = tma_map_2d_bf16(a.latent, a.latent_rows, 256, 256, 4, 64, 1, &tm4)) != cudaSuccess) return e;
-    const size_t smem = (size_t)NS * STAGE + 1024 + 2 * AW * 8 * CH * 4 + 2 * NS * 8 + 64;
+    const size_t smem = (size_t)ANS * STAGE + 1024 + 2 * AW * 8 * XROW * 4 + 2 * ANS * 8 + 64;
     static int smem_set = 0;
     if (!smem_set) {
         if ((e = cudaFuncSetAttribute(attn_abs_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
@@ -618,7 +664,7 @@ cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     AbsArgs k{};
     k.q = (const bf16*)a.q; k.ldq = a.ldq; k.k_off = a.k_off; k.o = (bf16*)a.o; k.ldo = a.ldo; k.batch = a.batch;
     k.znew = (const bf16*)a.znew; k.ldz = a.ldz; k.cache = (bf16*)const_cast<void*>(a.latent); k.tcap = a.tcap; k.step = a.step;
-    k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k;
+    k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k; k.dbg = a.dbg;
     const int grid = a.batch < max_ctas ? a.batch : max_ctas;
     const dim3 block(32 * (AW + 1));
     if (g_attn_abs_minb == 3) {

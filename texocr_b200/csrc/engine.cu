@@ -24,6 +24,8 @@ extern int g_tc_split_k;
 extern int g_tc_persistent;
 extern int g_tc_persistent_stages;
 extern int g_tc_min_ctas;
+extern int g_tc_deep_ring;
+extern int g_tc_shallow_ring;
 #include "tc_gemm.h"
 
 static std::string g_create_error;
@@ -948,6 +950,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
             ab.znew = xnbuf; ab.ldz = 256; ab.tcap = tcap; ab.step = step; ab.o = ca; ab.ldo = 2048; ab.batch = rows;
             if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
                 ab.trace = h->attn_trace.as<unsigned long long>() + (size_t)branch * 3 * 2048; ab.trace_step = step; ab.trace_k = 2 * l;
+                ab.dbg = h->attn_trace.as<unsigned long long>() + (size_t)MAX_BRANCH * 3 * 2048;
             }
             {
                 PdlGuard guard;
@@ -1003,6 +1006,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
             ab.q = qa; ab.ldq = 2048; ab.latent = h->dec_enc; ab.latent_rows = h->crosskv_rows; ab.k_off = d_enc_off + row0; ab.o = ca; ab.ldo = 2048; ab.batch = rows;
             if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
                 ab.trace = h->attn_trace.as<unsigned long long>() + (size_t)branch * 3 * 2048; ab.trace_step = step; ab.trace_k = 2 * l + 1;
+                ab.dbg = h->attn_trace.as<unsigned long long>() + (size_t)MAX_BRANCH * 3 * 2048 + 8;
             }
             {
                 PdlGuard guard;
@@ -1237,7 +1241,8 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     ENSURE(h->dec_state, dec_state_bytes(B));
     ENSURE(h->out_ids, (size_t)B * tcap * 8);
     if (h->attn_trace_on) {
-        ENSURE(h->attn_trace, (size_t)MAX_BRANCH * 3 * 2048 * 8);
+        ENSURE(h->attn_trace, (size_t)MAX_BRANCH * 3 * 2048 * 8 + 128);
+        CK(cudaMemsetAsync((char*)h->attn_trace.p + (size_t)MAX_BRANCH * 3 * 2048 * 8, 0, 128, st));
         for (int i = 0; i < MAX_BRANCH; ++i) {
             char* base = (char*)h->attn_trace.p + (size_t)i * 3 * 2048 * 8;
             CK(cudaMemsetAsync(base, 0xff, 2 * 2048 * 8, st));
@@ -1849,6 +1854,8 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "gemm_persistent")) { g_tc_persistent = (int)value; return 0; }
+    if (!strcmp(name, "gemm_shallow_ring")) { g_tc_shallow_ring = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "gemm_deep_ring")) { g_tc_deep_ring = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "gemm_min_ctas")) { g_tc_min_ctas = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "gemm_persistent_stages")) { g_tc_persistent_stages = (int)value; return 0; }
     if (!strcmp(name, "gemm_split_k")) { g_tc_split_k = (int)value; drop_graphs(h); return 0; }

@@ -188,6 +188,7 @@ struct AttnAbsArgs {
     void* o; int ldo;
     int batch;
     unsigned long long* trace; const int* trace_step; int trace_k;
+    unsigned long long* dbg;      // debug phase timers (5 words), null = off
 };
 cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st);
 cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const KvLayout& lay, int max_ctas, cudaStream_t st);

@@ -26,6 +26,8 @@
 // or three TMA ring rounds they save.  Off by default.
 int g_tc_split_k = 0;
 int g_tc_persistent = 1;
+int g_tc_deep_ring = 0;          // 8-stage TMA ring for the K >= 2048 decode GEMMs (single batch: -2.5 %; six batches in flight: +7 %, the 160 KB CTAs crowd the SMs)
+int g_tc_shallow_ring = 0;       // 2-stage ring (40 KB at BN = 32) for every one-tile-per-CTA GEMM: smaller shared-memory footprint next to the attention CTAs
 int g_tc_min_ctas = 120;          // tile width rule: narrow the N tile (128 -> 64 -> 32) while the grid would have fewer CTAs than this
 int g_tc_persistent_stages = 0;   // 0 = as many ring stages as fit in 200 KB; n > 0 caps them (leaves shared memory to co-resident kernels)     // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
 
@@ -913,6 +915,12 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
             if (p.K == 512) return launch_cfg_ks<EPI, TC, 2>(a, w, a2, w2, p, st);
         }
         if ((g_tc_split_k & 2) && tiles < 120 && p.K == 2048) return launch_cfg_ks<EPI, TC, 4>(a, w, a2, w2, p, st);
+    }
+    if (SPLIT == 1 && g_tc_shallow_ring) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
+    if constexpr (SPLIT == 1 && BN == 32 && EPI == EPI_GLU_RES) {
+        // K = 2048 (folded out-projection of the absorbed attention): 32 k-blocks per CTA; an 8-stage ring (160 KB) keeps twice the
+        // bytes in flight per CTA (the grid is 64 CTAs, one per SM anyway)
+        if (g_tc_deep_ring && p.K >= 2048) return launch_cfg2<BN, EPI, TC, SPLIT, 8>(a, w, a2, w2, p, st);
     }
     return launch_cfg2<BN, EPI, TC, SPLIT, 0>(a, w, a2, w2, p, st);
 }
