@@ -350,10 +350,24 @@ def main():
     roofline, shares = None, None
     if rank == 0:
         eng.set_option("decode_branches", 1)
+        eng.set_option("attn_trace", 1)            # in-kernel %globaltimer phase sums of the attention kernel (see below)
         eng.profile_enable(True)
         model.generate(img_dev, max_len=MAX_LEN)
         rows = eng.profile_read()
         eng.profile_enable(False)
+        phases, window_s = None, None
+        try:
+            allraw = eng.debug_read("attn_trace", 16 * 3 * 2048 * 2 + 32).view(torch.int64).cpu()
+            tr = allraw[:3 * 2048].reshape(3, 256, 8).double()          # branch 0: entry (min over CTAs), ready (min), end (max)
+            ok = tr[2] > 0
+            window_s = float(((tr[2] - tr[1]) * ok).sum()) * 1e-9         # launch-wide: first CTA past its dependency -> last CTA done
+            raw = allraw[16 * 3 * 2048:].double()
+            phases = {k: {"first_stage_us": float(raw[o + 1] / max(1.0, float(raw[o + 4])) / 1e3),
+                          "stage_loop_us": float(raw[o + 2] / max(1.0, float(raw[o + 4])) / 1e3),
+                          "epilogue_us": float(raw[o + 3] / max(1.0, float(raw[o + 4])) / 1e3)} for k, o in (("self", 0), ("cross", 8))}
+        except Exception:
+            phases = None
+        eng.set_option("attn_trace", 0)
         eng.set_option("decode_branches", 0)
         tot = sum(r["ms"] for r in rows) or 1.0
         shares = {r["name"]: round(r["ms"] / tot, 4) for r in sorted(rows, key=lambda r: -r["ms"])}
@@ -379,6 +393,18 @@ def main():
         # the same launches on SURVEY section 8d's per-key figure (projected K/V, 2,048 B per key and layer): the absorbed kernel
         # moves a quarter of those bytes, so this "effective" rate may exceed the HBM peak
         roofline["achieved_on_survey_bytes"] = ach * (4.0 if args.precision == "bf16" else 1.0)
+        if phases and args.precision == "bf16":
+            # what the kernel does while it streams: mean time a CTA spends in its stage loop (all CTAs of a launch run side by
+            # side, one sequence each), against the same algorithmic bytes -- the launch-level figure above adds launch,
+            # first-stage latency, epilogue and tail of a ~9 us CTA lifetime
+            by = {r["name"]: r for r in attn}
+            loop_s = sum(by[n]["launches"] * phases[k]["stage_loop_us"] * 1e-6 for n, k in (("dec_attn_self", "self"), ("dec_attn_cross", "cross")) if n in by)
+            if loop_s > 0 and window_s:
+                roofline["in_kernel"] = {"achieved": a_bytes / window_s / 1e9, "unit": "GB/s", "frac": a_bytes / window_s / 1e9 / peaks["hbm_gbs"],
+                                         "method": "%globaltimer, per launch: first CTA released by its dependency -> last CTA finished (engine option "
+                                                   "attn_trace); excludes launch latency and the CUDA-event overhead of the figure above",
+                                         "mean_cta_phases_us": phases,
+                                         "mean_cta_stage_loop_gbs": a_bytes / loop_s / 1e9}
         # whole-step view against the HBM roofline of SURVEY.md section 8d (bf16 KV cache bytes + per-step weights)
         s_tok = synth.encoder_tokens(H, W)
         esz = 2 if args.precision == "bf16" else 4
@@ -433,7 +459,7 @@ def main():
                    "batch_per_gpu": B, "max_len": MAX_LEN, "image": [H, W], "precision": args.precision,
                    "parallelism": f"dp{world} (independent shards, token-id all_gather)",
                    "batches_in_flight": n_fly, "decode_branches_per_batch": args.branches if n_fly > 1 else 6,
-                   "l2_policy": "working set (KV cache >= 1 GB, activations >= 3 GB per step) exceeds the 126 MB L2; no explicit flush"},
+                   "l2_policy": "working set per batch in flight (0.25 GB latent attention cache + 0.2 GB encoder memory / decode buffers + >= 3 GB encoder activations) exceeds the 126 MB L2 many times over; no explicit flush"},
         "e2e": e2e, "one_batch_at_a_time": serial, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernel_time_shares": shares,
         "cpu_baseline": cpu_baseline, "encoder": encoder, "next_rows": next_rows,
     }
