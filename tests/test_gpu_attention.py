@@ -115,3 +115,34 @@ def test_self_attention_absorbed(eng, t, B):
     assert torch.isfinite(out.float()).all() and float(err.max()) < 2e-2, float(err.max())
     cache.view(B, tcap, 256)[:, t] = float("nan")
     assert torch.equal(out, eng.debug_attn_abs(q, cache, znew=znew, tcap=tcap, step=step))      # run-to-run reproducible
+
+
+def test_absorbed_attention_several_units_per_cta(eng):
+    """More sequences than resident CTAs: a CTA walks several units (ring and score-exchange buffers carry over between them)."""
+    lens = [17, 97, 33, 16, 1, 40, 97] * 260                     # 1820 sequences
+    B = len(lens)
+    off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(19)
+    enc = torch.randn(int(off[-1]), 256, device="cuda", generator=g).to(torch.bfloat16)
+    q = (torch.randn(B, 2048, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    out = eng.debug_attn_abs(q, enc, k_off=off)
+    for _ in range(3):
+        assert torch.equal(out, eng.debug_attn_abs(q, enc, k_off=off))
+    for b in list(range(0, B, 37)) + [B - 1]:
+        mem = enc[int(off[b]):int(off[b + 1])].float()
+        ref = (torch.softmax((q[b].float().reshape(8, 256) @ mem.T) * 0.125, dim=-1) @ mem).reshape(-1)
+        assert (out[b].float() - ref).abs().max() / ref.abs().max() < 2e-2, b
+    # self-attention, 1500 sequences, odd stage counts
+    tcap, Bs = 64, 1500
+    for t in (5, 37, 48):
+        cache = torch.randn(Bs * tcap, 256, device="cuda", generator=g).to(torch.bfloat16)
+        znew = torch.randn(Bs, 256, device="cuda", generator=g).to(torch.bfloat16)
+        qs = (torch.randn(Bs, 2048, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+        step = torch.tensor([t], dtype=torch.int32, device="cuda")
+        o1 = eng.debug_attn_abs(qs, cache, znew=znew, tcap=tcap, step=step)
+        z = cache.view(Bs, tcap, 256)[:, : t + 1].float()
+        sc = torch.einsum("bhc,bjc->bhj", qs.float().view(Bs, 8, 256), z) * 0.125
+        ref = torch.einsum("bhj,bjc->bhc", torch.softmax(sc, dim=-1), z).reshape(Bs, 2048)
+        err = (o1.float() - ref).abs().amax(1) / ref.abs().amax(1)
+        assert float(err.max()) < 2e-2, (t, float(err.max()))
+        assert torch.equal(o1, eng.debug_attn_abs(qs, cache, znew=znew, tcap=tcap, step=step))

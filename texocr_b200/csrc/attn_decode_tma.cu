@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         for (int s = 0; s < 4; ++s) { qn[2 * s] = ldcg_u32(qp + 8 * s + tq); qn[2 * s + 1] = ldcg_u32(qp + 8 * s + 4 + tq); }
     };
     if ((int)blockIdx.x < units) load_header(blockIdx.x);
+    int xiter = 0;          // score-exchange buffer parity: runs across units (a CTA may own several), never reset
     const unsigned long long t_ready = a.dbg ? gtime() : 0ull;
     unsigned long long t_first = 0ull;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -524,7 +525,8 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
                     }
                 }
             // exchange: row g (= head g), lane tq holds keys 16q+8j+2tq, +1
-            const uint32_t xb = xbuf_u32 + ((c >> 1) & 1) * (AW * 8 * XROW * 4) + (g * XROW + 2 * tq) * 4;
+            const uint32_t xb = xbuf_u32 + (xiter & 1) * (AW * 8 * XROW * 4) + (g * XROW + 2 * tq) * 4;
+            ++xiter;
 #pragma unroll
             for (int q = 0; q < 2; ++q)
 #pragma unroll
