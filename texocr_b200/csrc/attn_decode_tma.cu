@@ -12,6 +12,8 @@
 //
 // Reference semantics: model/attention.py:148-173 with q length 1 (energy * 0.125, softmax, . v); no masks are active in
 // generate (model/decoder.py:95: mask all True; causal over a prefix == attend to everything cached).
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc_gemm.h"
 
@@ -667,7 +669,21 @@ cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     k.q = (const bf16*)a.q; k.ldq = a.ldq; k.k_off = a.k_off; k.o = (bf16*)a.o; k.ldo = a.ldo; k.batch = a.batch;
     k.znew = (const bf16*)a.znew; k.ldz = a.ldz; k.cache = (bf16*)const_cast<void*>(a.latent); k.tcap = a.tcap; k.step = a.step;
     k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k; k.dbg = a.dbg;
-    const int grid = a.batch < max_ctas ? a.batch : max_ctas;
+    // persistent grid: never more CTAs than can be resident (the rest would only queue behind them without the cross-unit prefetch)
+    static int occ[2][2] = {{0, 0}, {0, 0}};
+    static int sms = 0;
+    const int vi = g_attn_abs_minb == 3 ? 0 : 1, si = a.znew ? 1 : 0;
+    if (!occ[vi][si]) {
+        int n = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const void* fn = vi == 0 ? (si ? (const void*)attn_abs_kernel<true, 3> : (const void*)attn_abs_kernel<false, 3>)
+                                 : (si ? (const void*)attn_abs_kernel<true, 4> : (const void*)attn_abs_kernel<false, 4>);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 32 * (AW + 1), smem) != cudaSuccess || n < 1) n = 1;
+        occ[vi][si] = n;
+    }
+    const int cap = std::min(max_ctas, occ[vi][si] * (sms > 0 ? sms : 148));
+    const int grid = a.batch < cap ? a.batch : cap;
     const dim3 block(32 * (AW + 1));
     if (g_attn_abs_minb == 3) {
         if (a.znew) return launch_pdl(PDL_ATTN_TMA, attn_abs_kernel<true, 3>, dim3(grid), block, smem, st, tm, tm4, k);
