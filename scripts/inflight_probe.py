@@ -31,7 +31,7 @@ for n in ns:
     bar = threading.Barrier(n + 1)
 
     def work(i):
-        st = torch.cuda.Stream()
+        st = torch.cuda.Stream(priority=int(os.environ.get('WORKER_PRIO', '0')))
         with torch.cuda.stream(st):
             for _ in range(2):
                 models[i].generate(img, T)

@@ -1266,7 +1266,11 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     const BranchPlan bp = plan_branches(h, B);
     for (int i = 0; i < bp.n; ++i) {
         if (!h->branch_stream[i]) {
-            CK(cudaStreamCreateWithFlags(&h->branch_stream[i], cudaStreamNonBlocking));
+            // decode streams get the highest priority: their kernels are small and latency-bound, so with several batches in flight they
+            // should be placed ahead of the wide encoder kernels of other handles, which then fill the gaps
+            int pr_lo = 0, pr_hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+            CK(cudaStreamCreateWithPriority(&h->branch_stream[i], cudaStreamNonBlocking, h->decode_priority == 1 ? pr_hi : pr_lo));
             CK(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
         }
     }
@@ -1277,7 +1281,10 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     // Stream of branch i: its own non-blocking stream (branch 0 included when there are several branches), so the
     // branches run as independent, phase-shifted pipelines that only meet again at the end of the call.
     cudaStream_t bst[MAX_BRANCH];
-    for (int i = 0; i < bp.n; ++i) bst[i] = (bp.n == 1 || !graph_ok) ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
+    // a single branch also moves to the engine's own (high-priority) decode stream, so that with several handles at work the small
+    // decode kernels are placed ahead of other handles' wide encoder kernels
+    const bool own = graph_ok && (bp.n > 1 || h->decode_priority);
+    for (int i = 0; i < bp.n; ++i) bst[i] = !own ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
     const void* ckv_key = absorb ? h->dec_enc : h->crosskv_hm.p;
     const int samp_key = h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0;
     // ---- coupled mode: one graph holds all branches of `spg` steps; attention launches are chained across branches (FIFO of
@@ -1383,7 +1390,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
             h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
             h->gkey.kv = const_cast<void*>(kv_key); h->gkey.ckv = const_cast<void*>(ckv_key); h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
         }
-        if (bp.n > 1) {      // fork: every branch stream waits for the work already queued on st, then starts with its phase shift
+        if (own) {      // fork: every branch stream waits for the work already queued on st, then starts with its phase shift
             CK(cudaEventRecord(h->fork_ev, st));
             for (int i = 0; i < bp.n; ++i) {
                 CK(cudaStreamWaitEvent(bst[i], h->fork_ev, 0));
@@ -1422,7 +1429,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
             ++polls;
         }
     }
-    if (graph_ok && bp.n > 1 && fifo == 0) {      // join
+    if (own && fifo == 0) {      // join
         for (int i = 0; i < bp.n; ++i) {
             CK(cudaEventRecord(h->join_ev[i], bst[i]));
             CK(cudaStreamWaitEvent(st, h->join_ev[i], 0));
@@ -1827,6 +1834,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
     if (!strcmp(name, "attn_abs_minb")) { g_attn_abs_minb = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "decode_priority")) { h->decode_priority = (int)value; return 0; }      // before the first generate call
     if (!strcmp(name, "self_absorb")) { h->self_absorb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "cross_absorb")) { h->cross_absorb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_trace")) { h->attn_trace_on = value != 0; drop_graphs(h); return 0; }
