@@ -392,7 +392,11 @@ def main():
                     "share_of_step_kernel_time": round(a_ms / tot, 4)}
         # the same launches on SURVEY section 8d's per-key figure (projected K/V, 2,048 B per key and layer): the absorbed kernel
         # moves a quarter of those bytes, so this "effective" rate may exceed the HBM peak
-        roofline["achieved_on_survey_bytes"] = ach * (4.0 if args.precision == "bf16" else 1.0)
+        surv = ach * (4.0 if args.precision == "bf16" else 1.0)
+        roofline["achieved_on_survey_bytes"] = surv
+        roofline["on_survey_bytes"] = {"achieved": surv, "unit": "GB/s", "frac": surv / peaks["hbm_gbs"],
+                                       "note": "SURVEY.md 8d counts 2,048 B per key and layer (projected K/V); achieved / frac above use the 512 B "
+                                               "this formulation actually has to move (conservative); `traffic` is measured DRAM bytes per launch"}
         if phases and args.precision == "bf16":
             # what the kernel does while it streams: mean time a CTA spends in its stage loop (all CTAs of a launch run side by
             # side, one sequence each), against the same algorithmic bytes -- the launch-level figure above adds launch,
