@@ -293,6 +293,7 @@ static int pack_attn(texocr_handle* h, const std::string& p, bool cross, AttnW& 
         fold_absorbed(*q, *k, *v, *wo, wqk, wvoi);
         if ((r = upload_act(h, wqk, &out.wqk))) return r;
         if ((r = upload_act(h, wvoi, &out.wvo))) return r;
+        if ((r = upload_act(h, v->data, &out.wv))) return r;      // [512 = head*64 + d, 256]: block-diagonal value projection of C
     }
     std::vector<float> woi, boi;
     interleave_rows(wo->data, 512, 512, woi);
@@ -455,6 +456,7 @@ static int finalize_weights(texocr_handle* h) {
 static cudaError_t run_gemm(texocr_handle* h, const GemmArgs& g, cudaStream_t st) {
     if ((h->dbg_skip & 8) && g.M <= 512) return cudaSuccess;
     if (h->use_tcgen05 && g.dt_a == DT_BF16 && !g.conv && tc_gemm_supported(g)) return launch_gemm_tc(g, st);
+    if (g.a_block_k) return cudaErrorInvalidValue;      // block-diagonal mode exists in the tcgen05 kernel only
     return launch_gemm_simt(g, st);
 }
 static GemmArgs mk_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K, int epi,
@@ -839,6 +841,21 @@ static int run_encoder(texocr_handle* h, const float* d_img, const EncGeom& g, c
 }
 
 // memory (device fp32 or already-typed copy) -> h->crosskv [ntok, L*1024]   (K/V of every cross-attention layer, once)
+// y = out-projection(C) + bo -> GLU -> + residual for the absorbed attention, C = [rows, 8 x 256] softmax-weighted latent averages:
+// either one folded GEMM (K = 2048), or the per-head value projection (block-diagonal, K = 256) into `o` followed by the ordinary
+// Wo GEMM -- 4x fewer FLOPs / weight bytes and a shorter dependent chain (12 instead of 32 k-blocks)
+static int sub_abs_out(texocr_handle* h, const RowCtx& rc, const AttnW& w, const void* ca, cudaStream_t st) {
+    if (!h->absorb_two_stage) {
+        GemmArgs go = mk_gemm(ca, 2048, w.wvo, 2048, rowf(h->s, rc, 256), 256, rc.rows, 512, 2048, EPI_GLU_RES, h->dt, DT_F32, w.bo, rowf(h->x, rc, 256), 256);
+        LAUNCH(rc.kc_gemm, 1, gemm_bytes(go, h->esz), gemm_flops(go), run_gemm(h, go, st));
+        return 0;
+    }
+    GemmArgs gv = mk_gemm(ca, 2048, w.wv, 256, rowa(h, h->o, rc, 512), 512, rc.rows, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
+    gv.a_block_k = 256;
+    LAUNCH(rc.kc_gemm, 1, gemm_bytes(gv, h->esz), gemm_flops(gv), run_gemm(h, gv, st));
+    return sub_attn_out(h, rc, w, st);
+}
+
 // generate loop, bf16 tier: absorbed cross-attention (needs the TMA attention path and the per-branch kernel graphs)
 static bool use_absorb(const texocr_handle* h) {
     return h->dt == DT_BF16 && h->use_tcgen05 && (h->use_tma_attn == 1 || h->use_tma_attn == 3) && !h->decode_mega &&
@@ -960,8 +977,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
                            launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
             }
             if ((r = fifo_after(2 * l))) return r;
-            GemmArgs go = mk_gemm(ca, 2048, h->dec_self[l].wvo, 2048, sbuf, 256, rows, 512, 2048, EPI_GLU_RES, h->dt, DT_F32, h->dec_self[l].bo, xbuf, 256);
-            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(go, e), gemm_flops(go), run_gemm(h, go, st));
+            if ((r = sub_abs_out(h, rc, h->dec_self[l], ca, st))) return r;
         } else {
         // ---- causal self-attention over the KV cache
         if (fuse) {
@@ -1016,8 +1032,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
                            launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
             }
             if ((r = fifo_after(2 * l + 1))) return r;
-            GemmArgs go = mk_gemm(ca, 2048, h->dec_cross[l].wvo, 2048, sbuf, 256, rows, 512, 2048, EPI_GLU_RES, h->dt, DT_F32, h->dec_cross[l].bo, xbuf, 256);
-            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(go, e), gemm_flops(go), run_gemm(h, go, st));
+            if ((r = sub_abs_out(h, rc, h->dec_cross[l], ca, st))) return r;
         } else {
         // ---- cross-attention over the (pre-projected) encoder memory; q goes to the first 512 columns of this branch's qkv rows
         if (fuse) {
@@ -1835,6 +1850,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
     if (!strcmp(name, "attn_abs_minb")) { g_attn_abs_minb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "decode_priority")) { h->decode_priority = (int)value; return 0; }      // before the first generate call
+    if (!strcmp(name, "absorb_two_stage")) { h->absorb_two_stage = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "self_absorb")) { h->self_absorb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "cross_absorb")) { h->cross_absorb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_trace")) { h->attn_trace_on = value != 0; drop_graphs(h); return 0; }

@@ -31,7 +31,7 @@ struct ConvW {           // one weight-standardised convolution + its GroupNorm
 };
 
 struct AttnW { void* wqkv = nullptr; void* wq = nullptr; void* wo = nullptr; float* bo = nullptr;
-               void* wqk = nullptr; void* wvo = nullptr; };    // cross, bf16 tier: Wq^T.Wk per head [2048,256] and Wo.Wv per head [512,2048] (absorbed K / V projections)
+               void* wqk = nullptr; void* wvo = nullptr; void* wv = nullptr; };    // cross, bf16 tier: Wq^T.Wk per head [2048,256] and Wo.Wv per head [512,2048] (absorbed K / V projections)
 struct MlpW { void* w1 = nullptr; float* b1 = nullptr; void* w2 = nullptr; float* b2 = nullptr; };
 
 enum KClass {
@@ -124,6 +124,8 @@ struct texocr_handle {
     // bf16 tier generate loop: cross-attention streams the [S,256] encoder memory once for all heads instead of per-head K/V
     // (K / V projections folded into the query / output projections).  0 = projected K/V cache.
     int cross_absorb = 1;
+    int absorb_two_stage = 1;                  // out-projection of the absorbed attention as per-head value projection (block-diagonal GEMM, K = 256)
+                                               // + the ordinary Wo GEMM (K = 512) instead of one folded K = 2048 GEMM
     int self_absorb = 1;                       // same for the self-attention: the cache holds the layer's 256-wide LayerNorm'd inputs
     bool self_abs_active = false;              // decided per generate call (run_crosskv)
     DevBuf latcache;                           // [layer][sequence][position][256] bf16 latent cache of the absorbed self-attention

@@ -42,6 +42,7 @@ struct TcParams {
     // implicit-GEMM convolution (TMA im2col loads of A): cpk = 64-channel chunks per filter tap (0 = plain GEMM)
     int cv_cpk, cv_ksz, cv_stride, cv_lower, cv_Wo, cv_Ho;
     int stages;       // persistent kernel: ring stages actually used (<= SmemP::STAGES)
+    int a_block_k;    // block-diagonal GEMM (one-tile-per-CTA kernel, BN = 64): n-tile j reads A columns from j * a_block_k
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -369,8 +370,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_im2col(&tmA, &full[s], st, cc, cv_w, cv_h, cv_n, kx, ky);
                     if (SPLIT == 3) tma_load_im2col(&tmA2, &full[s], st + S::A_BYTES, cc, cv_w, cv_h, cv_n, kx, ky);
                 } else {
-                    tma_load_2d(&tmA, &full[s], st, (kb0 + kb) * BK, m0);
-                    if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, (kb0 + kb) * BK, m0);
+                    const int ak = (kb0 + kb) * BK + (int)blockIdx.x * p.a_block_k;
+                    tma_load_2d(&tmA, &full[s], st, ak, m0);
+                    if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, ak, m0);
                 }
             }
         }
@@ -903,7 +905,7 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     // many tiles (encoder / teacher-forced sizes): shallow pipeline, several CTAs per SM; few tiles: deep pipeline
     const long tiles = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
     if constexpr (BN >= 64) {
-        if (g_tc_persistent && tiles >= 296) return launch_persistent<BN, EPI, TC, SPLIT>(a, w, a2, w2, p, tiles, st);
+        if (g_tc_persistent && tiles >= 296 && !p.a_block_k) return launch_persistent<BN, EPI, TC, SPLIT>(a, w, a2, w2, p, tiles, st);
     }
     if (SPLIT == 1 && BN >= 64 && tiles >= 592) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
     if constexpr (SPLIT == 1 && BN == 32 && (EPI == EPI_GLU_RES || EPI == EPI_BIAS_RES)) {
@@ -1006,7 +1008,12 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
     const bool split = g.A2 != nullptr;
     if (split) bn = g.N <= 64 ? 64 : 128;
+    if (g.a_block_k) {
+        if (split || g.im2col.ksz > 0 || g.N % 64 != 0) return cudaErrorInvalidValue;
+        bn = 64;
+    }
     TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1, 0, 0, 0, 0, 0, 0};
+    p.a_block_k = g.a_block_k;
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
     const bool conv = g.im2col.ksz > 0;
@@ -1015,7 +1022,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
         if (c.C % BK != 0 || g.K != c.ksz * c.ksz * c.C || (long)c.N * c.Wo * c.Ho != g.M) return cudaErrorInvalidValue;
         p.cv_cpk = c.C / BK; p.cv_ksz = c.ksz; p.cv_stride = c.stride; p.cv_lower = -c.pad_lo; p.cv_Wo = c.Wo; p.cv_Ho = c.Ho;
         if ((e = tma_map_im2col_bf16(g.A, c, &a)) != cudaSuccess) return e;
-    } else if ((e = get_map(g.A, g.M, g.K, g.lda, BM, &a)) != cudaSuccess) return e;
+    } else if ((e = get_map(g.A, g.M, g.a_block_k ? (g.N / 64) * g.a_block_k : g.K, g.lda, BM, &a)) != cudaSuccess) return e;
     if ((e = get_map(g.W, g.N, g.K, g.ldw, bn, &w)) != cudaSuccess) return e;
     a2 = a; w2 = w;
     if (split) {
