@@ -143,7 +143,7 @@ def run_reference_arm(args, rank: int):
     if rank != 0:
         return
     total = max(1, args.steps + args.warmup)
-    n_eq = max(1, min(8, 48 // total))
+    n_eq = max(1, min(8, 160 // total))        # B = 8 (BASELINE config 1) at ~4.7 s per step on 16 cores unless many steps are asked for
     v, cores, per_step = cpu_reference_eq_per_s(n_eq, steps=args.steps, warmup=args.warmup)
     sample = f"B={n_eq} synthetic {H}x{W} images, full {MAX_LEN}-step greedy loop without KV cache (reference algorithm), fp32 torch CPU"
     line = {

@@ -29,8 +29,8 @@ class GeneratePipeline:
     ``branches``: decode branches per replica (rows per kernel launch = batch / branches).  With several batches in flight
     the device sees ``in_flight * branches`` independent kernel chains; fewer, larger launches per chain are better then
     (measured on B200 at batch 512 with the projected-K/V attention: in_flight 6 x 1 branch 7.9 k eq/s, 8 x 1: 7.9 k, 4 x 2: 7.5 k,
-    4 x 4: 7.4 k, 3 x 6: 6.8 k, one batch at a time with 6 branches 5.5 k; with the absorbed attention 6 x 1: 10.3-10.6 k, 8 x 1: 10.3 k,
-    6 x 2: 9.8 k).
+    4 x 4: 7.4 k, 3 x 6: 6.8 k, one batch at a time with 6 branches 5.5 k; with the absorbed attention 6 x 1: 11.0-11.1 k, 8 x 1 about the same,
+    6 x 2: 5 % less).
     """
 
     def __init__(self, model, in_flight: int = 6, branches: Optional[int] = 1):
