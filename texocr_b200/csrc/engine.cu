@@ -1159,7 +1159,7 @@ static int run_generate_mega(texocr_handle* h, const DecState& ds, int eos, cons
     const int L = c.dec_layers;
     ENSURE(h->mega_part, (size_t)B * MEGA_CLUSTER * 8);
     for (int s2 = 0; s2 < 2; ++s2)
-        if (!h->poll_ev[s2][0]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][0], cudaEventDisableTiming));
+        if (!h->poll_ev[s2][0]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][0], cudaEventDisableTiming | cudaEventBlockingSync));
     MegaArgs a{};
     a.B = B; a.L = L; a.V = c.vocab_size; a.tcap = tcap; a.eos = eos; a.G = groups;
     for (int l = 0; l < L; ++l) {
@@ -1206,7 +1206,11 @@ static int run_generate_mega(texocr_handle* h, const DecState& ds, int eos, cons
     CK(cudaMemcpyAsync(&h->h_poll[2 * MAX_BRANCH], ds.done_step, MAX_BRANCH * 4, cudaMemcpyDeviceToHost, st));
     int r;
     if ((r = from_device(h, out_ids, h->out_ids.p, (size_t)B * tcap * 8, st))) return r;
-    CK(cudaStreamSynchronize(st));
+    // The host waits on blocking-sync events (the thread sleeps instead of spinning): with several batches in flight per GPU and
+    // several ranks per box there are more waiting host threads than cores.
+    if (!h->done_ev) CK(cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventRecord(h->done_ev, st));
+    CK(cudaEventSynchronize(h->done_ev));
     int done = 0;
     bool all_done = true;
     for (int i = 0; i < groups; ++i) {
@@ -1354,7 +1358,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
         CK(cudaEventRecord(h->fork_ev, st));
         CK(cudaStreamWaitEvent(cs, h->fork_ev, 0));
         for (int s2 = 0; s2 < 2; ++s2)
-            if (!h->poll_ev[s2][0]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][0], cudaEventDisableTiming));
+            if (!h->poll_ev[s2][0]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][0], cudaEventDisableTiming | cudaEventBlockingSync));
         for (int i = 0; i < bp.n; ++i)
             if ((r = enqueue_first_embed(h, B, bp.row0[i], bp.rows[i], i, cs))) return r;
         const int POLL = 16;
@@ -1415,7 +1419,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     }
     for (int s2 = 0; s2 < 2; ++s2)
         for (int i = 0; i < bp.n; ++i)
-            if (!h->poll_ev[s2][i]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][i], cudaEventDisableTiming));
+            if (!h->poll_ev[s2][i]) CK(cudaEventCreateWithFlags(&h->poll_ev[s2][i], cudaEventDisableTiming | cudaEventBlockingSync));
     for (int i = 0; i < bp.n && fifo == 0; ++i)
         if ((r = enqueue_first_embed(h, B, bp.row0[i], bp.rows[i], i, bst[i]))) return r;
     // Host runs ahead of the device by at most 2*POLL steps; an early exit costs at most that many extra steps.
@@ -1452,7 +1456,11 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     }
     CK(cudaMemcpyAsync(&h->h_poll[2 * MAX_BRANCH], ds.done_step, MAX_BRANCH * 4, cudaMemcpyDeviceToHost, st));
     if ((r = from_device(h, out_ids, h->out_ids.p, (size_t)B * tcap * 8, st))) return r;
-    CK(cudaStreamSynchronize(st));
+    // The host waits on blocking-sync events (the thread sleeps instead of spinning): with several batches in flight per GPU and
+    // several ranks per box there are more waiting host threads than cores.
+    if (!h->done_ev) CK(cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventRecord(h->done_ev, st));
+    CK(cudaEventSynchronize(h->done_ev));
     // every row holds an EOS once every branch has seen one in all of its rows: the LAST branch to finish decides
     int done = 0;
     bool all_done = true;
@@ -1518,6 +1526,7 @@ void texocr_destroy(texocr_handle* h) {
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);
     if (h->geom_ev) cudaEventDestroy(h->geom_ev);
+    if (h->done_ev) cudaEventDestroy(h->done_ev);
     if (h->hop_in) cudaEventDestroy(h->hop_in);
     if (h->hop_out) cudaEventDestroy(h->hop_out);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

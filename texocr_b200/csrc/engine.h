@@ -68,6 +68,7 @@ struct texocr_handle {
     // ---- workspaces (grow-only)
     DevBuf geom;                               // int32: img_off[B+1] | img_hw[2B] | tok_off[B+1] | row_off[B+1]
     int* h_geom = nullptr; size_t h_geom_cap = 0;   // pinned staging for geom
+    cudaEvent_t done_ev = nullptr;             // blocking-sync event the host waits on at the end of a generate call
     cudaEvent_t geom_ev = nullptr, hop_in = nullptr, hop_out = nullptr;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaStream_t branch_stream[16] = {nullptr}; cudaEvent_t join_ev[16] = {nullptr}; cudaEvent_t fork_ev = nullptr;
