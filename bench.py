@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -311,8 +311,10 @@ def main():
         pipe.warm_up(img_dev, MAX_LEN)
         for _ in range(args.warmup):
             steps_device(n_fly)
+    # one sampler per job (rank 0's GPU), not per rank: eight nvidia-smi pollers next to eight ranks perturb the launch path
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if rank == 0:
+        clocks.start()
     serial = None
     if pipe is None:
         l0 = eng.kernel_launches()
