@@ -66,7 +66,8 @@ typedef struct {
     int32_t bos_token, eos_token, pad_token;
     int32_t encoder_kind;    /* texocr_encoder_kind                                           */
     int32_t precision;       /* texocr_precision: FP32 = parity tier (FFMA everywhere);
-                                BF16 = bf16 operands / KV cache, fp32 accumulate + statistics  */
+                                BF16 = bf16 operands / attention cache, fp32 accumulate + statistics; the
+                                generate loop runs its attention in the absorbed (latent) form, DESIGN.md 5c    */
 } texocr_config;
 
 /* replaces: create_model(config) (model/ocr_model.py:113-130) */
