@@ -87,3 +87,50 @@ dist.destroy_process_group()
                           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
                          capture_output=True, text=True, env=env, timeout=240)
     assert "GATHER_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_generate_pipeline_host_logic_with_stand_in_engines():
+    """GeneratePipeline's host side (queue, worker threads, ordering, result buffers, error propagation) with stand-in engines:
+    no device and no native library involved -- the GPU behaviour is covered by test_pipeline_of_batches_in_flight_matches_generate."""
+    import threading
+    import time
+    import torch
+    from texocr_b200.pipeline import GeneratePipeline
+
+    class FakeEngine:
+        def __init__(self, tag, delay):
+            self.tag, self.delay, self.calls, self.threads = tag, delay, 0, set()
+
+        def generate(self, images, max_len, out=None):
+            self.calls += 1
+            self.threads.add(threading.get_ident())
+            time.sleep(self.delay * (1 + (int(images.sum()) % 3)))            # finish out of order
+            if int(images.flatten()[0]) < 0:
+                raise RuntimeError("bad batch")
+            res = images.reshape(images.shape[0], -1)[:, :1].to(torch.int64).repeat(1, max_len)
+            if out is not None:
+                out[:, :max_len] = res
+                return out[:, :max_len]
+            return res
+
+        def kernel_launches(self):
+            return self.calls
+
+    engines = [FakeEngine(i, 0.002) for i in range(3)]
+    pipe = GeneratePipeline(None, engines=engines)
+    batches = [torch.full((2 + i % 3, 1, 2, 2), float(i)) for i in range(11)]
+    got = list(pipe.generate_batches(batches, 5))
+    assert [int(g[0, 0]) for g in got] == list(range(11)) and all(g.shape == (2 + i % 3, 5) for i, g in enumerate(got))     # submission order
+    assert sum(e.calls for e in engines) == 11 and all(e.calls > 0 for e in engines)           # work was shared
+    assert all(len(e.threads) == 1 for e in engines) and len({next(iter(e.threads)) for e in engines}) == 3   # one thread per engine
+    outs = [torch.zeros((b.shape[0], 8), dtype=torch.int64) for b in batches]
+    got2 = list(pipe.generate_batches(batches, 8, outs=outs))
+    assert all(g.data_ptr() == o.data_ptr() and int(o[0, 7]) == i for i, (g, o) in enumerate(zip(got2, outs)))
+    pipe.warm_up(batches[0], 3)
+    assert pipe.kernel_launches() == 11 + 11 + 3
+    bad = [batches[0], torch.full((1, 1, 2, 2), -1.0), batches[2]]
+    with pytest.raises(RuntimeError, match="bad batch"):
+        list(pipe.generate_batches(bad, 4))
+    assert int(list(pipe.generate_batches(batches[:2], 2))[1][0, 0]) == 1                      # still usable after an error
+    pipe.close()
+    assert pipe.engines == []

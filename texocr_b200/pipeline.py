@@ -33,19 +33,25 @@ class GeneratePipeline:
     6 x 2: 5 % less).
     """
 
-    def __init__(self, model, in_flight: int = 6, branches: Optional[int] = 1):
+    def __init__(self, model, in_flight: int = 6, branches: Optional[int] = 1, engines: Optional[Sequence] = None):
         if in_flight < 1:
             raise ValueError("in_flight must be >= 1")
-        if model.device.type != "cuda":
-            raise RuntimeError("texocr_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
         self.model = model
-        self.device = model.device
-        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        sd = model.state_dict()
-        self.engines: List[Engine] = [Engine(model.dims, sd, model.precision, idx) for _ in range(in_flight)]
-        if branches:
-            for e in self.engines:
-                e.set_option("decode_branches", int(branches))
+        if engines is not None:
+            # host-logic tests inject stand-in engines (objects with generate(images, max_len, out=)); no device is touched
+            self.device = None
+            self.engines = list(engines)
+        else:
+            if model.device.type != "cuda":
+                raise RuntimeError("texocr_b200 runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+            self.device = model.device
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            sd = model.state_dict()
+            self.engines = [Engine(model.dims, sd, model.precision, idx) for _ in range(in_flight)]
+            if branches:
+                for e in self.engines:
+                    e.set_option("decode_branches", int(branches))
+        in_flight = len(self.engines)
         self._q: "queue.Queue" = queue.Queue()
         self._threads = [threading.Thread(target=self._worker, args=(i,), daemon=True) for i in range(in_flight)]
         for t in self._threads:
@@ -54,14 +60,19 @@ class GeneratePipeline:
     # ------------------------------------------------------------------ workers
     def _worker(self, i: int):
         eng = self.engines[i]
-        torch.cuda.set_device(self.device)
-        stream = torch.cuda.Stream(device=self.device)
+        stream = None
+        if self.device is not None:
+            torch.cuda.set_device(self.device)
+            stream = torch.cuda.Stream(device=self.device)
         while True:
             job = self._q.get()
             if job is None:
                 return
             images, max_len, out, ready, slot, results, done = job
             try:
+                if stream is None:
+                    results[slot] = eng.generate(images, max_len, out=out)
+                    continue
                 with torch.cuda.stream(stream):
                     if ready is not None:
                         stream.wait_event(ready)              # inputs were produced on the caller's stream
@@ -81,7 +92,7 @@ class GeneratePipeline:
         results: List = [None] * n
         done = [threading.Semaphore(0) for _ in range(n)]
         ready = None
-        if any(isinstance(b, torch.Tensor) and b.is_cuda for b in batches):
+        if self.device is not None and any(isinstance(b, torch.Tensor) and b.is_cuda for b in batches):
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.device))
         for i, b in enumerate(batches):
@@ -97,7 +108,8 @@ class GeneratePipeline:
         batch pays for them.  Must not overlap generate_batches."""
         for e in self.engines:
             e.generate(batch, int(max_len))
-        torch.cuda.synchronize(self.device)
+        if self.device is not None:
+            torch.cuda.synchronize(self.device)
 
     def kernel_launches(self) -> int:
         return sum(e.kernel_launches() for e in self.engines)
@@ -108,7 +120,8 @@ class GeneratePipeline:
         for t in self._threads:
             t.join(timeout=10)
         for e in self.engines:
-            e.close()
+            if hasattr(e, "close"):
+                e.close()
         self.engines = []
 
     def __enter__(self):
