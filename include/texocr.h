@@ -183,6 +183,14 @@ TEXOCR_API int texocr_debug_attn_decode(texocr_handle* h, int32_t self, const vo
 TEXOCR_API int texocr_debug_attn_abs(texocr_handle* h, const void* q, void* latent, int64_t latent_rows, const int32_t* k_off_dev,
                           const void* znew, int32_t tcap, const int32_t* step_dev, void* out, int32_t batch, void* stream);
 
+/* Test hook, host only (needs no device and no handle): the weight folding of the absorbed attention.
+ * wq / wk / wv float32 [512, 256], wo float32 [512, 512] of one MultiHeadAttention (model/attention.py:87-99) ->
+ * wqk_out float32 [2048, 256] (row h*256 + c = sum_d Wk[h*64+d][c] * Wq[h*64+d][:]) and wvo_out float32 [512, 2048] (column
+ * h*256 + c = sum_d Wo[:, h*64+d] * Wv[h*64+d][c]; rows interleaved (value, gate) like the out-projection for its GLU epilogue),
+ * both computed from the bf16 roundings of the inputs, as the bf16 tier does. */
+TEXOCR_API int texocr_debug_fold_absorbed(const float* wq, const float* wk, const float* wv, const float* wo, float* wqk_out,
+                               float* wvo_out);
+
 #ifdef __cplusplus
 }
 #endif

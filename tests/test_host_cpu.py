@@ -134,3 +134,38 @@ def test_generate_pipeline_host_logic_with_stand_in_engines():
     assert int(list(pipe.generate_batches(batches[:2], 2))[1][0, 0]) == 1                      # still usable after an error
     pipe.close()
     assert pipe.engines == []
+
+
+def test_absorbed_attention_weight_folding_is_the_same_function():
+    """The library's own folding code (host only, no device): attention computed from the folded matrices -- Q' = x Wqk^T scored
+    against the 256-wide latent rows, C = P Z, y = C Wvo^T -- equals the reference formulation q K^T / softmax / P V / Wo
+    (model/attention.py:114-180) on the same bf16-rounded weights, in float64."""
+    import ctypes as C
+    import numpy as np
+    from texocr_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(5)
+    bf = lambda a: torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+    wq, wk, wv = (rng.standard_normal((512, 256)).astype(np.float32) * 0.06 for _ in range(3))
+    wo = rng.standard_normal((512, 512)).astype(np.float32) * 0.04
+    wqk = np.empty((2048, 256), np.float32)
+    wvo = np.empty((512, 2048), np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert lib.texocr_debug_fold_absorbed(ptr(wq), ptr(wk), ptr(wv), ptr(wo), ptr(wqk), ptr(wvo)) == 0
+    x = rng.standard_normal((5, 256))             # query-side inputs (LayerNorm'd rows)
+    z = rng.standard_normal((7, 256))             # latent rows (encoder memory / cached LayerNorm'd inputs)
+    q64, k64, v64, o64 = (bf(w).astype(np.float64) for w in (wq, wk, wv, wo))
+    q = (x @ q64.T).reshape(5, 8, 64)
+    k = (z @ k64.T).reshape(7, 8, 64)
+    v = (z @ v64.T).reshape(7, 8, 64)
+    sc = np.einsum("nhd,mhd->hnm", q, k) * 0.125
+    p = np.exp(sc - sc.max(-1, keepdims=True)); p /= p.sum(-1, keepdims=True)
+    y = np.einsum("hnm,mhd->nhd", p, v).reshape(5, 512) @ o64.T                      # [5, 512]: value half | gate half
+    y_il = np.empty_like(y); y_il[:, 0::2] = y[:, :256]; y_il[:, 1::2] = y[:, 256:]  # the GLU epilogue's (value, gate) interleave
+    qa = (x @ wqk.astype(np.float64).T).reshape(5, 8, 256)
+    sa = np.einsum("nhc,mc->hnm", qa, z) * 0.125
+    pa = np.exp(sa - sa.max(-1, keepdims=True)); pa /= pa.sum(-1, keepdims=True)
+    ca = np.einsum("hnm,mc->nhc", pa, z).reshape(5, 2048)
+    ya = ca @ wvo.astype(np.float64).T
+    assert np.abs(sa - sc).max() < 1e-4 * np.abs(sc).max()                            # fp32 storage of the folded matrices
+    assert np.abs(ya - y_il).max() < 1e-4 * np.abs(y_il).max()

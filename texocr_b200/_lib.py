@@ -23,7 +23,7 @@ EXPORTS = (
     "texocr_create", "texocr_destroy", "texocr_last_error", "texocr_set_weight", "texocr_finalize_weights",
     "texocr_encode", "texocr_decoder_logits", "texocr_decoder_generate", "texocr_generate", "texocr_cross_entropy",
     "texocr_kernel_launches", "texocr_profile_enable", "texocr_profile_read", "texocr_set_option", "texocr_debug_read",
-    "texocr_debug_gemm", "texocr_debug_attn_decode", "texocr_debug_attn_abs", "texocr_set_sampling", "texocr_debug_sample_step", "texocr_preprocess_u8",
+    "texocr_debug_gemm", "texocr_debug_attn_decode", "texocr_debug_attn_abs", "texocr_debug_fold_absorbed", "texocr_set_sampling", "texocr_debug_sample_step", "texocr_preprocess_u8",
 )
 
 
@@ -76,6 +76,7 @@ def load_library() -> C.CDLL:
     lib.texocr_debug_read.restype = i64
     lib.texocr_debug_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]
     lib.texocr_debug_attn_decode.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, i64, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]
+    lib.texocr_debug_fold_absorbed.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.texocr_debug_attn_abs.argtypes = [vp, vp, vp, i64, vp, vp, i32, vp, vp, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)

@@ -1991,4 +1991,16 @@ int texocr_debug_attn_abs(texocr_handle* h, const void* q, void* latent, int64_t
     CK(cudaStreamSynchronize(st));
     return 0;
 }
+
+int texocr_debug_fold_absorbed(const float* wq, const float* wk, const float* wv, const float* wo, float* wqk_out, float* wvo_out) {
+    if (!wq || !wk || !wv || !wo || !wqk_out || !wvo_out) return TEXOCR_ERR_ARG;
+    HostTensor q, k, v, o;
+    q.shape = k.shape = v.shape = {512, 256}; o.shape = {512, 512};
+    q.data.assign(wq, wq + 512 * 256); k.data.assign(wk, wk + 512 * 256); v.data.assign(wv, wv + 512 * 256); o.data.assign(wo, wo + 512 * 512);
+    std::vector<float> wqk, wvoi;
+    fold_absorbed(q, k, v, o, wqk, wvoi);
+    memcpy(wqk_out, wqk.data(), wqk.size() * sizeof(float));
+    memcpy(wvo_out, wvoi.data(), wvoi.size() * sizeof(float));
+    return 0;
+}
 }  // extern "C"
