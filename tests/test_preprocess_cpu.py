@@ -23,7 +23,10 @@ def test_bucket_batches_match_reference_sampler():
     assert _rows(g["bucket_shuf_e0"]) != _rows(g["bucket_shuf_e1"])
     assert len(b) == int(g["bucket_shuf_len"]) and len(BucketBatcher(sizes, 4, keep_small=False)) == int(g["bucket_drop_len"])
     # every batch holds one image size only; every image appears exactly once when small batches are kept
-    for batch in bucket_batches(sizes, 4):
+    for batch in bucket_batches(sizes, 4, keep_small=True):
         assert len({sizes[i] for i in batch}) == 1
-    assert sorted(i for batch in bucket_batches(sizes, 4) for i in batch) == list(range(len(sizes)))
+    assert sorted(i for batch in bucket_batches(sizes, 4, keep_small=True) for i in batch) == list(range(len(sizes)))
+    # defaults are the reference sampler's (data_wrangling/dataset.py:282): keep_small=False, seed=42
+    assert bucket_batches(sizes, 4) == _rows(g["bucket_drop_e0"])
+    assert list(BucketBatcher(sizes, 4, shuffle=True)) == bucket_batches(sizes, 4, shuffle=True, seed=42)
     assert bucket_batches([], 4) == []

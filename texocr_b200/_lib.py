@@ -15,7 +15,7 @@ import torch
 from .spec import ModelDims
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtexocr_b200.so")
+LIB_PATH = os.environ.get("TEXOCR_B200_LIB") or os.path.join(_HERE, "libtexocr_b200.so")      # the override is for A/B builds of experiments
 ABI_VERSION = 1
 
 # every symbol include/texocr.h declares (tests check the library exports exactly these)

@@ -18,6 +18,8 @@
 #include "tc_gemm.h"
 
 int g_attn_full_tail = 0;
+int g_attn_l2_policy = 0;    // attn_abs_kernel TMA loads: bit 0 = self-attention cache rows evict-first (each row is read once per step and layer),
+                             // bit 1 = cross-attention memory rows evict-last (the same [S, 256] rows serve all 4 layers of all 256 steps)
 int g_attn_abs_minb = 3;     // attn_abs_kernel: 3 = 128 registers, no spills (default: 1-3 % better with batches in flight); 4 = 96 registers (small spills), 4 CTAs per SM
 
 namespace {
@@ -68,6 +70,11 @@ TX_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 TX_DEVINL uint64_t l2_evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+TX_DEVINL uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint64_t pol) {
@@ -366,7 +373,10 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
 // Self-attention: this step's own latent row (position t) is written into the last stage by the consumers (it is key t of
 // that stage) and appended to the cache for the following steps.
 constexpr int AW = 4;                       // consumer warps = 64-column blocks of a latent row
-constexpr int ANS = 5;                      // ring stages of the absorbed kernel (40 KB)
+#ifndef TEXOCR_ABS_STAGES
+#define TEXOCR_ABS_STAGES 5
+#endif
+constexpr int ANS = TEXOCR_ABS_STAGES;                      // ring stages of the absorbed kernel (40 KB)
 constexpr int XROW = 40;                    // floats per (warp, head) row of the score exchange: 32 keys, padded so that a half-warp's float2 accesses hit 32 distinct banks
 struct AbsArgs {
     const bf16* q; int ldq;            // [batch, ldq]: head h at h*256 (absorbed query, unscaled)
@@ -378,6 +388,7 @@ struct AbsArgs {
     int batch;
     unsigned long long* trace; const int* trace_step; int trace_k;
     unsigned long long* dbg;           // debug: sums over CTAs of [wait for predecessor, first data, stage loop, epilogue] ns + count
+    int l2_policy;                     // 0 = no hint, 1 = evict-first, 2 = evict-last
 };
 
 template <bool SELF, int MINB>
@@ -416,6 +427,8 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         if (lane == 0) {
             int it = 0;
             if (SELF) asm volatile("fence.proxy.async.global;" ::: "memory");     // cache rows were appended by generic-proxy stores of earlier steps
+            const bool hint = a.l2_policy != 0;
+            const uint64_t pol = a.l2_policy == 2 ? l2_evict_last_policy() : l2_evict_first_policy();
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 int row0, nc;      // nc = rows to fetch; self: the t cached rows (this step's own row is added by the consumers)
                 if (SELF) { row0 = u * a.tcap; nc = t; }
@@ -429,13 +442,19 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
                     if (left >= CH) {
                         mbar_expect_tx(&full[s], STAGE);
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) tma_load_2d_nohint(&tm, &full[s], st + cb * HTILE, 64 * cb, r);
+                        for (int cb = 0; cb < 4; ++cb) {
+                            if (hint) tma_load_2d(&tm, &full[s], st + cb * HTILE, 64 * cb, r, pol);
+                            else tma_load_2d_nohint(&tm, &full[s], st + cb * HTILE, 64 * cb, r);
+                        }
                     } else {               // tail: 4-row boxes (none at all when only this step's own row is left)
                         const int n4 = left > 0 ? (left + 3) >> 2 : 0;
                         mbar_expect_tx(&full[s], n4 * 4 * 512);
                         for (int j = 0; j < n4; ++j)
 #pragma unroll
-                            for (int cb = 0; cb < 4; ++cb) tma_load_2d_nohint(&tm4, &full[s], st + cb * HTILE + j * 512, 64 * cb, r + 4 * j);
+                            for (int cb = 0; cb < 4; ++cb) {
+                                if (hint) tma_load_2d(&tm4, &full[s], st + cb * HTILE + j * 512, 64 * cb, r + 4 * j, pol);
+                                else tma_load_2d_nohint(&tm4, &full[s], st + cb * HTILE + j * 512, 64 * cb, r + 4 * j);
+                            }
                     }
                 }
             }
@@ -669,6 +688,7 @@ cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     k.q = (const bf16*)a.q; k.ldq = a.ldq; k.k_off = a.k_off; k.o = (bf16*)a.o; k.ldo = a.ldo; k.batch = a.batch;
     k.znew = (const bf16*)a.znew; k.ldz = a.ldz; k.cache = (bf16*)const_cast<void*>(a.latent); k.tcap = a.tcap; k.step = a.step;
     k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k; k.dbg = a.dbg;
+    k.l2_policy = a.znew ? ((g_attn_l2_policy & 1) ? 1 : 0) : ((g_attn_l2_policy & 2) ? 2 : 0);
     // persistent grid: never more CTAs than can be resident (the rest would only queue behind them without the cross-unit prefetch)
     static int occ[2][2] = {{0, 0}, {0, 0}};
     static int sms = 0;

@@ -23,6 +23,8 @@
 extern int g_tc_split_k;
 extern int g_tc_persistent;
 extern int g_tc_persistent_stages;
+extern int g_tc_persist_min_tiles;
+extern int g_tc_tiles_per_cta;
 extern int g_tc_min_ctas;
 extern int g_tc_deep_ring;
 extern int g_tc_shallow_ring;
@@ -38,6 +40,7 @@ static std::recursive_mutex g_dev_mu;
 int g_texocr_pdl = 0x3f;
 extern int g_attn_full_tail;
 extern int g_attn_abs_minb;
+extern int g_attn_l2_policy;
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -1305,7 +1308,9 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     const bool own = graph_ok && (bp.n > 1 || h->decode_priority);
     for (int i = 0; i < bp.n; ++i) bst[i] = !own ? st : (i == 0 ? h->own_stream2 : h->branch_stream[i]);
     const void* ckv_key = absorb ? h->dec_enc : h->crosskv_hm.p;
-    const int samp_key = h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0;
+    const int samp_key = h->samp_temp > 0.0 ? sampling_k(h) : 0;      // seed and temperature are compared in full (gkey.samp_seed / samp_temp)
+    const uint64_t seed_key = h->samp_temp > 0.0 ? h->samp_seed : 0;
+    const double temp_key = h->samp_temp > 0.0 ? h->samp_temp : 0.0;
     // ---- coupled mode: one graph holds all branches of `spg` steps; attention launches are chained across branches (FIFO of
     // depth `fifo`), everything else of a branch only depends on the branch itself
     const int fifo = (graph_ok && bp.n > 1 && h->attn_fifo > 0 && 2 * c.dec_layers <= FIFO_STRIDE) ? std::min(h->attn_fifo, bp.n) : 0;
@@ -1313,7 +1318,8 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
         cudaStream_t cs = h->own_stream2;
         const int spg = std::max(1, std::min(h->steps_per_graph, 16));
         const bool hit = h->cgraph_exec[0] && h->cgraph_exec[1] && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos &&
-                         h->gkey.max_s == max_s && h->gkey.samp == samp_key && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == kv_key &&
+                         h->gkey.max_s == max_s && h->gkey.samp == samp_key && h->gkey.samp_seed == seed_key && h->gkey.samp_temp == temp_key &&
+                         h->gkey.enc_off == d_enc_off && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == kv_key &&
                          h->gkey.ckv == ckv_key && h->gkey.x == h->x.p && h->gkey.nb == bp.n && h->gkey.fifo == fifo && h->gkey.spg == spg;
         if (!hit) {
             std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
@@ -1351,7 +1357,8 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
                 h->cgraph_kernels[slot] = (int)(h->launches - before);
                 h->launches = before;
             }
-            h->gkey.samp = samp_key; h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
+            h->gkey.samp = samp_key; h->gkey.samp_seed = seed_key; h->gkey.samp_temp = temp_key; h->gkey.enc_off = d_enc_off;
+            h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
             h->gkey.kv = const_cast<void*>(kv_key); h->gkey.ckv = const_cast<void*>(ckv_key); h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
             h->gkey.fifo = fifo; h->gkey.spg = spg;
         }
@@ -1389,7 +1396,8 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
     if (fifo > 0) {
     } else if (graph_ok) {
         const bool hit = h->graph_exec && h->gkey.B == B && h->gkey.tcap == tcap && h->gkey.eos == eos && h->gkey.max_s == max_s &&
-                         h->gkey.samp == (h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0) && h->gkey.ntok == h->crosskv_rows && h->gkey.kv == kv_key && h->gkey.ckv == ckv_key && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
+                         h->gkey.samp == samp_key && h->gkey.samp_seed == seed_key && h->gkey.samp_temp == temp_key && h->gkey.enc_off == d_enc_off &&
+                         h->gkey.ntok == h->crosskv_rows && h->gkey.kv == kv_key && h->gkey.ckv == ckv_key && h->gkey.x == h->x.p && h->gkey.nb == bp.n;
         if (!hit) {
             std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
             drop_graphs(h);
@@ -1405,7 +1413,7 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
             h->graph = h->bgraph[0]; h->graph_exec = h->bgraph_exec[0];
             h->gkey.kernels = (int)(h->launches - before) / bp.n;
             h->launches = before;        // capture does not execute
-            h->gkey.samp = h->samp_temp > 0.0 ? sampling_k(h) * 1000003 + (int)(h->samp_seed % 1000003) + (int)(h->samp_temp * 4096) : 0;
+            h->gkey.samp = samp_key; h->gkey.samp_seed = seed_key; h->gkey.samp_temp = temp_key; h->gkey.enc_off = d_enc_off;
             h->gkey.B = B; h->gkey.tcap = tcap; h->gkey.eos = eos; h->gkey.max_s = max_s; h->gkey.nb = bp.n;
             h->gkey.kv = const_cast<void*>(kv_key); h->gkey.ckv = const_cast<void*>(ckv_key); h->gkey.x = h->x.p; h->gkey.ntok = h->crosskv_rows;
         }
@@ -1525,6 +1533,7 @@ void texocr_destroy(texocr_handle* h) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);
+    if (h->h_bos) cudaFreeHost(h->h_bos);
     if (h->geom_ev) cudaEventDestroy(h->geom_ev);
     if (h->done_ev) cudaEventDestroy(h->done_ev);
     if (h->hop_in) cudaEventDestroy(h->hop_in);
@@ -1711,9 +1720,16 @@ int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, in
     if ((r = plan_geometry(h, hw, batch, g, st))) return r;
     const void* d_img = nullptr;
     if ((r = to_device(h, images, (size_t)total_pixels(hw, batch) * 4, h->img_stage, &d_img, st))) return r;
-    std::vector<int64_t> start((size_t)batch, (int64_t)h->cfg.bos_token);      // model/ocr_model.py:57
+    // start column = BOS for every row (model/ocr_model.py:57): pinned, constant content, copied on the work stream
+    if (h->h_bos_cap < (size_t)batch) {
+        std::lock_guard<std::recursive_mutex> lk(g_dev_mu);
+        if (h->h_bos) { CK(cudaStreamSynchronize(st)); CK(cudaFreeHost(h->h_bos)); h->h_bos = nullptr; }
+        h->h_bos_cap = std::max((size_t)batch, (size_t)1024);
+        CK(cudaMallocHost(&h->h_bos, h->h_bos_cap * 8));
+        for (size_t i = 0; i < h->h_bos_cap; ++i) h->h_bos[i] = (int64_t)h->cfg.bos_token;
+    }
     ENSURE(h->ids_stage, (size_t)batch * 8);
-    CK(cudaMemcpy(h->ids_stage.p, start.data(), (size_t)batch * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(h->ids_stage.p, h->h_bos, (size_t)batch * 8, cudaMemcpyHostToDevice, st));
     if ((r = run_encoder(h, (const float*)d_img, g, st))) return r;
     if ((r = run_crosskv(h, h->enc_out.as<float>(), h->dt == DT_F32 ? nullptr : h->enc_a.p, g.ntok, st, true))) return r;
     return run_generate(h, h->ids_stage.as<int64_t>(), h->cfg.eos_token, g.d_tok_off, g.max_tok, (double)g.ntok, batch, max_len, out_ids, n_steps, st);
@@ -1857,6 +1873,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "attn_l2_policy")) { g_attn_l2_policy = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_abs_minb")) { g_attn_abs_minb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "decode_priority")) { h->decode_priority = (int)value; return 0; }      // before the first generate call
     if (!strcmp(name, "absorb_two_stage")) { h->absorb_two_stage = (int)value; drop_graphs(h); return 0; }
@@ -1868,6 +1885,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "fifo_pdl")) { h->fifo_pdl = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_full_tail")) { g_attn_full_tail = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "fuse_ln")) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
+    if (!strcmp(name, "keep_logits")) { h->keep_logits = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "poison")) { h->poison = value != 0; return 0; }
     if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(8, value)); drop_graphs(h); return 0; }
     if (!strcmp(name, "dbg_skip")) { h->dbg_skip = (int)value; drop_graphs(h); return 0; }
@@ -1890,6 +1908,8 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "gemm_shallow_ring")) { g_tc_shallow_ring = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "gemm_deep_ring")) { g_tc_deep_ring = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "gemm_min_ctas")) { g_tc_min_ctas = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "gemm_persist_min_tiles")) { g_tc_persist_min_tiles = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "gemm_tiles_per_cta")) { g_tc_tiles_per_cta = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "gemm_persistent_stages")) { g_tc_persistent_stages = (int)value; return 0; }
     if (!strcmp(name, "gemm_split_k")) { g_tc_split_k = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "im2col_tma")) { h->use_im2col_tma = value != 0; return 0; }

@@ -88,6 +88,7 @@ struct texocr_handle {
     DevBuf prep_meta, prep_in, prep_out;       // texocr_preprocess_u8 staging
     DevBuf mega_part;                          // cluster-persistent decode kernel: per-CTA argmax partials [B][16] (float | int)
     int* h_poll = nullptr;                     // pinned: done_step polls
+    int64_t* h_bos = nullptr; size_t h_bos_cap = 0;   // pinned: the BOS start column of texocr_generate (constant content)
     int last_backbone_pixels = 0;
     int crosskv_rows = 0;
 
@@ -108,7 +109,8 @@ struct texocr_handle {
     cudaGraph_t cgraph[2] = {nullptr, nullptr}; cudaGraphExec_t cgraph_exec[2] = {nullptr, nullptr}; int cgraph_kernels[2] = {0, 0};
     std::vector<cudaEvent_t> fifo_ev;           // [step in graph][branch][8 attention launches]
     cudaEvent_t* fifo_wait = nullptr; cudaEvent_t* fifo_rec = nullptr;     // set around enqueue_decode_step while capturing
-    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; int fifo = 0; int spg = 0; int absorb = 0; } gkey;
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; int fifo = 0; int spg = 0; int absorb = 0;
+             const int* enc_off = nullptr; uint64_t samp_seed = 0; double samp_temp = 0.0; } gkey;   // enc_off: the cross-attention launches bake this device pointer in
 
     // ---- instrumentation
     int64_t launches = 0;
@@ -133,6 +135,7 @@ struct texocr_handle {
     const void* dec_enc = nullptr;             // bf16 encoder memory of the current generate call [crosskv_rows, 256]
     int use_tma_attn = 1;     // 0 = simple kernel, 1 = TMA kernel for self + cross, 2 = self only, 3 = cross only
     bool fuse_ln = false;    // decode step: LayerNorms computed inside the consuming tcgen05 GEMM (bf16 tier)
+    bool keep_logits = false;   // debug / tests: the decode step also leaves its last-position logits in h->logits (texocr_debug_read "logits")
     bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate
     int dbg_skip = 0;        // timing experiments only: 1 self-attn, 2 cross-attn, 4 LayerNorms, 8 GEMMs (results are garbage)
     // sampling (texocr_set_sampling): temp <= 0 = greedy

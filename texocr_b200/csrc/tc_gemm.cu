@@ -29,6 +29,8 @@ int g_tc_persistent = 1;
 int g_tc_deep_ring = 0;          // 8-stage TMA ring for the K >= 2048 decode GEMMs (single batch: -2.5 %; six batches in flight: +7 %, the 160 KB CTAs crowd the SMs)
 int g_tc_shallow_ring = 0;       // 2-stage ring (40 KB at BN = 32) for every one-tile-per-CTA GEMM: smaller shared-memory footprint next to the attention CTAs
 int g_tc_min_ctas = 120;          // tile width rule: narrow the N tile (128 -> 64 -> 32) while the grid would have fewer CTAs than this
+int g_tc_persist_min_tiles = 296; // persistent kernel for GEMMs of at least this many tiles ...
+int g_tc_tiles_per_cta = 0;       // ... on ceil(tiles / this) CTAs (0 = one CTA per SM): decode-sized GEMMs on few, longer-lived CTAs
 int g_tc_persistent_stages = 0;   // 0 = as many ring stages as fit in 200 KB; n > 0 caps them (leaves shared memory to co-resident kernels)     // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
 
 namespace {
@@ -892,7 +894,8 @@ cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         attr_set = true;
     }
-    const unsigned grid = (unsigned)std::min<long>(tiles, sms);
+    unsigned grid = (unsigned)std::min<long>(tiles, sms);
+    if (g_tc_tiles_per_cta > 0 && tiles < 296) grid = (unsigned)std::min<long>(sms, (tiles + g_tc_tiles_per_cta - 1) / g_tc_tiles_per_cta);
     TcParams pp = p;
     pp.stages = g_tc_persistent_stages > 0 ? std::max(2, std::min(g_tc_persistent_stages, S::STAGES)) : S::STAGES;
     const size_t smem = (size_t)S::TOTAL - (size_t)(S::STAGES - pp.stages) * S::STAGE;
@@ -905,7 +908,7 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     // many tiles (encoder / teacher-forced sizes): shallow pipeline, several CTAs per SM; few tiles: deep pipeline
     const long tiles = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
     if constexpr (BN >= 64) {
-        if (g_tc_persistent && tiles >= 296 && !p.a_block_k) return launch_persistent<BN, EPI, TC, SPLIT>(a, w, a2, w2, p, tiles, st);
+        if (g_tc_persistent && tiles >= g_tc_persist_min_tiles && !p.a_block_k) return launch_persistent<BN, EPI, TC, SPLIT>(a, w, a2, w2, p, tiles, st);
     }
     if (SPLIT == 1 && BN >= 64 && tiles >= 592) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
     if constexpr (SPLIT == 1 && BN == 32 && (EPI == EPI_GLU_RES || EPI == EPI_BIAS_RES)) {
@@ -1004,8 +1007,8 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     // tile width: keep >= ~1 wave of CTAs when M is small (decode steps), 128 otherwise
     const long mt = (g.M + BM - 1) / BM;
     int bn = 128;
-    if (mt * ((g.N + 127) / 128) < 120) bn = 64;
-    if (mt * ((g.N + 63) / 64) < 120 && g.N >= 64) bn = 32;
+    if (mt * ((g.N + 127) / 128) < g_tc_min_ctas) bn = 64;
+    if (mt * ((g.N + 63) / 64) < g_tc_min_ctas && g.N >= 64) bn = 32;
     const bool split = g.A2 != nullptr;
     if (split) bn = g.N <= 64 ? 64 : 128;
     if (g.a_block_k) {

@@ -20,7 +20,8 @@ def process_output(output: str) -> str:
 class Detokenizer:
     """id -> text table of a trained byte-pair tokenizer (tokenizer/tokenizer.py:11-33 for the table construction)."""
 
-    def __init__(self, vocab_bytes: Dict[int, bytes], special_tokens: Optional[Dict[str, int]] = None):
+    def __init__(self, vocab_bytes: Dict[int, bytes], special_tokens: Optional[Dict[str, int]] = None,
+                 vocab_size: Optional[int] = None):
         self.special_tokens = dict(special_tokens or {})
         self.vocab_bytes = {int(k): bytes(v) for k, v in vocab_bytes.items()}
         for tok, tid in self.special_tokens.items():
@@ -28,15 +29,21 @@ class Detokenizer:
         # the reference decodes every token on its own (errors='replace'), so a multi-byte character split over two
         # tokens becomes replacement characters: keep that behaviour by precomputing per-token strings
         self.pieces = {k: v.decode("utf-8", errors="replace") for k, v in self.vocab_bytes.items()}
-        self.vocab_size = len(self.vocab_bytes)
+        # the model is built for the DECLARED vocabulary (line 1 of the tokenizer file, model/ocr_model.py:76): byte-pair
+        # training may stop early (tokenizer/tokenizer.py `if not stats: break`), so the table can hold fewer entries while the
+        # special ids still sit at vocab_size - 1 and below
+        self.vocab_size = len(self.vocab_bytes) if vocab_size is None else int(vocab_size)
+        if self.vocab_bytes and max(self.vocab_bytes) >= self.vocab_size:
+            raise ValueError(f"token id {max(self.vocab_bytes)} does not fit a vocabulary of {self.vocab_size}")
 
     @classmethod
-    def from_merges(cls, merges: Iterable[Sequence[int]], special_tokens: Optional[Dict[str, int]] = None) -> "Detokenizer":
+    def from_merges(cls, merges: Iterable[Sequence[int]], special_tokens: Optional[Dict[str, int]] = None,
+                    vocab_size: Optional[int] = None) -> "Detokenizer":
         """merges: (left id, right id, new id) in training order; ids 0..255 are the raw bytes."""
         vocab = {i: bytes([i]) for i in range(256)}
         for left, right, new in merges:
             vocab[int(new)] = vocab[int(left)] + vocab[int(right)]
-        return cls(vocab, special_tokens)
+        return cls(vocab, special_tokens, vocab_size)
 
     @classmethod
     def load(cls, path: str) -> "Detokenizer":
@@ -48,10 +55,9 @@ class Detokenizer:
             merges = ast.literal_eval(f.readline().strip())
         if not isinstance(special, dict) or not isinstance(merges, dict):
             raise ValueError(f"{path}: not a tokenizer file (expected two dict literals after the vocabulary size)")
-        out = cls.from_merges([(l, r, t) for (l, r), t in merges.items()], special)
-        if out.vocab_size > vocab_size:
-            raise ValueError(f"{path}: {out.vocab_size} entries for a declared vocabulary of {vocab_size}")
-        return out
+        if 256 + len(merges) + len(special) > vocab_size:
+            raise ValueError(f"{path}: {256 + len(merges) + len(special)} entries for a declared vocabulary of {vocab_size}")
+        return cls.from_merges([(l, r, t) for (l, r), t in merges.items()], special, vocab_size)
 
     def decode(self, tokens: Iterable[int]) -> str:
         """RegExTokenizer.decode: concatenation of the per-token strings; unknown ids raise like the reference."""

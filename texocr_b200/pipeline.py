@@ -92,7 +92,12 @@ class GeneratePipeline:
         results: List = [None] * n
         done = [threading.Semaphore(0) for _ in range(n)]
         ready = None
-        if self.device is not None and any(isinstance(b, torch.Tensor) and b.is_cuda for b in batches):
+        def on_device(b):
+            if isinstance(b, torch.Tensor):
+                return b.is_cuda
+            return any(isinstance(t, torch.Tensor) and t.is_cuda for t in b)        # ragged batch: a list of image tensors
+
+        if self.device is not None and any(on_device(b) for b in batches):
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.device))
         for i, b in enumerate(batches):

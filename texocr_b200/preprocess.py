@@ -11,8 +11,8 @@ from collections import OrderedDict
 from typing import Iterator, List, Sequence, Tuple
 
 
-def bucket_batches(sizes: Sequence[Tuple[int, int]], batch_size: int, keep_small: bool = True, shuffle: bool = False,
-                   seed: int = 0) -> List[List[int]]:
+def bucket_batches(sizes: Sequence[Tuple[int, int]], batch_size: int, keep_small: bool = False, shuffle: bool = False,
+                   seed: int = 42) -> List[List[int]]:
     """One epoch of BucketBatchSampler.__iter__ (data_wrangling/dataset.py:303-318) over ``sizes[i]`` = (w, h) of image i."""
     groups: "OrderedDict[Tuple[int, int], List[int]]" = OrderedDict()
     for i, s in enumerate(sizes):
@@ -32,7 +32,8 @@ def bucket_batches(sizes: Sequence[Tuple[int, int]], batch_size: int, keep_small
 class BucketBatcher:
     """Stateful form: every ``iter()`` is one epoch; a shuffling batcher advances its seed per epoch like the reference."""
 
-    def __init__(self, sizes: Sequence[Tuple[int, int]], batch_size: int, keep_small: bool = True, shuffle: bool = False, seed: int = 0):
+    def __init__(self, sizes: Sequence[Tuple[int, int]], batch_size: int, keep_small: bool = False, shuffle: bool = False, seed: int = 42):
+        # defaults as BucketBatchSampler.__init__ (data_wrangling/dataset.py:280-301): keep_small=False, seed=42
         self.sizes = [(int(w), int(h)) for w, h in sizes]
         self.batch_size, self.keep_small, self.shuffle, self.seed = batch_size, keep_small, shuffle, seed
 
