@@ -7,7 +7,7 @@ from texocr_b200 import spec, synth
 
 pytestmark = pytest.mark.gpu
 
-EPI_STORE, EPI_GLU_RES, EPI_GEGLU, EPI_BIAS_RES = 0, 1, 2, 3
+EPI_STORE, EPI_GLU_RES, EPI_GEGLU, EPI_BIAS_RES, EPI_ARGMAX = 0, 1, 2, 3, 4
 
 
 @pytest.fixture(scope="module")
@@ -109,3 +109,40 @@ def test_fp32_ffma_gemm(eng):
     eng.debug_gemm(A, W, C, epi=EPI_GLU_RES, bias=bias, res=res, use_tc=False)
     ref = _ref(A.double(), W.double(), EPI_GLU_RES, bias.double(), res.double()).float()
     assert (C - ref).abs().max() / ref.abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("M,N", [(512, 1000), (86, 1000), (300, 64), (129, 1024)])
+def test_vocab_gemm_with_argmax_epilogue(eng, M, N):
+    """EPI_ARGMAX (the decode step's vocabulary projection, model/decoder.py:60,103): every 32-column tile is reduced to
+    (max, first index of the max) of acc + bias in the GEMM epilogue; the logits themselves are never stored.  Checked against
+    torch on the same operands: per-tile maxima within fp32 GEMM tolerance, indices equal to torch's argmax of the reference
+    wherever the top-2 gap inside the tile is not a rounding tie, and exact lowest-index tie-breaking on duplicated columns."""
+    K = 256
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.06).to(torch.bfloat16)
+    W[N // 2 + 1] = W[N // 2]                                   # two identical columns inside one tile: the first must win
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    bias[N // 2 + 1] = bias[N // 2]
+    nt = (N + 31) // 32
+    P = torch.full((M, nt, 2), float("nan"), device="cuda")
+    eng.debug_gemm(A, W, P, epi=EPI_ARGMAX, bias=bias, use_tc=True, ldc=nt)
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    pad = torch.full((M, nt * 32 - N), float("-inf"), device="cuda")
+    tiles = torch.cat((ref, pad), 1).reshape(M, nt, 32)
+    top2 = tiles.topk(2, dim=-1).values
+    mx, idx = P[..., 0], P[..., 1].contiguous().view(torch.int32)
+    assert (mx - top2[..., 0]).abs().max() / ref.abs().max() < 2e-5
+    ref_idx = tiles.argmax(-1).to(torch.int32) + 32 * torch.arange(nt, device="cuda", dtype=torch.int32)
+    clear = (top2[..., 0] - top2[..., 1]) > 1e-4 * ref.abs().max()
+    assert bool((idx == ref_idx)[clear].all())
+    assert bool((idx >= 0).all()) and bool((idx < N).all())
+    dup_tile = (N // 2) // 32
+    assert not bool((idx[:, dup_tile] == N // 2 + 1).any())     # the duplicate never beats the first occurrence
+    # whole-row argmax from the partials == torch argmax of the reference (up to rounding ties)
+    row_best = mx.argmax(-1)
+    row_idx = idx.gather(1, row_best[:, None])[:, 0]
+    t2 = ref.topk(2, dim=-1).values
+    ok = (t2[:, 0] - t2[:, 1]) > 1e-4 * ref.abs().max()
+    assert bool((row_idx.long() == ref.argmax(-1))[ok].all())

@@ -269,15 +269,16 @@ class Engine:
         self._check(self.lib.texocr_debug_sample_step(self.h, logits.data_ptr(), logits.shape[0], int(step), int(call), out.data_ptr()))
         return out
 
-    def debug_gemm(self, A, W, C, epi=0, bias=None, res=None, use_tc=True, A2=None, W2=None):
-        """Test hook: C = epi(A @ W.T) through the engine's GEMM kernels (tensors on the device, row-major)."""
+    def debug_gemm(self, A, W, C, epi=0, bias=None, res=None, use_tc=True, A2=None, W2=None, ldc=None):
+        """Test hook: C = epi(A @ W.T) through the engine's GEMM kernels (tensors on the device, row-major).
+        ``ldc`` overrides C's leading dimension (epi 4: in {max, index} pairs)."""
         M, K = A.shape
         N = W.shape[0]
         dt_a = 1 if A.dtype == torch.bfloat16 else 0
         dt_c = 1 if C.dtype == torch.bfloat16 else 0
         ptr = lambda t: None if t is None else t.data_ptr()
         self._check(self.lib.texocr_debug_gemm(self.h, A.data_ptr(), W.data_ptr(), C.data_ptr(), M, N, K, A.stride(0), W.stride(0),
-                                               C.stride(0), epi, dt_a, dt_c, ptr(bias), ptr(res), 0 if res is None else res.stride(0),
+                                               C.stride(0) if ldc is None else int(ldc), epi, dt_a, dt_c, ptr(bias), ptr(res), 0 if res is None else res.stride(0),
                                                1 if use_tc else 0, ptr(A2), ptr(W2), self._stream()))
         return C
 

@@ -373,6 +373,9 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
 // Self-attention: this step's own latent row (position t) is written into the last stage by the consumers (it is key t of
 // that stage) and appended to the cache for the following steps.
 constexpr int AW = 4;                       // consumer warps = 64-column blocks of a latent row
+#ifndef TEXOCR_ABS_SKIP
+#define TEXOCR_ABS_SKIP 0
+#endif
 #ifndef TEXOCR_ABS_STAGES
 #define TEXOCR_ABS_STAGES 5
 #endif
@@ -539,9 +542,13 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
 #pragma unroll
                         for (int s2 = 0; s2 < 2; ++s2) {
                             uint32_t b0, b1, b2, b3;
+#if !(TEXOCR_ABS_SKIP & 1)       /* timing experiment builds only: bit 0 drops the score MMAs, bit 1 the P.Z MMAs (garbage results) */
                             ldsm_x4(kts[q] + off_qk[j][s2], b0, b1, b2, b3);
                             mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2], qa[4 * s2 + 1], b0, b1);
                             mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2 + 2], qa[4 * s2 + 3], b2, b3);
+#else
+                            b0 = b1 = b2 = b3 = 0u; sc[q][j][0] += __uint_as_float(qa[4 * s2] & 0x3f800000u);
+#endif
                         }
                     }
                 }
@@ -606,10 +613,14 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
 #pragma unroll
                     for (int np = 0; np < 4; ++np) {
                         uint32_t b0, b1, b2, b3;
+#if !(TEXOCR_ABS_SKIP & 2)
                         ldsm_x4_t(kts[q] + off_pv[np], b0, b1, b2, b3);
                         if (last) { b0 &= vm_lo[q]; b2 &= vm_lo[q]; b1 &= vm_hi[q]; b3 &= vm_hi[q]; }
                         mma_bf16_top(o[2 * np][0], o[2 * np][1], pa0, pa2, b0, b1);
                         mma_bf16_top(o[2 * np + 1][0], o[2 * np + 1][1], pa0, pa2, b2, b3);
+#else
+                        b0 = b1 = b2 = b3 = 0u; o[2 * np][0] += __uint_as_float(pa0 & 0x3f800000u); o[2 * np + 1][1] += __uint_as_float(pa2 & 0x3f800000u);
+#endif
                     }
                 }
             }
@@ -631,6 +642,7 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         }
     }
     if (tr) atomicMax(tr + 4096, gtime());
+    if (a.dbg && threadIdx.x == 32) { atomicAdd(a.dbg + 5, gtime() - t_entry0); atomicAdd(a.dbg + 6, 1ull); }      // CTA residency, all units
 }
 
 int g_smem_set = 0;

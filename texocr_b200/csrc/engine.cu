@@ -458,7 +458,14 @@ static int finalize_weights(texocr_handle* h) {
 // tcgen05 path for bf16 operands when the shape fits its tiles, FFMA path otherwise (and always in the fp32 tier).
 static cudaError_t run_gemm(texocr_handle* h, const GemmArgs& g, cudaStream_t st) {
     if ((h->dbg_skip & 8) && g.M <= 512) return cudaSuccess;
-    if (h->use_tcgen05 && g.dt_a == DT_BF16 && !g.conv && tc_gemm_supported(g)) return launch_gemm_tc(g, st);
+    if (h->use_tcgen05 && g.dt_a == DT_BF16 && !g.conv && tc_gemm_supported(g)) {
+        if (h->attn_trace_on && h->attn_trace.p && g.M <= 4096) {      // decode-sized GEMM: per-CTA residency sums next to the attention timers
+            GemmArgs gd = g;
+            gd.dbg = h->attn_trace.as<unsigned long long>() + (size_t)16 * 3 * 2048 + 16;
+            return launch_gemm_tc(gd, st);
+        }
+        return launch_gemm_tc(g, st);
+    }
     if (g.a_block_k) return cudaErrorInvalidValue;      // block-diagonal mode exists in the tcgen05 kernel only
     return launch_gemm_simt(g, st);
 }
@@ -1081,14 +1088,23 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
         }
     }
     float* lg = h->logits.as<float>() + (size_t)row0 * c.vocab_size;
-    if (fuse) {
+    // greedy bf16 tier: the vocabulary GEMM reduces every 32-column tile to (max, first index) in its epilogue and the token
+    // kernel finishes the argmax over those partials -- the logits never reach HBM (model/decoder.py:60,103 takes
+    // logits[:, -1] of a full (B, T, V) tensor).  Sampling and the keep_logits debug option need the row of logits itself.
+    const int nparts = (c.vocab_size + 31) / 32;
+    const bool fused_amax = !fuse && h->dt == DT_BF16 && h->use_tcgen05 && h->samp_temp <= 0.0 && !h->keep_logits && h->amax_part.p;
+    float2* parts = fused_amax ? h->amax_part.as<float2>() + (size_t)row0 * nparts : nullptr;
+    if (fused_amax) {
+        GemmArgs gl = mk_gemm(xnbuf, 256, h->w_logits, 256, parts, nparts, rows, c.vocab_size, 256, EPI_ARGMAX, h->dt, DT_F32, h->b_logits, nullptr, 0);
+        LAUNCH(KC_DEC_GEMM, 1, (double)rows * 256 * e + (double)c.vocab_size * 256 * e + (double)rows * nparts * 8, gemm_flops(gl), run_gemm(h, gl, st));
+    } else if (fuse) {
         if ((r = gemm_ln(h->w_logits, c.vocab_size, lg, c.vocab_size, EPI_STORE, DT_F32, h->b_logits, false, false, h->dec_norm_g, h->dec_norm_b))) return r;
     } else {
         GemmArgs gl = mk_gemm(xnbuf, 256, h->w_logits, 256, lg, c.vocab_size, rows, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
         LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gl, e), gemm_flops(gl), run_gemm(h, gl, st));
     }
     ArgmaxArgs aa{};
-    aa.logits = lg; aa.B = rows; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>() + (size_t)row0 * tcap; aa.out_ld = tcap;
+    aa.logits = lg; aa.partials = parts; aa.nparts = nparts; aa.B = rows; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>() + (size_t)row0 * tcap; aa.out_ld = tcap;
     aa.cur_tok = ds.cur_tok + row0; aa.step = step; aa.seen_eos = ds.seen + row0; aa.done_step = ds.done_step + branch;
     aa.block_counter = ds.block_counter + branch; aa.eos = eos;
     aa.tok_emb = h->tok_emb; aa.pos_emb = h->pos_emb; aa.emb_dt = h->dt; aa.emb_max_pos = tcap;
@@ -1097,7 +1113,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
     if (h->samp_temp > 0.0) {
         aa.topk = sampling_k(h); aa.inv_temp = (float)(1.0 / h->samp_temp); aa.seed = h->samp_seed; aa.row_base = row0; aa.call_ctr = ds.call_ctr;
     }
-    LAUNCH(KC_DEC_ARGMAX, 1, (double)rows * c.vocab_size * 4, 0.0, launch_argmax_step(aa, st));
+    LAUNCH(KC_DEC_ARGMAX, 1, fused_amax ? (double)rows * nparts * 8 : (double)rows * c.vocab_size * 4, 0.0, launch_argmax_step(aa, st));
     return 0;
 }
 
@@ -1257,14 +1273,15 @@ static int run_generate(texocr_handle* h, const int64_t* d_start, int eos, const
                launch_crosskv_head_major(h->crosskv.p, h->crosskv_hm.p, ntok, c.dec_layers, h->dt, st));
     }
     ENSURE(h->logits, (size_t)B * c.vocab_size * 4);
+    if (h->dt == DT_BF16 && h->use_tcgen05) ENSURE(h->amax_part, (size_t)B * ((c.vocab_size + 31) / 32) * 8);
     if (h->self_abs_active) ENSURE(h->latcache, (size_t)c.dec_layers * B * tcap * 256 * h->esz);
     else ENSURE(h->kvcache, (size_t)c.dec_layers * B * tcap * 1024 * h->esz);
     const void* kv_key = h->self_abs_active ? h->latcache.p : h->kvcache.p;
     ENSURE(h->dec_state, dec_state_bytes(B));
     ENSURE(h->out_ids, (size_t)B * tcap * 8);
     if (h->attn_trace_on) {
-        ENSURE(h->attn_trace, (size_t)MAX_BRANCH * 3 * 2048 * 8 + 128);
-        CK(cudaMemsetAsync((char*)h->attn_trace.p + (size_t)MAX_BRANCH * 3 * 2048 * 8, 0, 128, st));
+        ENSURE(h->attn_trace, (size_t)MAX_BRANCH * 3 * 2048 * 8 + 512);
+        CK(cudaMemsetAsync((char*)h->attn_trace.p + (size_t)MAX_BRANCH * 3 * 2048 * 8, 0, 512, st));
         for (int i = 0; i < MAX_BRANCH; ++i) {
             char* base = (char*)h->attn_trace.p + (size_t)i * 3 * 2048 * 8;
             CK(cudaMemsetAsync(base, 0xff, 2 * 2048 * 8, st));
@@ -1529,7 +1546,7 @@ void texocr_destroy(texocr_handle* h) {
                       &h->raw3, &h->rawDs, &h->gn_partial, &h->gn_stats[0], &h->gn_stats[1], &h->gn_stats[2], &h->gn_stats[3],
                       &h->proj_out, &h->patch_cols, &h->backbone_a, &h->col, &h->x, &h->s, &h->xn, &h->qkv, &h->o, &h->hid, &h->logits,
                       &h->enc_out, &h->enc_a, &h->crosskv, &h->crosskv_hm, &h->kvcache, &h->ids_stage, &h->mask_stage, &h->enc_stage, &h->tgt_stage,
-                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg, &h->attn_trace, &h->qabs, &h->cabs, &h->latcache, &h->prep_meta, &h->prep_in, &h->prep_out};
+                      &h->row_loss, &h->scalars, &h->dec_state, &h->out_ids, &h->mega_part, &h->mega_dbg, &h->attn_trace, &h->amax_part, &h->qabs, &h->cabs, &h->latcache, &h->prep_meta, &h->prep_in, &h->prep_out};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->h_geom) cudaFreeHost(h->h_geom);
     if (h->h_poll) cudaFreeHost(h->h_poll);

@@ -78,6 +78,7 @@ struct texocr_handle {
     DevBuf gn_partial, gn_stats[4];
     DevBuf proj_out, patch_cols, backbone_a, col;
     DevBuf x, s, xn, qkv, o, hid, logits;
+    DevBuf amax_part;                          // decode step, bf16 tier greedy: [B][ceil(V/32)] {max, index} partials of the vocabulary GEMM (no logits in HBM)
     DevBuf qabs, cabs;                         // absorbed cross-attention: queries / memory averages [rows, 8 x 256]
     DevBuf enc_out, enc_a, crosskv, crosskv_hm, kvcache;      // crosskv: GEMM output [tok][L*1024]; crosskv_hm: head-major copy for decoding
     DevBuf ids_stage, mask_stage, enc_stage, tgt_stage, row_loss, scalars;

@@ -27,7 +27,11 @@ enum GemmEpi {
     EPI_STORE = 0,      // C = A.W^T (+bias)                       out type = dt_c
     EPI_GLU_RES = 1,    // pairs (2j,2j+1): (a+ba)*sigmoid(g+bg) + res    -> float [M, N/2]
     EPI_GEGLU = 2,      // pairs (2j,2j+1): (a+ba)*gelu_erf(g+bg)         -> dt_a  [M, N/2]
-    EPI_BIAS_RES = 3    // acc + bias + res                                -> float [M, N]
+    EPI_BIAS_RES = 3,   // acc + bias + res                                -> float [M, N]
+    // tcgen05 path only, 32-column tiles: per row the (max, lowest index of the max) of acc + bias over the tile's columns
+    // -> {float max, int index} at C[row * ldc + tile] (8 bytes each; ldc = number of 32-column tiles).  The vocabulary
+    // projection of the decode step: the logits themselves are never stored (model/decoder.py:60,103)
+    EPI_ARGMAX = 4
 };
 
 struct ConvGather {      // implicit-GEMM view of a convolution over a ragged NHWC pixel batch
@@ -57,6 +61,9 @@ struct GemmArgs {
     // [64j, 64j+64) (W is [N, K]); A has N/64 * a_block_k columns.  0 = ordinary GEMM.  (per-head value projection of the absorbed
     // attention: C_h [256] -> 64 values with Wv_h)
     int a_block_k;
+    // debug (engine option attn_trace): per-CTA residency sums of the launch: [0] ns waiting for the predecessor grid,
+    // [1] ns from there to CTA exit, [2] CTAs.  null = off
+    unsigned long long* dbg;
 };
 cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 
@@ -112,6 +119,7 @@ cudaError_t launch_embed_ln(const int64_t* ids, const int* step, int T, int rows
                             int dt_a, cudaStream_t st);
 struct ArgmaxArgs {
     const float* logits; int B, V;
+    const float2* partials; int nparts;  // greedy only, non-null: per row `nparts` {max, index bits} partials of the logits (EPI_ARGMAX GEMM) instead of `logits`
     int64_t* out_ids; int out_ld;        // out_ids[b*out_ld + step]
     int64_t* cur_tok;                    // [B] next input token
     int* step;                           // device step counter (incremented by the last block)

@@ -190,12 +190,21 @@ __global__ void __launch_bounds__(256) argmax_step_kernel(ArgmaxArgs a) {
         }
         if (a.emb_x && t + 1 < a.emb_max_pos) embed_next(a, row, tok, t + 1, lane, egg, ebb);
     } else if (row < a.B) {
-        const float* l = a.logits + (size_t)row * a.V;
         float best = -INFINITY;
         int bi = 0x7fffffff;
-        for (int i = lane; i < a.V; i += 32) {
-            const float v = __ldcg(l + i);
-            if (v > best) { best = v; bi = i; }       // ascending scan: first maximum wins (torch argmax)
+        if (a.partials) {      // the vocabulary GEMM already reduced every 32-column tile to its (max, first index)
+            const float2* pp = a.partials + (size_t)row * a.nparts;
+            for (int i = lane; i < a.nparts; i += 32) {
+                const float2 v = __ldcg(pp + i);
+                const int vi = __float_as_int(v.y);
+                if (v.x > best || (v.x == best && vi < bi)) { best = v.x; bi = vi; }
+            }
+        } else {
+            const float* l = a.logits + (size_t)row * a.V;
+            for (int i = lane; i < a.V; i += 32) {
+                const float v = __ldcg(l + i);
+                if (v > best) { best = v; bi = i; }       // ascending scan: first maximum wins (torch argmax)
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

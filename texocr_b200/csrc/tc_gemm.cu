@@ -45,7 +45,9 @@ struct TcParams {
     int cv_cpk, cv_ksz, cv_stride, cv_lower, cv_Wo, cv_Ho;
     int stages;       // persistent kernel: ring stages actually used (<= SmemP::STAGES)
     int a_block_k;    // block-diagonal GEMM (one-tile-per-CTA kernel, BN = 64): n-tile j reads A columns from j * a_block_k
+    unsigned long long* dbg;      // debug residency sums (GemmArgs::dbg)
 };
+TX_DEVINL unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 TX_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -212,6 +214,8 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
     mbar_wait(tmem_full, parity);
     tcgen05_fence_after();
     if (nparts) mbar_wait_cluster(part_full, 0);                // split-K: the peers' partial tiles have landed in our shared memory
+    float am_best = -INFINITY;                                  // EPI_ARGMAX: running maximum of this thread's row over the tile
+    int am_idx = 0x7fffffff;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t raw[32];
@@ -244,6 +248,12 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
                     }
                 }
             }
+        }
+        if constexpr (EPI == EPI_ARGMAX) {                      // ascending scan, strict >: the first maximum wins (torch argmax)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < nvalid && v[i] > am_best) { am_best = v[i]; am_idx = n + i; }
+            continue;
         }
         float o[NOUT];
         if (PRE_RES) {
@@ -280,6 +290,10 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         stage_copy<RB, true>(stg, reinterpret_cast<uint8_t*>(reinterpret_cast<TO*>(p.C) + (size_t)mrow0 * p.ldc + ncol),
                              (size_t)p.ldc * sizeof(TO), lane, rows_ok, nvalid_out * (int)sizeof(TO));
         __syncwarp();
+    }
+    if constexpr (EPI == EPI_ARGMAX) {
+        if (lane < rows_ok)
+            reinterpret_cast<float2*>(p.C)[(size_t)(mrow0 + lane) * p.ldc + n0 / BN] = make_float2(am_best, __int_as_float(am_idx));
     }
 }
 
@@ -319,6 +333,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kb0 = kz * nkb;
 
     if (!p.late_trigger) pdl_launch_dependents();
+    unsigned long long dbg_t0 = 0ull, dbg_t1 = 0ull;
+    if (p.dbg && threadIdx.x == 0) dbg_t0 = gtime_ns();
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -348,6 +364,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (SPLIT == 3) tma_load_2d(&tmW2, &full[kb], st + S::NOPS * S::A_BYTES + S::W_BYTES, (kb0 + kb) * BK, n0);
             }
             pdl_wait();
+            if (p.dbg) dbg_t1 = gtime_ns();
             // convolution: base input pixel of the tile's first output pixel m0 = (n, oh, ow)
             int cv_w = 0, cv_h = 0, cv_n = 0;
             if (p.cv_cpk) {
@@ -422,6 +439,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (KS > 1 && !(kz > 0 && warp >= 2)) cluster_wait();         // pairs with the arrive above (peer epilogue warps waited already)
     tcgen05_fence_before();
     __syncthreads();
+    if (p.dbg && threadIdx.x == 0) {
+        const unsigned long long t2 = gtime_ns();
+        atomicAdd(p.dbg, dbg_t1 - dbg_t0); atomicAdd(p.dbg + 1, t2 - dbg_t1); atomicAdd(p.dbg + 2, 1ull);
+    }
     if (p.late_trigger) pdl_launch_dependents();
     if (warp == 1) {
         tcgen05_fence_after();
@@ -940,6 +961,9 @@ cudaError_t launch_epi(const GemmArgs& g, const CUtensorMap& a, const CUtensorMa
         case EPI_GLU_RES: return launch_cfg<BN, EPI_GLU_RES, float, SPLIT>(a, w, a2, w2, p, st);
         case EPI_GEGLU: return launch_cfg<BN, EPI_GEGLU, bf16, SPLIT>(a, w, a2, w2, p, st);
         case EPI_BIAS_RES: return launch_cfg<BN, EPI_BIAS_RES, float, SPLIT>(a, w, a2, w2, p, st);
+        case EPI_ARGMAX:
+            if constexpr (BN == 32 && SPLIT == 1) return launch_cfg2<32, EPI_ARGMAX, float, 1, 0>(a, w, a2, w2, p, st);
+            return cudaErrorInvalidValue;
     }
     return cudaErrorInvalidValue;
 }
@@ -996,6 +1020,7 @@ bool tc_gemm_supported(const GemmArgs& g) {
     if (g.K % BK != 0 || g.N % 8 != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0) return false;
     if (g.im2col.ksz > 0 && (g.im2col.C % BK != 0 || g.im2col.ksz > 7)) return false;
     if (((uintptr_t)g.A | (uintptr_t)g.W) & 15) return false;
+    if (g.epi == EPI_ARGMAX) return g.A2 == nullptr && g.im2col.ksz == 0 && !g.a_block_k && g.ldc >= (g.N + 31) / 32;
     if (g.epi == EPI_STORE) { if (g.ldc % 8 != 0) return false; }
     else if (g.ldc % 4 != 0) return false;
     if ((g.epi == EPI_GLU_RES || g.epi == EPI_BIAS_RES) && (!g.res || g.ldres % 4 != 0)) return false;
@@ -1015,8 +1040,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
         if (split || g.im2col.ksz > 0 || g.N % 64 != 0) return cudaErrorInvalidValue;
         bn = 64;
     }
+    if (g.epi == EPI_ARGMAX) bn = 32;      // the partial layout is defined on 32-column tiles
     TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1, 0, 0, 0, 0, 0, 0};
-    p.a_block_k = g.a_block_k;
+    p.a_block_k = g.a_block_k; p.dbg = g.dbg;
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
     const bool conv = g.im2col.ksz > 0;
