@@ -285,8 +285,12 @@ def test_absorbed_attention_matches_projected_kv(m16, m32):
     B, V = len(src), m16.dims.vocab
 
     def first_logits(model):
-        model.generate(src, 1)
-        return model.engine().debug_read("logits", B * V).reshape(B, V).cpu()
+        model.engine().set_option("keep_logits", 1)        # the greedy bf16 loop keeps no logits unless asked to (fused vocab GEMM + argmax)
+        try:
+            model.generate(src, 1)
+            return model.engine().debug_read("logits", B * V).reshape(B, V).cpu()
+        finally:
+            model.engine().set_option("keep_logits", 0)
 
     ref32 = first_logits(m32)
     modes = ((1, 1), (0, 0), (1, 0), (0, 1))          # (cross, self)
