@@ -68,7 +68,7 @@ TX_DEVINL int image_chunks(int npix, int nchunk) { return max(1, min(nchunk, (np
 // partial[b][chunk][32][2] (double) then stats[b][32] = (mean, rstd).  Fixed summation order.
 template <int C>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ raw, const int* __restrict__ img_off,
-                                                       int level, int nchunk, double* __restrict__ partial, int skip_le_pix) {
+                                                       int level, int nchunk, double* __restrict__ partial) {
     constexpr int C4 = C / 4;             // float4 columns
     constexpr int RPP = 256 / C4;         // rows per pass
     constexpr int CPG = C / 32;
@@ -77,7 +77,6 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int p0 = img_off[b] >> (2 * level), p1 = img_off[b + 1] >> (2 * level);
     const int npix = p1 - p0;
-    if (npix <= skip_le_pix) return;      // this image is normalised by gn_fused_kernel
     const int used = image_chunks(npix, nchunk);
     if (chunk >= used) return;
     const int per = (npix + used - 1) / used;
@@ -144,7 +143,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, const int*
     const int C = a.C, C4 = C / 4, cpg = C / 32;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int p0 = img_off[b] >> (2 * a.level), p1 = img_off[b + 1] >> (2 * a.level);
-    if (p1 - p0 <= a.skip_le_pix) return;      // this image is normalised by gn_fused_kernel
     const int used = image_chunks(p1 - p0, nchunk);
     if (chunk >= used) return;
     const int per = (p1 - p0 + used - 1) / used;
@@ -168,113 +166,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, const int*
     for (int p = lo + rl; p < hi; p += rpp) {
         const size_t o = (size_t)p * C + c;
         float4 v = ld4(a.raw + o);
-        float r[4] = {(v.x - mean[0]) * sc[0] + be[0], (v.y - mean[1]) * sc[1] + be[1],
-                      (v.z - mean[2]) * sc[2] + be[2], (v.w - mean[3]) * sc[3] + be[3]};
-        if (a.raw2) {
-            float4 u = ld4(a.raw2 + o);
-            r[0] += (u.x - mean2[0]) * sc2[0] + be2[0]; r[1] += (u.y - mean2[1]) * sc2[1] + be2[1];
-            r[2] += (u.z - mean2[2]) * sc2[2] + be2[2]; r[3] += (u.w - mean2[3]) * sc2[3] + be2[3];
-        }
-        if (a.res) {
-            float4 u = ld4(a.res + o);
-            r[0] += u.x; r[1] += u.y; r[2] += u.z; r[3] += u.w;
-        }
-        if (a.res_hi) {
-            float4 u = ld4(reinterpret_cast<const bf16*>(a.res_hi) + o), w = ld4(reinterpret_cast<const bf16*>(a.res_lo) + o);
-            r[0] += u.x + w.x; r[1] += u.y + w.y; r[2] += u.z + w.z; r[3] += u.w + w.w;
-        }
-        if (a.relu) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) r[i] = fmaxf(r[i], 0.f);
-        }
-        if (a.out) st4(a.out + o, make_float4(r[0], r[1], r[2], r[3]));
-        else store_split4(reinterpret_cast<bf16*>(a.out_hi) + o, reinterpret_cast<bf16*>(a.out_lo) + o, r);
-    }
-}
-
-// ------------------------------------------------------------------ GroupNorm in ONE pass over HBM (statistics + apply)
-// CTA = (image, block of 32 channels): the slab raw[pixels of the image][32 channels] (128 bytes per pixel) is pulled into
-// shared memory with cp.async (everything in flight at once), the group statistics are reduced from there in a fixed order
-// that depends on the image alone (bit-reproducible, batch-composition independent, fp32 per-thread partials over <= 50 rows,
-// then fp64), and the normalised / residual-added / ReLU'd rows are written straight from the slab: 4 B read + 4 B written
-// per activation instead of the 4 + 4 + 4 of the statistics pass followed by the apply pass.  Images whose slab does not
-// fit (more than `pix_cap` pixels at this level) are skipped here and take the two-pass kernels (skip_le_pix).
-constexpr int GF_CB = 32;                 // channels per slab: a multiple of every group size C/32 for C in 64 .. 1024
-TX_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__global__ void __launch_bounds__(256) gn_fused_kernel(GnApplyArgs a, const int* __restrict__ img_off, int pix_cap) {
-    extern __shared__ __align__(16) uint8_t gf_smem[];
-    const int C = a.C, cpg = C / 32;
-    const int b = blockIdx.y, cb0 = blockIdx.x * GF_CB;
-    const int p0 = img_off[b] >> (2 * a.level), p1 = img_off[b + 1] >> (2 * a.level);
-    const int npix = p1 - p0;
-    if (npix > pix_cap) return;
-    double* red_s = reinterpret_cast<double*>(gf_smem);          // [8 warps][32 channels]
-    double* red_q = red_s + 8 * GF_CB;
-    float* ch_mean = reinterpret_cast<float*>(red_q + 8 * GF_CB); // [32] per channel of the slab
-    float* ch_rstd = ch_mean + GF_CB;
-    float* slab = ch_rstd + GF_CB;                                // [npix][32]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* src = a.raw + (size_t)p0 * C + cb0;
-    for (int i = tid; i < npix * 8; i += 256) cp_async16(slab + (size_t)i * 4, src + (size_t)(i >> 3) * C + (i & 7) * 4);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // ---- statistics: thread = (float4 column c4, row lane rl); rows rl, rl + 32, ... in order
-    const int c4 = tid & 7, rl = tid >> 3;
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int p = rl; p < npix; p += 32) {
-        const float4 v = *reinterpret_cast<const float4*>(slab + (size_t)p * GF_CB + c4 * 4);
-        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-        q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
-    }
-    // the 4 row lanes of a warp that share a column: (r0 + r1) + (r2 + r3), the same in every lane
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        s[i] += __shfl_xor_sync(0xffffffffu, s[i], 8);  q[i] += __shfl_xor_sync(0xffffffffu, q[i], 8);
-        s[i] += __shfl_xor_sync(0xffffffffu, s[i], 16); q[i] += __shfl_xor_sync(0xffffffffu, q[i], 16);
-    }
-    if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { red_s[warp * GF_CB + c4 * 4 + i] = (double)s[i]; red_q[warp * GF_CB + c4 * 4 + i] = (double)q[i]; }
-    }
-    __syncthreads();
-    if (tid < GF_CB) {      // every channel of a group computes the group's statistics in the same order
-        const int g0 = (tid / cpg) * cpg;
-        double sa = 0.0, sq = 0.0;
-        for (int ch = g0; ch < g0 + cpg; ++ch)
-            for (int w = 0; w < 8; ++w) { sa += red_s[w * GF_CB + ch]; sq += red_q[w * GF_CB + ch]; }
-        const double n = (double)npix * cpg;
-        const double mean = sa / n;
-        double var = sq / n - mean * mean;       // biased variance (F.group_norm)
-        if (var < 0.0) var = 0.0;
-        ch_mean[tid] = (float)mean;
-        ch_rstd[tid] = (float)(1.0 / sqrt(var + 1e-5));
-        if (a.stats_out && tid == g0) {           // (mean, rstd) of the group, for a consumer that normalises this tensor again
-            a.stats_out[((size_t)b * 32 + (cb0 + g0) / cpg) * 2] = (float)mean;
-            a.stats_out[((size_t)b * 32 + (cb0 + g0) / cpg) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
-        }
-    }
-    __syncthreads();
-    // ---- apply, straight from the slab
-    const int c = cb0 + c4 * 4;
-    float mean[4], sc[4], be[4], mean2[4], sc2[4], be2[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        mean[i] = ch_mean[c4 * 4 + i];
-        sc[i] = ch_rstd[c4 * 4 + i] * a.gamma[c + i];
-        be[i] = a.beta[c + i];
-        if (a.raw2) {
-            const int gi = (c + i) / cpg;
-            mean2[i] = a.stats2[((size_t)b * 32 + gi) * 2];
-            sc2[i] = a.stats2[((size_t)b * 32 + gi) * 2 + 1] * a.gamma2[c + i];
-            be2[i] = a.beta2[c + i];
-        } else { mean2[i] = sc2[i] = be2[i] = 0.f; }
-    }
-    for (int p = rl; p < npix; p += 32) {
-        const size_t o = (size_t)(p0 + p) * C + c;
-        const float4 v = *reinterpret_cast<const float4*>(slab + (size_t)p * GF_CB + c4 * 4);
         float r[4] = {(v.x - mean[0]) * sc[0] + be[0], (v.y - mean[1]) * sc[1] + be[1],
                       (v.z - mean[2]) * sc[2] + be[2], (v.w - mean[3]) * sc[3] + be[3]};
         if (a.raw2) {
@@ -427,14 +318,14 @@ cudaError_t launch_stem_conv(const float* img, const float* w, float* raw1, cons
 }
 
 cudaError_t launch_gn_stats(const float* raw, int C, int level, const int* img_off, int nimg, int nchunk,
-                            double* partial, float* stats, cudaStream_t st, int skip_le_pix) {
+                            double* partial, float* stats, cudaStream_t st) {
     dim3 grid(nchunk, nimg);
     switch (C) {
-        case 64: gn_stats_kernel<64><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial, skip_le_pix); break;
-        case 128: gn_stats_kernel<128><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial, skip_le_pix); break;
-        case 256: gn_stats_kernel<256><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial, skip_le_pix); break;
-        case 512: gn_stats_kernel<512><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial, skip_le_pix); break;
-        case 1024: gn_stats_kernel<1024><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial, skip_le_pix); break;
+        case 64: gn_stats_kernel<64><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 128: gn_stats_kernel<128><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 256: gn_stats_kernel<256><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 512: gn_stats_kernel<512><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
+        case 1024: gn_stats_kernel<1024><<<grid, 256, 0, st>>>(raw, img_off, level, nchunk, partial); break;
         default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();
@@ -447,23 +338,6 @@ cudaError_t launch_gn_apply(const GnApplyArgs& a, const int* img_off, int nimg, 
     if (a.C % 4 != 0 || a.C / 4 > 256) return cudaErrorInvalidValue;
     dim3 grid(nchunk, nimg);
     gn_apply_kernel<<<grid, 256, 0, st>>>(a, img_off, nchunk);
-    return cudaGetLastError();
-}
-
-int gn_fused_pix_cap() { return 1600; }      // slab of 1600 pixels x 32 channels x 4 B = 200 KB (+ 5 KB of reduction space)
-
-cudaError_t launch_gn_fused(const GnApplyArgs& a, const int* img_off, int nimg, int max_pix, cudaStream_t st) {
-    if (a.C % GF_CB != 0 || max_pix <= 0 || max_pix > gn_fused_pix_cap()) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)2 * 8 * GF_CB * 8 + 2 * GF_CB * 4 + (size_t)max_pix * GF_CB * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        const size_t most = (size_t)2 * 8 * GF_CB * 8 + 2 * GF_CB * 4 + (size_t)gn_fused_pix_cap() * GF_CB * 4;
-        cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    dim3 grid(a.C / GF_CB, nimg);
-    gn_fused_kernel<<<grid, 256, smem, st>>>(a, img_off, gn_fused_pix_cap());
     return cudaGetLastError();
 }
 

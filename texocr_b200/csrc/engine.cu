@@ -683,33 +683,14 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
         LAUNCH(KC_CONV, 1, gemm_bytes(ga, 4), gemm_flops(ga), launch_gemm_tc(ga, st));
         return 0;
     };
-    auto gstats = [&](const float* raw, int C, int level, float* stt, int skip_le_pix = 0) -> int {
+    auto gstats = [&](const float* raw, int C, int level, float* stt) -> int {
         LAUNCH(KC_GN_STATS, 2, (double)g.P[level] * C * 4, 0.0,
-               launch_gn_stats(raw, C, level, g.d_img_off, B, nchunk_for(g.P[level], B), partial, stt, st, skip_le_pix));
+               launch_gn_stats(raw, C, level, g.d_img_off, B, nchunk_for(g.P[level], B), partial, stt, st));
         return 0;
     };
-    // which images can be normalised in one pass at each level (their 32-channel slabs fit in shared memory): a property of
-    // the image alone, so an image's result does not depend on what else is in the batch
-    const int cap = gn_fused_pix_cap();
-    int max_small[5] = {0, 0, 0, 0, 0};
-    bool any_big[5] = {false, false, false, false, false};
-    for (int b = 0; b < B; ++b)
-        for (int l = 1; l <= 4; ++l) {
-            const int npix = (g.img_off[b + 1] - g.img_off[b]) >> (2 * l);
-            if (npix <= cap) max_small[l] = std::max(max_small[l], npix); else any_big[l] = true;
-        }
-    // GroupNorm of a.raw (+ normalised / plain residual, ReLU) -> split-bf16 pair: one pass where the slab fits, else statistics + apply
-    auto gnorm = [&](GnApplyArgs& a, float* stt, Pair out, int level, double bytes_per) -> int {
-        a.out = nullptr; a.out_hi = out.hi; a.out_lo = out.lo; a.level = level; a.skip_le_pix = 0;
-        const bool fused = h->gn_fused && max_small[level] > 0;
-        if (fused)
-            LAUNCH(KC_GN_APPLY, 1, (double)g.P[level] * a.C * bytes_per, 0.0, launch_gn_fused(a, g.d_img_off, B, max_small[level], st));
-        if (!fused || any_big[level]) {
-            int r2;
-            if ((r2 = gstats(a.raw, a.C, level, stt, fused ? cap : 0))) return r2;
-            a.stats = stt; a.skip_le_pix = fused ? cap : 0;
-            LAUNCH(KC_GN_APPLY, 1, (double)g.P[level] * a.C * bytes_per, 0.0, launch_gn_apply(a, g.d_img_off, B, nchunk_for(g.P[level], B), st));
-        }
+    auto gapply = [&](GnApplyArgs& a, Pair out, int level, double bytes_per) -> int {
+        a.out = nullptr; a.out_hi = out.hi; a.out_lo = out.lo; a.level = level;
+        LAUNCH(KC_GN_APPLY, 1, (double)g.P[level] * a.C * bytes_per, 0.0, launch_gn_apply(a, g.d_img_off, B, nchunk_for(g.P[level], B), st));
         return 0;
     };
     int r;
@@ -726,27 +707,30 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
                 if ((r = gstats(h->rawDs.as<float>(), ds->cout, Lout, stats[3]))) return r;
             }
             if ((r = conv(c1, x, Lx, Lx, h->rawMid.as<float>()))) return r;
+            if ((r = gstats(h->rawMid.as<float>(), c1.cout, Lx, stats[0]))) return r;
             Pair m1 = pair_of(h->actMid, (size_t)g.P[Lx] * c1.cout);
             {
                 GnApplyArgs a{};
-                a.raw = h->rawMid.as<float>(); a.gamma = c1.gamma; a.beta = c1.beta; a.C = c1.cout; a.relu = 1;
-                if ((r = gnorm(a, stats[0], m1, Lx, 8))) return r;
+                a.raw = h->rawMid.as<float>(); a.stats = stats[0]; a.gamma = c1.gamma; a.beta = c1.beta; a.C = c1.cout; a.relu = 1;
+                if ((r = gapply(a, m1, Lx, 8))) return r;
             }
             if ((r = conv(c2, m1, Lx, Lout, h->rawMid2.as<float>()))) return r;
+            if ((r = gstats(h->rawMid2.as<float>(), c2.cout, Lout, stats[1]))) return r;
             Pair m2 = pair_of(h->actMid2, (size_t)g.P[Lout] * c2.cout);
             {
                 GnApplyArgs a{};
-                a.raw = h->rawMid2.as<float>(); a.gamma = c2.gamma; a.beta = c2.beta; a.C = c2.cout; a.relu = 1;
-                if ((r = gnorm(a, stats[1], m2, Lout, 8))) return r;
+                a.raw = h->rawMid2.as<float>(); a.stats = stats[1]; a.gamma = c2.gamma; a.beta = c2.beta; a.C = c2.cout; a.relu = 1;
+                if ((r = gapply(a, m2, Lout, 8))) return r;
             }
             if ((r = conv(c3, m2, Lout, Lout, h->raw3.as<float>()))) return r;
+            if ((r = gstats(h->raw3.as<float>(), c3.cout, Lout, stats[2]))) return r;
             Pair out = pair_of(*pingpong[pp], (size_t)g.P[Lout] * c3.cout);
             {
                 GnApplyArgs a{};
-                a.raw = h->raw3.as<float>(); a.gamma = c3.gamma; a.beta = c3.beta; a.C = c3.cout; a.relu = 1;
+                a.raw = h->raw3.as<float>(); a.stats = stats[2]; a.gamma = c3.gamma; a.beta = c3.beta; a.C = c3.cout; a.relu = 1;
                 if (ds) { a.raw2 = h->rawDs.as<float>(); a.stats2 = stats[3]; a.gamma2 = ds->gamma; a.beta2 = ds->beta; }
                 else { a.res_hi = x.hi; a.res_lo = x.lo; }
-                if ((r = gnorm(a, stats[2], out, Lout, 12))) return r;
+                if ((r = gapply(a, out, Lout, 12))) return r;
             }
             x = out; pp ^= 1; Lx = Lout;
         }
@@ -1918,7 +1902,6 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "fifo_pdl")) { h->fifo_pdl = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_full_tail")) { g_attn_full_tail = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "fuse_ln")) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
-    if (!strcmp(name, "gn_fused")) { h->gn_fused = value != 0; return 0; }
     if (!strcmp(name, "keep_logits")) { h->keep_logits = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "poison")) { h->poison = value != 0; return 0; }
     if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(8, value)); drop_graphs(h); return 0; }

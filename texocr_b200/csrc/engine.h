@@ -121,7 +121,6 @@ struct texocr_handle {
     double prof_ms[KC_COUNT] = {0}; double prof_bytes[KC_COUNT] = {0}; double prof_flops[KC_COUNT] = {0};
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
-    bool gn_fused = true;         // bf16 tier: GroupNorm statistics + apply in one pass over HBM where an image's 32-channel slab fits in shared memory
     bool use_im2col_tma = true;   // bf16 tier, same-size batches: 3x3 / strided convolutions as implicit GEMMs (TMA im2col loads)
     int decode_mega = 0;      // bf16 tier: 1 = experimental cluster-persistent decode kernel (decode_mega.cu), 0 = per-branch kernel graphs.
                               // Token-identical to the branch path but ~1.8x slower at B = 512 (issue-bound at 8 warps per SM)

@@ -70,9 +70,8 @@ cudaError_t launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 // ---- backbone pieces (conv_gn.cu)
 cudaError_t launch_stem_conv(const float* img, const float* w /*[49][64] std*/, float* raw1, const int* img_off,
                              const int* img_hw, int nimg, int total_p1, cudaStream_t st);
-// skip_le_pix: images with at most this many pixels at `level` are left out (they are normalised by launch_gn_fused)
 cudaError_t launch_gn_stats(const float* raw, int C, int level, const int* img_off, int nimg, int nchunk,
-                            double* partial, float* stats, cudaStream_t st, int skip_le_pix = 0);
+                            double* partial, float* stats, cudaStream_t st);
 struct GnApplyArgs {
     const float* raw; const float* stats; const float* gamma; const float* beta;       // main input
     const float* raw2; const float* stats2; const float* gamma2; const float* beta2;   // optional normalised residual
@@ -81,13 +80,7 @@ struct GnApplyArgs {
     float* out;                                                                          // fp32 output, or
     void* out_hi; void* out_lo;                                                          // split-bf16 pair: v = hi + lo
     int C, level, relu;
-    int skip_le_pix;                                                                     // two-pass apply: leave out images of at most this many pixels
-    float* stats_out;                                                                    // one-pass kernel: optional (mean, rstd) [B][32][2] of the main input
 };
-// GroupNorm statistics + apply in one pass over HBM for the images of at most gn_fused_pix_cap() pixels at a.level (the
-// image's 32-channel slabs are held in shared memory); a.stats is not read.  max_pix = the largest such image of the batch.
-int gn_fused_pix_cap();
-cudaError_t launch_gn_fused(const GnApplyArgs& a, const int* img_off, int nimg, int max_pix, cudaStream_t st);
 cudaError_t launch_gn_apply(const GnApplyArgs& a, const int* img_off, int nimg, int nchunk, cudaStream_t st);
 // out2 (fp32) or the split-bf16 pair (out_hi, out_lo)
 cudaError_t launch_gn_apply_maxpool(const float* raw1, const float* stats, const float* gamma, const float* beta,
