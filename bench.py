@@ -245,6 +245,31 @@ def measure_next_rows(model, img_dev, peaks, stream):
     return out
 
 
+def job_plan(total: int, batch: int, rank: int, world: int):
+    """Strong-scaling job (BASELINE configs[4]): `total` equations = ceil(total / batch) batches with FIXED boundaries, dealt to the
+    ranks as contiguous runs of whole batches, so every batch is decoded by the same kernels on the same rows whatever the
+    world size.  Returns the list of global batch indices of this rank."""
+    n_batches = (total + batch - 1) // batch
+    lo, hi = shard_range(n_batches, rank, world)
+    return list(range(lo, hi))
+
+
+BATCH_SEEDS = 8      # distinct synthetic batches of a strong-scaling job: global batch j holds the images of seed 1234 + j % BATCH_SEEDS
+
+
+def class_table(rows, peaks):
+    """Per kernel class of one eagerly launched batch: time, achieved GB/s and TFLOP/s on the engine's algorithmic bytes / FLOPs
+    (DESIGN.md section 5), against both measured peaks."""
+    out = {}
+    for r in sorted(rows, key=lambda r: -r["ms"]):
+        sec = r["ms"] / 1e3
+        gbs, tf = r["bytes"] / sec / 1e9, r["flops"] / sec / 1e12
+        out[r["name"]] = {"ms": round(r["ms"], 4), "launches": int(r["launches"]), "avg_us": round(r["ms"] * 1e3 / max(1, r["launches"]), 3),
+                          "gbs": round(gbs, 1), "frac_hbm": round(gbs / peaks["hbm_gbs"], 4),
+                          "tflops": round(tf, 2), "frac_tensor": round(tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), 4)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,8 +280,12 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--in-flight", type=int, default=6, help="batches decoded concurrently per GPU (1 = one at a time)")
     ap.add_argument("--branches", type=int, default=1, help="decode branches per batch when several batches are in flight")
+    ap.add_argument("--total", type=int, default=0, help="strong scaling (BASELINE configs[4]): a fixed job of this many equations in "
+                    "batches of --batch, contiguous runs of batches per rank; --steps is then the number of batches per rank")
+    ap.add_argument("--verify", action="store_true", help="rank 0 re-decodes another rank's batch and checks the gathered block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the roofline / encoder / next-rows measurements after the timed region")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -286,17 +315,32 @@ def main():
     model.eval()
     eng = model.engine()
     B = args.batch
-    lo, hi = shard_range(B * world, rank, world)                    # this rank's contiguous shard of the job's image list
-    img_host = synth.synth_images(hi - lo, H, W, seed=1234 + rank).pin_memory()
-    img_dev = img_host.cuda()
-    out_host = torch.empty((hi - lo, MAX_LEN), dtype=torch.int64).pin_memory()
+    strong = args.total > 0
+    if strong:
+        my_batches = job_plan(args.total, B, rank, world)
+        n_max = len(job_plan(args.total, B, 0, world))              # rank 0 holds the longest run; shorter ranks pad with repeats
+        args.steps = n_max
+        seeds = [1234 + (j % BATCH_SEEDS) for j in my_batches] + [1234] * (n_max - len(my_batches))
+        pool = {sd_: synth.synth_images(B, H, W, seed=sd_).pin_memory() for sd_ in sorted(set(seeds))}
+        host_batches = [pool[sd_] for sd_ in seeds]
+    else:
+        lo, hi = shard_range(B * world, rank, world)                # this rank's contiguous shard of the job's image list
+        host_batches = [synth.synth_images(hi - lo, H, W, seed=1234 + rank).pin_memory()] * args.steps
+    dev_pool = {}
+    for hb in host_batches:
+        if hb.data_ptr() not in dev_pool:
+            dev_pool[hb.data_ptr()] = hb.cuda()
+    dev_batches = [dev_pool[hb.data_ptr()] for hb in host_batches]
+    img_host, img_dev = host_batches[0], dev_batches[0]
+    rows_per_batch = img_host.shape[0]
+    out_host = torch.empty((rows_per_batch, MAX_LEN), dtype=torch.int64).pin_memory()
     stream = torch.cuda.current_stream()
     n_fly = max(1, min(args.in_flight, args.steps))
     pipe = None
     if n_fly > 1:
         from texocr_b200.pipeline import GeneratePipeline
         pipe = GeneratePipeline(model, in_flight=n_fly, branches=args.branches)
-        outs_host = [torch.empty((hi - lo, MAX_LEN), dtype=torch.int64).pin_memory() for _ in range(args.steps)]
+        outs_host = [torch.empty((rows_per_batch, MAX_LEN), dtype=torch.int64).pin_memory() for _ in range(args.steps)]
 
     def barrier():
         if dist is not None:
@@ -310,8 +354,8 @@ def main():
         if whole:
             fn(steps)          # runs all `steps` batches (several in flight); returns after the last one has completed
         else:
-            for _ in range(steps):
-                fn()
+            for i in range(steps):
+                fn(i)
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -319,27 +363,28 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def step_device():
-        tok = model.generate(img_dev, max_len=MAX_LEN)             # public API; inputs resident in HBM
-        return gather_tokens(tok, world)
+    gathered = {}              # step -> (world * rows, MAX_LEN) token ids of the last timed pass (kept for --verify)
 
-    def step_e2e():
-        tok = eng.generate(img_host, MAX_LEN, out=out_host)         # C-ABI with HOST buffers: H2D + D2H inside the call
+    def step_device(i=0):
+        tok = model.generate(dev_batches[i % len(dev_batches)], max_len=MAX_LEN)             # public API; inputs resident in HBM
+        gathered[i] = gather_tokens(tok, world)
+
+    def step_e2e(i=0):
+        tok = eng.generate(host_batches[i % len(host_batches)], MAX_LEN, out=out_host)         # C-ABI with HOST buffers: H2D + D2H inside the call
         if world > 1:
             gather_tokens(tok.cuda(non_blocking=True), world)
-        return tok
 
     def steps_device(k):       # k batches resident in HBM through the pipeline (public API: GeneratePipeline.generate_batches)
-        for tok in pipe.generate_batches([img_dev] * k, MAX_LEN):
-            gather_tokens(tok, world)
+        for i, tok in enumerate(pipe.generate_batches(dev_batches[:k], MAX_LEN)):
+            gathered[i] = gather_tokens(tok, world)
 
     def steps_e2e(k):          # k batches from pinned HOST memory, token ids back to pinned host memory
-        for tok in pipe.generate_batches([img_host] * k, MAX_LEN, outs=outs_host[:k]):
+        for tok in pipe.generate_batches(host_batches[:k], MAX_LEN, outs=outs_host[:k]):
             if world > 1:
                 gather_tokens(tok.cuda(non_blocking=True), world)
 
-    for _ in range(args.warmup):
-        step_device()
+    for i in range(args.warmup):
+        step_device(i)
     if pipe is not None:
         pipe.warm_up(img_dev, MAX_LEN)
         for _ in range(args.warmup):
@@ -357,11 +402,37 @@ def main():
         l0 = pipe.kernel_launches()
         ms = timed(steps_device, args.steps, whole=True)
         launches = pipe.kernel_launches() - l0
-        ms_1 = timed(step_device, args.steps)
-        serial = {"value": world * B * args.steps / (ms_1 / 1e3), "unit": UNIT, "ms_per_step": ms_1 / args.steps,
-                  "note": "the same K batches, one model.generate call at a time (6 decode branches per batch)"}
+        if not strong:
+            ms_1 = timed(step_device, min(args.steps, 6))
+            serial = {"value": world * B * min(args.steps, 6) / (ms_1 / 1e3), "unit": UNIT, "ms_per_step": ms_1 / min(args.steps, 6),
+                      "note": "the same batches, one model.generate call at a time (6 decode branches per batch): what a caller of the "
+                              "reference's own loop (test.py:27-40) gets without the pipeline"}
     clk = clocks.stop()
-    value = world * B * args.steps / (ms / 1e3)
+    done_eq = sum(len(job_plan(args.total, B, r, world)) for r in range(world)) * B if strong else world * B * args.steps
+    value = done_eq / (ms / 1e3)
+
+    # ---- --verify: the gathered block of another rank equals a re-decode of that rank's images on THIS GPU (the
+    # N-GPU result must equal the 1-GPU result for the same images bit for bit)
+    verify = None
+    if args.verify:
+        if pipe is not None:
+            steps_device(min(args.steps, n_fly))       # refresh `gathered` from a pass whose blocks are all kept
+        else:
+            step_device(0)
+        if rank == 0:
+            peer = world - 1
+            if strong:
+                peer_batches = job_plan(args.total, B, peer, world)
+                seed = 1234 + (peer_batches[0] % BATCH_SEEDS)
+            else:
+                seed = 1234 + peer
+            again = model.generate(synth.synth_images(rows_per_batch, H, W, seed=seed).cuda(), max_len=MAX_LEN)
+            block = gathered[0][peer * rows_per_batch:(peer + 1) * rows_per_batch]
+            same = bool(torch.equal(again, block))
+            verify = {"ok": same, "peer_rank": peer, "rows": rows_per_batch,
+                      "what": "rank 0 re-decoded the first batch of the peer rank from the same seed and compared it with the block the all_gather delivered"}
+            if not same:
+                raise SystemExit("verify failed: gathered block differs from the re-decode: " + json.dumps(verify))
 
     e2e = None
     if not args.no_e2e:
@@ -371,19 +442,19 @@ def main():
         else:
             steps_e2e(n_fly)
             ms_e = timed(steps_e2e, args.steps, whole=True)
-        e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": UNIT,
+        e2e = {"value": done_eq / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(img_host.numel() * 4 * world), "d2h_bytes_per_step": int(out_host.numel() * 8 * world)}
     if pipe is not None:
         pipe.close()
 
-    # ---- roofline of the dominant kernel.  One extra step is launched eagerly (no CUDA graph, one decode branch so that every
-    # kernel sees the full batch) with CUDA events around every launch on the launching stream (texocr_profile_*); the
-    # engine accounts algorithmic bytes / FLOPs per launch with the formulas of DESIGN.md section 5.  The decode attention
-    # kernel (attn_decode_tma_kernel: self + cross instantiations) is the dominant kernel of the step (ncu launch list in
-    # profiles/); the small GEMM / LayerNorm kernels are launch-latency bound and listed in kernel_time_shares.
+    # ---- rooflines.  One extra batch is launched eagerly (no CUDA graph, one decode branch, nothing else on the GPU) with CUDA
+    # events around every launch on the launching stream (texocr_profile_*); the engine accounts algorithmic bytes / FLOPs per
+    # launch.  `roofline` = the kernel with the largest share of that batch's kernel time;
+    # `roofline_by_class` = every class against both measured peaks; `roofline_attention` = the HBM-bound decode attention in detail.
     peaks, peaks_src = load_peaks()
-    roofline, shares = None, None
-    if rank == 0:
+    roofline = roofline_attn = by_class = shares = job = None
+    encoder = next_rows = None
+    if rank == 0 and not args.no_extras:
         eng.set_option("decode_branches", 1)
         eng.set_option("attn_trace", 1)            # in-kernel %globaltimer phase sums of the attention kernel (see below)
         eng.profile_enable(True)
@@ -392,7 +463,7 @@ def main():
         eng.profile_enable(False)
         phases, window_s = None, None
         try:
-            allraw = eng.debug_read("attn_trace", 16 * 3 * 2048 * 2 + 32).view(torch.int64).cpu()
+            allraw = eng.debug_read("attn_trace", 16 * 3 * 2048 * 2 + 128).view(torch.int64).cpu()
             tr = allraw[:3 * 2048].reshape(3, 256, 8).double()          # branch 0: entry (min over CTAs), ready (min), end (max)
             ok = tr[2] > 0
             window_s = float(((tr[2] - tr[1]) * ok).sum()) * 1e-9         # launch-wide: first CTA past its dependency -> last CTA done
@@ -406,77 +477,103 @@ def main():
         eng.set_option("decode_branches", 0)
         tot = sum(r["ms"] for r in rows) or 1.0
         shares = {r["name"]: round(r["ms"] / tot, 4) for r in sorted(rows, key=lambda r: -r["ms"])}
+        by_class = class_table(rows, peaks)
+        traffic_db = {}
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic_db = json.load(open(tp))
+            except Exception:
+                traffic_db = {}
+        kernel_of = {"dec_gemm_q": "tc_gemm_kernel<64, EPI_STORE, bf16> (absorbed query projection, N = 2048, K = 256; 8 launches per decode step)",
+                     "dec_gemm_wo": "tc_gemm_kernel<32, EPI_GLU_RES, float> (attention out-projection + GLU + residual, K = 512; 8 per step)",
+                     "dec_gemm_w1": "tc_gemm_kernel<64, EPI_GEGLU, bf16> (MLP in + GeGLU, N = 2048; 4 per step)",
+                     "dec_gemm_w2": "tc_gemm_kernel<32, EPI_BIAS_RES, float> (MLP out + residual, K = 1024; 4 per step)",
+                     "dec_gemm_vproj": "tc_gemm_kernel<64, EPI_STORE, bf16> block-diagonal (per-head value projection; 8 per step)",
+                     "dec_attn_self": "attn_abs_kernel<self> (absorbed decode self-attention; 4 per step)",
+                     "dec_attn_cross": "attn_abs_kernel<cross> (absorbed decode cross-attention; 4 per step)",
+                     "conv_gemm": "tc_gemm_persistent_kernel<128, EPI_STORE, float, bf16x3> (backbone convolutions)",
+                     "gn_apply": "gn_apply_kernel (GroupNorm apply + residual + ReLU, split-bf16 out)"}
+        top = max(rows, key=lambda r: r["ms"])
+        tc = by_class[top["name"]]
+        tensor_bound = top["flops"] > 0 and top["name"] not in HBM_CLASSES
+        t_key = {"dec_gemm_q": "tc_gemm_kernel_64_store_bf16", "dec_attn_self": "attn_abs_kernel", "dec_attn_cross": "attn_abs_kernel"}.get(top["name"])
+        ratio = (traffic_db.get(t_key) or {}).get("dram_bytes_over_algorithmic") if t_key else None
+        roofline = {"bound": "tensor" if tensor_bound else "hbm", "kernel": kernel_of.get(top["name"], top["name"]), "class": top["name"],
+                    "achieved": tc["tflops"] if tensor_bound else tc["gbs"],
+                    "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) if tensor_bound else peaks["hbm_gbs"],
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                    "frac": tc["frac_tensor"] if tensor_bound else tc["frac_hbm"],
+                    "traffic": (ratio * top["bytes"] / max(1, top["launches"])) if ratio else None,
+                    "peak_source": (peaks_src + " (MEASURED_PEAKS.json, sustained bf16 / hbm_gbs)") if peaks_src == "measured" else "fallback",
+                    "launches": int(top["launches"]), "avg_us": tc["avg_us"], "share_of_batch_kernel_time": shares[top["name"]],
+                    "algorithmic_flops_per_launch": top["flops"] / max(1, top["launches"]),
+                    "algorithmic_bytes_per_launch": top["bytes"] / max(1, top["launches"]),
+                    "also_gbs": tc["gbs"], "also_frac_hbm": tc["frac_hbm"],
+                    "method": "CUDA events around every launch of one eagerly launched batch (single branch, nothing else resident); the "
+                              "kernel is one 128 x BN tile per CTA: TMA -> 16 tcgen05.mma -> TMEM -> store, 4-6 us of dependent latency "
+                              "per launch, so its tensor-pipe fraction is small by construction (profiles/r02_*; DESIGN.md section 5)"}
         attn = [r for r in rows if r["name"] in ("dec_attn_self", "dec_attn_cross")]
         a_ms = sum(r["ms"] for r in attn)
         a_bytes = sum(r["bytes"] for r in attn)
         a_n = sum(r["launches"] for r in attn)
-        ach = a_bytes / (a_ms / 1e3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            try:
-                tj = json.load(open(tp))
-                ratio = (tj.get("attn_abs_kernel") or tj.get("attn_decode_tma_kernel", {})).get("dram_bytes_over_algorithmic")
-                traffic = ratio * a_bytes / a_n if ratio else None
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": "attn_abs_kernel<self> + attn_abs_kernel<cross> (absorbed decode attention, 8 launches per decode step)",
-                    "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": traffic, "peak_source": peaks_src + " (MEASURED_PEAKS.json hbm_gbs)" if peaks_src == "measured" else "fallback",
-                    "launches": a_n, "avg_us": a_ms * 1e3 / max(1, a_n), "algorithmic_bytes_per_launch": a_bytes / max(1, a_n),
-                    "share_of_step_kernel_time": round(a_ms / tot, 4)}
-        # the same launches on SURVEY section 8d's per-key figure (projected K/V, 2,048 B per key and layer): the absorbed kernel
-        # moves a quarter of those bytes, so this "effective" rate may exceed the HBM peak
-        surv = ach * (4.0 if args.precision == "bf16" else 1.0)
-        roofline["achieved_on_survey_bytes"] = surv
-        roofline["on_survey_bytes"] = {"achieved": surv, "unit": "GB/s", "frac": surv / peaks["hbm_gbs"],
-                                       "note": "SURVEY.md 8d counts 2,048 B per key and layer (projected K/V); achieved / frac above use the 512 B "
-                                               "this formulation actually has to move (conservative); `traffic` is measured DRAM bytes per launch"}
-        if phases and args.precision == "bf16":
-            # what the kernel does while it streams: mean time a CTA spends in its stage loop (all CTAs of a launch run side by
-            # side, one sequence each), against the same algorithmic bytes -- the launch-level figure above adds launch,
-            # first-stage latency, epilogue and tail of a ~9 us CTA lifetime
-            by = {r["name"]: r for r in attn}
-            loop_s = sum(by[n]["launches"] * phases[k]["stage_loop_us"] * 1e-6 for n, k in (("dec_attn_self", "self"), ("dec_attn_cross", "cross")) if n in by)
-            if loop_s > 0 and window_s:
-                roofline["in_kernel"] = {"achieved": a_bytes / window_s / 1e9, "unit": "GB/s", "frac": a_bytes / window_s / 1e9 / peaks["hbm_gbs"],
-                                         "method": "%globaltimer, per launch: first CTA released by its dependency -> last CTA finished (engine option "
-                                                   "attn_trace); excludes launch latency and the CUDA-event overhead of the figure above",
-                                         "mean_cta_phases_us": phases,
-                                         "mean_cta_stage_loop_gbs": a_bytes / loop_s / 1e9}
-        # whole-step view against the HBM roofline of SURVEY.md section 8d (bf16 KV cache bytes + per-step weights)
+        if a_n:
+            ach = a_bytes / (a_ms / 1e3) / 1e9
+            ratio = (traffic_db.get("attn_abs_kernel") or {}).get("dram_bytes_over_algorithmic")
+            roofline_attn = {"bound": "hbm", "kernel": "attn_abs_kernel<self> + attn_abs_kernel<cross> (absorbed decode attention, 8 launches per decode step)",
+                             "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                             "traffic": ratio * a_bytes / a_n if ratio else None, "launches": a_n, "avg_us": a_ms * 1e3 / a_n,
+                             "algorithmic_bytes_per_launch": a_bytes / a_n, "share_of_batch_kernel_time": round(a_ms / tot, 4),
+                             "bytes_basis": "512 B per key and layer (the 256-wide bf16 latent row all 8 heads share); SURVEY.md 8d counts "
+                                            "2,048 B per key and layer for projected K/V -- this formulation moves a quarter of that"}
+            if phases and args.precision == "bf16" and window_s:
+                by = {r["name"]: r for r in attn}
+                loop_s = sum(by[n]["launches"] * phases[k]["stage_loop_us"] * 1e-6 for n, k in (("dec_attn_self", "self"), ("dec_attn_cross", "cross")) if n in by)
+                roofline_attn["in_kernel"] = {"achieved": a_bytes / window_s / 1e9, "unit": "GB/s", "frac": a_bytes / window_s / 1e9 / peaks["hbm_gbs"],
+                                              "method": "%globaltimer, per launch: first CTA released by its dependency -> last CTA finished (engine option attn_trace)",
+                                              "mean_cta_phases_us": phases,
+                                              "mean_cta_stage_loop_gbs": a_bytes / loop_s / 1e9 if loop_s > 0 else None}
+        # ---- the whole job against the HBM roofline: bytes this implementation has to move per batch (absorbed attention: 2,048 B per
+        # cached position / memory token and step = 4 layers x 512 B; weights once per step) and SURVEY.md 8d's bytes for the same work
         s_tok = synth.encoder_tokens(H, W)
-        esz = 2 if args.precision == "bf16" else 4
-        # SURVEY's accounting (projected cross K/V re-read every step) and what this implementation actually has to move
-        # (bf16 tier: absorbed cross-attention streams the [S,256] memory, 2,048 instead of 8,192 B per memory token and step)
-        step_bytes_ref = sum(synth.decode_step_bytes(B, t, s_tok) for t in range(1, MAX_LEN + 1)) * (esz / 2)
-        mem_row = 2048 if args.precision == "bf16" else 8192
-        step_bytes = sum(synth.decode_step_bytes(B, t, s_tok, mem_row=mem_row) for t in range(1, MAX_LEN + 1)) * (esz / 2)
-        roofline["job_decode_bytes_per_step_survey"] = step_bytes_ref
-        roofline["job_decode_bytes_per_step"] = step_bytes
-        roofline["job_hbm_frac"] = (step_bytes * args.steps / (ms / 1e3) / 1e9) / peaks["hbm_gbs"]
-        # secondary metric of BASELINE.json: encoder img/s (configs[1]: 256 mixed-width images, ragged batch)
+        absorbed = args.precision == "bf16"
+        row_b = 2048 if absorbed else 16384
+        # per-step decoder weights of the absorbed formulation: per layer 2 x Wqk [2048,256] + 2 x Wv [512,256] + 2 x Wo [512,512] + W1 + W2
+        w_step = (4 * 2621440 + 257000 + 1024) * 2 if absorbed else 15222736 * 2
+        moved = sum(synth.decode_step_bytes(B, t, s_tok, w_step=w_step, kv_row=row_b, mem_row=row_b) for t in range(1, MAX_LEN + 1))
+        survey = sum(synth.decode_step_bytes(B, t, s_tok) for t in range(1, MAX_LEN + 1)) * (1.0 if absorbed else 2.0)
+        sec_per_batch = ms / 1e3 / args.steps
+        job = {"decode_bytes_moved_per_batch": moved, "decode_bytes_survey_per_batch": survey,
+               "hbm_frac_bytes_moved": moved / sec_per_batch / 1e9 / peaks["hbm_gbs"],
+               "hbm_frac_survey_effective": survey / sec_per_batch / 1e9 / peaks["hbm_gbs"],
+               "note": "bytes_moved = what the decode loop of this formulation reads per batch (latent rows + per-step weights); "
+                       "survey_effective divides SURVEY.md 8d's projected-K/V bytes by the same time: an algorithmic saving, not HBM utilisation. "
+                       "Both use the whole step time, encoder included"}
+        # secondary metric of BASELINE.json: encoder img/s -- configs[1] (256 mixed-width images, one ragged batch) and the headline's own batch
+        def enc_rate(batch, n_img, flops):
+            for _ in range(2):
+                model.encoder(batch)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                model.encoder(batch)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t_ms = e0.elapsed_time(e1) / 3
+            tf = flops / (t_ms / 1e3) / 1e12
+            return {"value": n_img / (t_ms / 1e3), "unit": "images/s", "ms": t_ms, "algorithmic_tflops": tf,
+                    "frac_of_bf16_peak": tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])}
         widths = synth.synth_widths(256, seed=77)
         rag = [synth.synth_images(1, H, w, seed=500 + i)[0].cuda() for i, w in enumerate(widths)]
-        for _ in range(2):
-            model.encoder(rag)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(3):
-            model.encoder(rag)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        enc_ms = e0.elapsed_time(e1) / 3
-        enc_flops = sum(synth.encoder_flops(H, w) for w in widths)
-        encoder = {"metric": "encoder img/s", "value": 256 / (enc_ms / 1e3), "ms": enc_ms,
-                   "workload": "BASELINE configs[1]: 256 images, H=64, widths 128..1008 (multiples of 16), one ragged batch",
-                   "algorithmic_tflops": enc_flops / (enc_ms / 1e3) / 1e12,
-                   "frac_of_bf16_peak": enc_flops / (enc_ms / 1e3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])}
+        encoder = {"metric": "encoder img/s",
+                   "config2_ragged": dict(enc_rate(rag, 256, sum(synth.encoder_flops(H, w) for w in widths)),
+                                          workload="BASELINE configs[1]: 256 images, H=64, widths 128..1008 (multiples of 16), one ragged batch"),
+                   "uniform": dict(enc_rate(img_dev, rows_per_batch, synth.encoder_flops(H, W) * rows_per_batch),
+                                   workload=f"{rows_per_batch} images {H}x{W} (the headline batch)"),
+                   "note": "frac_of_bf16_peak is on ALGORITHMIC FLOPs; the backbone issues 3 MMAs per product (bf16x3), ceiling 0.41 (SURVEY.md 8d)"}
+        encoder["value"] = encoder["config2_ragged"]["value"]
         next_rows = measure_next_rows(model, img_dev, peaks, stream)
-    else:
-        encoder = None
-        next_rows = None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -489,18 +586,23 @@ def main():
         dist.destroy_process_group()
     if rank != 0:
         return
+    workload = (f"BASELINE configs[4]: data-parallel sweep of {args.total} synthetic equations in batches of {B} (fixed batch boundaries, "
+                f"contiguous runs of batches per rank), " if strong else "BASELINE configs[2]: ") + \
+               (f"full greedy generate with KV cache, batch {B} per GPU, {H}x{W} images, max_len {MAX_LEN}, default config.yml model "
+                f"(ResNetV2-hybrid ViT encoder + 4-layer decoder), random-init weights")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[2]: full greedy generate with KV cache, batch {B} per GPU, {H}x{W} images, "
-                               f"max_len {MAX_LEN}, default config.yml model (ResNetV2-hybrid ViT encoder + 4-layer decoder), random-init weights",
+        "config": {"workload": workload,
                    "batch_per_gpu": B, "max_len": MAX_LEN, "image": [H, W], "precision": args.precision,
                    "parallelism": f"dp{world} (independent shards, token-id all_gather)",
                    "batches_in_flight": n_fly, "decode_branches_per_batch": args.branches if n_fly > 1 else 6,
+                   "total_equations": done_eq if strong else None,
                    "l2_policy": "working set per batch in flight (0.25 GB latent attention cache + 0.2 GB encoder memory / decode buffers + >= 3 GB encoder activations) exceeds the 126 MB L2 many times over; no explicit flush"},
-        "e2e": e2e, "one_batch_at_a_time": serial, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "kernel_time_shares": shares,
-        "cpu_baseline": cpu_baseline, "encoder": encoder, "next_rows": next_rows,
+        "e2e": e2e, "one_batch_at_a_time": serial, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,
+        "roofline_by_class": by_class, "roofline_attention": roofline_attn, "job_hbm": job, "kernel_time_shares": shares,
+        "cpu_baseline": cpu_baseline, "encoder": encoder, "next_rows": next_rows, "verify": verify,
     }
     print(json.dumps(line), flush=True)
 

@@ -192,3 +192,35 @@ def test_fused_vocab_argmax_equals_logits_path(m16):
     finally:
         eng.set_option("keep_logits", 0)
     assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_one_large_generate_call_equals_sub_batch_calls(m16):
+    """model.generate with B >= 1024 decodes 512-row sub-batches concurrently on internal engine replicas: same tokens as
+    separate 512-row calls, and the reference's width contract when one sub-batch reaches its all-EOS step before another."""
+    img = synth.synth_images(1100, 32, 128, seed=61).cuda()
+    ref = torch.cat([m16.generate(c, 24) for c in torch.split(img, 512)], 0)
+    out = m16.generate(img, 24)
+    assert out.shape == (1100, 24) and torch.equal(out, ref)
+    # early exit: the whole batch stops at the step where its LAST row has produced the EOS
+    old_eos = m16.dims.eos
+    full = ref
+    import dataclasses
+    cand = None
+    for t in full[0, :20].tolist():                      # a token every row emits early becomes the EOS
+        hit = (full == t)
+        if bool(hit.any(1).all()):
+            steps = hit.float().argmax(1) + 1
+            per_chunk = [int(s.max()) for s in torch.split(steps, 512)]
+            if len(set(per_chunk)) > 1:
+                cand = (t, max(per_chunk))
+                break
+    if cand is None:
+        pytest.skip("no token reaches every row at different steps per sub-batch in this sample")
+    try:
+        m16.dims = dataclasses.replace(m16.dims, eos=cand[0])      # engine and replicas are rebuilt for the new EOS id
+        m16.eos_token = cand[0]
+        out = m16.generate(img, 24)
+        assert out.shape == (1100, cand[1]) and torch.equal(out, full[:, :cand[1]])
+    finally:
+        m16.dims = dataclasses.replace(m16.dims, eos=old_eos)
+        m16.eos_token = old_eos

@@ -89,6 +89,43 @@ dist.destroy_process_group()
     assert "GATHER_OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_strong_scaling_job_plan_and_verify_logic_world2(tmp_path):
+    """BASELINE configs[4] plumbing on CPU (gloo, world 2): a fixed job is cut into batches with fixed boundaries, every rank
+    takes a contiguous run of whole batches, the gathered block of the peer rank equals what rank 0 computes itself for that
+    batch (the check bench.py --verify does with the real decode) -- with a deterministic stand-in for the decode."""
+    from bench import job_plan
+    for world in (1, 2, 4, 8):
+        plans = [job_plan(65536, 512, r, world) for r in range(world)]
+        assert sum(plans, []) == list(range(128))                       # every batch exactly once, in order, contiguous per rank
+        assert max(len(p) for p in plans) - min(len(p) for p in plans) <= 1
+    assert [len(job_plan(1000, 512, r, 4)) for r in range(4)] == [1, 1, 0, 0]
+    script = tmp_path / "v2.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r})
+from bench import job_plan, gather_tokens, BATCH_SEEDS
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+def decode(seed):           # stand-in for model.generate on the batch of that seed: a pure function of the seed
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 1000, (16, 8), generator=g)
+mine = job_plan(16 * 6, 16, r, w)
+blocks = [gather_tokens(decode(1234 + j % BATCH_SEEDS), w) for j in mine]
+if r == 0:
+    peer = w - 1
+    pj = job_plan(16 * 6, 16, peer, w)[0]
+    assert torch.equal(blocks[0][peer * 16:(peer + 1) * 16], decode(1234 + pj % BATCH_SEEDS))
+    assert torch.equal(blocks[0][:16], decode(1234 + mine[0] % BATCH_SEEDS))
+    print("VERIFY_OK")
+dist.destroy_process_group()
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert "VERIFY_OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_generate_pipeline_host_logic_with_stand_in_engines():
     """GeneratePipeline's host side (queue, worker threads, ordering, result buffers, error propagation) with stand-in engines:
     no device and no native library involved -- the GPU behaviour is covered by test_pipeline_of_batches_in_flight_matches_generate."""

@@ -64,7 +64,8 @@ static int fail_cuda(texocr_handle* h, cudaError_t e, const char* what, int line
 // ------------------------------------------------------------------------------------------------ profiling / launch accounting
 static const char* kclass_name[KC_COUNT] = {
     "stem_conv", "gn_stats", "gn_apply", "conv_gemm", "enc_gemm", "enc_attn", "enc_rowwise", "crosskv_gemm",
-    "dec_gemm", "dec_attn_self", "dec_attn_cross", "dec_rowwise", "dec_argmax", "tf_gemm", "tf_attn", "tf_rowwise", "misc", "dec_mega"};
+    "dec_gemm", "dec_attn_self", "dec_attn_cross", "dec_rowwise", "dec_argmax", "tf_gemm", "tf_attn", "tf_rowwise", "misc", "dec_mega",
+    "dec_gemm_q", "dec_gemm_vproj", "dec_gemm_wo", "dec_gemm_w1", "dec_gemm_w2", "dec_gemm_logits"};
 
 static cudaEvent_t get_event(texocr_handle* h) {
     if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
@@ -476,8 +477,17 @@ static GemmArgs mk_gemm(const void* A, int lda, const void* W, int ldw, void* C,
     g.bias = bias; g.res = res; g.ldres = ldres; g.dt_a = dt_a; g.dt_c = dt_c; g.epi = epi; g.conv = nullptr;
     return g;
 }
+// algorithmic bytes of a GEMM launch: both operands once + what the epilogue reads / writes
 static double gemm_bytes(const GemmArgs& g, size_t esz) {
-    return (double)g.M * g.K * esz + (double)g.N * g.K * esz + (double)g.M * g.N * 4.0;
+    double out = 0.0;
+    switch (g.epi) {
+        case EPI_STORE: out = (double)g.M * g.N * (g.dt_c == DT_BF16 ? 2.0 : 4.0); break;
+        case EPI_GLU_RES: out = (double)g.M * (g.N / 2) * 8.0; break;        // fp32 residual in, fp32 out
+        case EPI_GEGLU: out = (double)g.M * (g.N / 2) * (double)esz; break;
+        case EPI_BIAS_RES: out = (double)g.M * g.N * 8.0; break;
+        default: break;
+    }
+    return (double)g.M * g.K * esz + (double)g.N * g.K * esz + out;
 }
 static double gemm_flops(const GemmArgs& g) { return 2.0 * g.M * (double)g.N * g.K; }
 
@@ -751,14 +761,14 @@ static inline void* rowa(texocr_handle* h, const DevBuf& b, const RowCtx& rc, in
 static int sub_attn_out(texocr_handle* h, const RowCtx& rc, const AttnW& w, cudaStream_t st) {
     // y = o.Wo^T + bo -> GLU -> + residual   [model/attention.py:96-99,180 ; 254]
     GemmArgs ga = mk_gemm(rowa(h, h->o, rc, 512), 512, w.wo, 512, rowf(h->s, rc, 256), 256, rc.rows, 512, 512, EPI_GLU_RES, h->dt, DT_F32, w.bo, rowf(h->x, rc, 256), 256);
-    LAUNCH(rc.kc_gemm, 1, gemm_bytes(ga, h->esz), gemm_flops(ga), run_gemm(h, ga, st));
+    LAUNCH(rc.kc_gemm == KC_DEC_GEMM ? KC_DEC_GEMM_WO : rc.kc_gemm, 1, gemm_bytes(ga, h->esz), gemm_flops(ga), run_gemm(h, ga, st));
     return 0;
 }
 static int sub_mlp(texocr_handle* h, const RowCtx& rc, const MlpW& w, cudaStream_t st) {
     GemmArgs g1 = mk_gemm(rowa(h, h->xn, rc, 256), 256, w.w1, 256, rowa(h, h->hid, rc, 1024), 1024, rc.rows, 2048, 256, EPI_GEGLU, h->dt, h->dt, w.b1, nullptr, 0);
-    LAUNCH(rc.kc_gemm, 1, gemm_bytes(g1, h->esz), gemm_flops(g1), run_gemm(h, g1, st));
+    LAUNCH(rc.kc_gemm == KC_DEC_GEMM ? KC_DEC_GEMM_W1 : rc.kc_gemm, 1, gemm_bytes(g1, h->esz), gemm_flops(g1), run_gemm(h, g1, st));
     GemmArgs g2 = mk_gemm(rowa(h, h->hid, rc, 1024), 1024, w.w2, 1024, rowf(h->s, rc, 256), 256, rc.rows, 256, 1024, EPI_BIAS_RES, h->dt, DT_F32, w.b2, rowf(h->x, rc, 256), 256);
-    LAUNCH(rc.kc_gemm, 1, gemm_bytes(g2, h->esz), gemm_flops(g2), run_gemm(h, g2, st));
+    LAUNCH(rc.kc_gemm == KC_DEC_GEMM ? KC_DEC_GEMM_W2 : rc.kc_gemm, 1, gemm_bytes(g2, h->esz), gemm_flops(g2), run_gemm(h, g2, st));
     return 0;
 }
 // x = LN(s); xn = LN(x)  (shared LayerNorm twice, model/attention.py:242-259), or the stack's final norm.
@@ -857,12 +867,14 @@ static int run_encoder(texocr_handle* h, const float* d_img, const EncGeom& g, c
 static int sub_abs_out(texocr_handle* h, const RowCtx& rc, const AttnW& w, const void* ca, cudaStream_t st) {
     if (!h->absorb_two_stage) {
         GemmArgs go = mk_gemm(ca, 2048, w.wvo, 2048, rowf(h->s, rc, 256), 256, rc.rows, 512, 2048, EPI_GLU_RES, h->dt, DT_F32, w.bo, rowf(h->x, rc, 256), 256);
-        LAUNCH(rc.kc_gemm, 1, gemm_bytes(go, h->esz), gemm_flops(go), run_gemm(h, go, st));
+        LAUNCH(rc.kc_gemm == KC_DEC_GEMM ? KC_DEC_GEMM_WO : rc.kc_gemm, 1, gemm_bytes(go, h->esz), gemm_flops(go), run_gemm(h, go, st));
         return 0;
     }
     GemmArgs gv = mk_gemm(ca, 2048, w.wv, 256, rowa(h, h->o, rc, 512), 512, rc.rows, 512, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
     gv.a_block_k = 256;
-    LAUNCH(rc.kc_gemm, 1, gemm_bytes(gv, h->esz), gemm_flops(gv), run_gemm(h, gv, st));
+    // algorithmic work of the block-diagonal GEMM: every row contracts 8 heads x (256 -> 64)
+    LAUNCH(rc.kc_gemm == KC_DEC_GEMM ? KC_DEC_GEMM_VPROJ : rc.kc_gemm, 1, (double)rc.rows * 2048 * h->esz + 512.0 * 256 * h->esz + (double)rc.rows * 512 * h->esz,
+           2.0 * rc.rows * 512.0 * 256, run_gemm(h, gv, st));
     return sub_attn_out(h, rc, w, st);
 }
 
@@ -971,7 +983,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
             void* qa = rowa(h, h->qabs, rc, 2048);
             void* ca = rowa(h, h->cabs, rc, 2048);
             GemmArgs gq = mk_gemm(xnbuf, 256, h->dec_self[l].wqk, 256, qa, 2048, rows, 2048, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
-            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gq, e), gemm_flops(gq), run_gemm(h, gq, st));
+            LAUNCH(KC_DEC_GEMM_Q, 1, (double)rows * 256 * e + 2048.0 * 256 * e + (double)rows * 2048 * e, gemm_flops(gq), run_gemm(h, gq, st));
             AttnAbsArgs ab{};
             ab.q = qa; ab.ldq = 2048; ab.latent = (char*)h->latcache.p + ((size_t)l * B + row0) * tcap * 256 * e; ab.latent_rows = (long)rows * tcap;
             ab.znew = xnbuf; ab.ldz = 256; ab.tcap = tcap; ab.step = step; ab.o = ca; ab.ldo = 2048; ab.batch = rows;
@@ -1027,7 +1039,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
             void* qa = rowa(h, h->qabs, rc, 2048);
             void* ca = rowa(h, h->cabs, rc, 2048);
             GemmArgs gc = mk_gemm(xnbuf, 256, h->dec_cross[l].wqk, 256, qa, 2048, rows, 2048, 256, EPI_STORE, h->dt, h->dt, nullptr, nullptr, 0);
-            LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gc, e), gemm_flops(gc), run_gemm(h, gc, st));
+            LAUNCH(KC_DEC_GEMM_Q, 1, (double)rows * 256 * e + 2048.0 * 256 * e + (double)rows * 2048 * e, gemm_flops(gc), run_gemm(h, gc, st));
             AttnAbsArgs ab{};
             ab.q = qa; ab.ldq = 2048; ab.latent = h->dec_enc; ab.latent_rows = h->crosskv_rows; ab.k_off = d_enc_off + row0; ab.o = ca; ab.ldo = 2048; ab.batch = rows;
             if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
@@ -1096,12 +1108,12 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
     float2* parts = fused_amax ? h->amax_part.as<float2>() + (size_t)row0 * nparts : nullptr;
     if (fused_amax) {
         GemmArgs gl = mk_gemm(xnbuf, 256, h->w_logits, 256, parts, nparts, rows, c.vocab_size, 256, EPI_ARGMAX, h->dt, DT_F32, h->b_logits, nullptr, 0);
-        LAUNCH(KC_DEC_GEMM, 1, (double)rows * 256 * e + (double)c.vocab_size * 256 * e + (double)rows * nparts * 8, gemm_flops(gl), run_gemm(h, gl, st));
+        LAUNCH(KC_DEC_GEMM_LOGITS, 1, (double)rows * 256 * e + (double)c.vocab_size * 256 * e + (double)rows * nparts * 8, gemm_flops(gl), run_gemm(h, gl, st));
     } else if (fuse) {
         if ((r = gemm_ln(h->w_logits, c.vocab_size, lg, c.vocab_size, EPI_STORE, DT_F32, h->b_logits, false, false, h->dec_norm_g, h->dec_norm_b))) return r;
     } else {
         GemmArgs gl = mk_gemm(xnbuf, 256, h->w_logits, 256, lg, c.vocab_size, rows, c.vocab_size, 256, EPI_STORE, h->dt, DT_F32, h->b_logits, nullptr, 0);
-        LAUNCH(KC_DEC_GEMM, 1, gemm_bytes(gl, e), gemm_flops(gl), run_gemm(h, gl, st));
+        LAUNCH(KC_DEC_GEMM_LOGITS, 1, gemm_bytes(gl, e), gemm_flops(gl), run_gemm(h, gl, st));
     }
     ArgmaxArgs aa{};
     aa.logits = lg; aa.partials = parts; aa.nparts = nparts; aa.B = rows; aa.V = c.vocab_size; aa.out_ids = h->out_ids.as<int64_t>() + (size_t)row0 * tcap; aa.out_ld = tcap;
@@ -1749,7 +1761,7 @@ int texocr_generate(texocr_handle* h, const float* images, const int32_t* hw, in
     CK(cudaMemcpyAsync(h->ids_stage.p, h->h_bos, (size_t)batch * 8, cudaMemcpyHostToDevice, st));
     if ((r = run_encoder(h, (const float*)d_img, g, st))) return r;
     if ((r = run_crosskv(h, h->enc_out.as<float>(), h->dt == DT_F32 ? nullptr : h->enc_a.p, g.ntok, st, true))) return r;
-    return run_generate(h, h->ids_stage.as<int64_t>(), h->cfg.eos_token, g.d_tok_off, g.max_tok, (double)g.ntok, batch, max_len, out_ids, n_steps, st);
+    return run_generate(h, h->ids_stage.as<int64_t>(), h->no_early_exit ? -1 : h->cfg.eos_token, g.d_tok_off, g.max_tok, (double)g.ntok, batch, max_len, out_ids, n_steps, st);
 }
 
 int texocr_preprocess_u8(texocr_handle* h, const uint8_t* pixels, const int32_t* hwc, int32_t batch, int32_t pad_multiple,
@@ -1902,6 +1914,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "fifo_pdl")) { h->fifo_pdl = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_full_tail")) { g_attn_full_tail = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "fuse_ln")) { h->fuse_ln = value != 0; drop_graphs(h); return 0; }
+    if (!strcmp(name, "no_early_exit")) { h->no_early_exit = value != 0; return 0; }
     if (!strcmp(name, "keep_logits")) { h->keep_logits = value != 0; drop_graphs(h); return 0; }
     if (!strcmp(name, "poison")) { h->poison = value != 0; return 0; }
     if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(8, value)); drop_graphs(h); return 0; }

@@ -37,7 +37,10 @@ struct MlpW { void* w1 = nullptr; float* b1 = nullptr; void* w2 = nullptr; float
 enum KClass {
     KC_STEM = 0, KC_GN_STATS, KC_GN_APPLY, KC_CONV, KC_ENC_GEMM, KC_ENC_ATTN, KC_ENC_ROW, KC_CROSSKV_GEMM,
     KC_DEC_GEMM, KC_DEC_ATTN_SELF, KC_DEC_ATTN_CROSS, KC_DEC_ROW, KC_DEC_ARGMAX, KC_TF_GEMM, KC_TF_ATTN, KC_TF_ROW,
-    KC_MISC, KC_DEC_MEGA, KC_COUNT
+    KC_MISC, KC_DEC_MEGA,
+    // the decode-step GEMMs by role (bench.py sums them into "dec_gemm"; KC_DEC_GEMM itself = the projected-K/V formulation's QKV / q GEMMs)
+    KC_DEC_GEMM_Q, KC_DEC_GEMM_VPROJ, KC_DEC_GEMM_WO, KC_DEC_GEMM_W1, KC_DEC_GEMM_W2, KC_DEC_GEMM_LOGITS,
+    KC_COUNT
 };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; double bytes, flops; };
@@ -136,6 +139,7 @@ struct texocr_handle {
     const void* dec_enc = nullptr;             // bf16 encoder memory of the current generate call [crosskv_rows, 256]
     int use_tma_attn = 1;     // 0 = simple kernel, 1 = TMA kernel for self + cross, 2 = self only, 3 = cross only
     bool fuse_ln = false;    // decode step: LayerNorms computed inside the consuming tcgen05 GEMM (bf16 tier)
+    bool no_early_exit = false; // texocr_generate runs all max_len steps even when every row has produced an EOS (sub-batches of one large call)
     bool keep_logits = false;   // debug / tests: the decode step also leaves its last-position logits in h->logits (texocr_debug_read "logits")
     bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate
     int dbg_skip = 0;        // timing experiments only: 1 self-attn, 2 cross-attn, 4 LayerNorms, 8 GEMMs (results are garbage)

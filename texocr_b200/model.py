@@ -144,13 +144,15 @@ class OCRModel(nn.Module):
             object.__setattr__(m, "_owner", self._self_ref)
         self._engine: Optional[Engine] = None
         self._engine_key = None
+        self._pipe = None
+        self._pipe_key = None
 
     def _self_ref(self):
         return self
 
     # ------------------------------------------------------------------ engine lifecycle
     def _weights_key(self):
-        return (self.precision, str(self.device),
+        return (self.precision, str(self.device), self.dims,
                 tuple((p.data_ptr(), p._version) for p in self.parameters()))
 
     def engine(self) -> Engine:
@@ -166,6 +168,40 @@ class OCRModel(nn.Module):
             self._engine = Engine(self.dims, self.state_dict(), self.precision, idx)
             self._engine_key = key
         return self._engine
+
+    # ------------------------------------------------------------------ one large call = several sub-batches in flight
+    sub_batch = 512          # rows per sub-batch of a large generate call (BASELINE configs[2]'s batch)
+    max_in_flight = 6
+
+    def _generate_sub_batches(self, src: torch.Tensor, max_len: int) -> torch.Tensor:
+        """``generate`` for B >= 2 x sub_batch: the rows are independent, so the call is cut into sub-batches of ``sub_batch``
+        rows that are decoded concurrently by internal engine replicas (texocr_b200/pipeline.py) -- a caller of the
+        reference's loop (test.py:27-40) with a larger batch gets the pipelined rate from ONE call.  Same tokens as
+        sub-batch-sized calls.  The reference's shape contract is kept: the result is as wide as the slowest sub-batch needs
+        (the step at which every row of the WHOLE batch holds an EOS, model/decoder.py:115-118); a sub-batch that finished
+        earlier is decoded again without its early exit so that its rows carry the tokens the reference would have there."""
+        from .pipeline import GeneratePipeline
+        key = self._weights_key()
+        chunks = list(torch.split(src, self.sub_batch))
+        want = min(self.max_in_flight, len(chunks))
+        if self._pipe is None or self._pipe_key != key or len(self._pipe.engines) < want:
+            if self._pipe is not None:
+                self._pipe.close()
+            self._pipe = GeneratePipeline(self, in_flight=want, branches=1)
+            self._pipe_key = key
+        outs = list(self._pipe.generate_batches(chunks, max_len))
+        n = max(o.shape[1] for o in outs)
+        short = [i for i, o in enumerate(outs) if o.shape[1] < n]
+        if short:
+            for e in self._pipe.engines:
+                e.set_option("no_early_exit", 1)
+            try:
+                for i, o in zip(short, self._pipe.generate_batches([chunks[i] for i in short], n)):
+                    outs[i] = o
+            finally:
+                for e in self._pipe.engines:
+                    e.set_option("no_early_exit", 0)
+        return torch.cat(outs, dim=0)
 
     def resize_pos_embedding(self, new_len: int):
         """TeXOCRWrapper.__init__ (model/ocr_model.py:82-90): a checkpoint whose decoder positional table has another
@@ -232,6 +268,8 @@ class OCRModel(nn.Module):
         (1,H,W) images of different sizes (ragged batch) -- an extension over the reference's same-size batches."""
         eng = self.engine()
         if not sample:
+            if isinstance(src, torch.Tensor) and src.dim() == 4 and src.shape[0] >= 2 * self.sub_batch:
+                return self._generate_sub_batches(src, max_len)
             return eng.generate(src, max_len)
         eng.set_sampling(temp, 0.9, seed)
         try:
