@@ -37,7 +37,6 @@ def decode_us(label):
     print(f"{label}: generate(256) {t256:.1f} ms, generate(64) {t64:.1f} ms -> decode {(t256 - t64) / 192 * 1000:.0f} us/step (t in 64..256)")
 
 
-eng.set_option("fuse_ln", 0)
 for cps in (3, 4, 6):
     eng.set_option("attn_ctas_per_sm", cps)
     for nb, stag in ((1, 0), (4, 0), (4, 60), (8, 30)):

@@ -40,9 +40,9 @@ CASES = [
     (8, 512, 512, EPI_GLU_RES, torch.float32, True),
     (512, 512, 512, EPI_GLU_RES, torch.float32, True),
     (512, 2048, 256, EPI_GEGLU, torch.bfloat16, True),
-    (512, 256, 1024, EPI_BIAS_RES, torch.float32, True),      # decode MLP-out: split-K over a 4-CTA cluster
+    (512, 256, 1024, EPI_BIAS_RES, torch.float32, True),      # decode MLP-out
     (86, 256, 1024, EPI_BIAS_RES, torch.float32, True),
-    (86, 512, 512, EPI_GLU_RES, torch.float32, True),         # decode out-projection: split-K over a 2-CTA cluster, M tail
+    (86, 512, 512, EPI_GLU_RES, torch.float32, True),         # decode out-projection, M tail
     (512, 1000, 256, EPI_STORE, torch.float32, True),       # vocab projection: N tail inside a tile
     (300, 4096, 256, EPI_STORE, torch.bfloat16, False),     # M tail
     (49664, 1536, 256, EPI_STORE, torch.bfloat16, False),   # encoder-sized
@@ -55,16 +55,6 @@ CASES = [
 @pytest.mark.parametrize("use_tc", [True, False])
 def test_bf16_gemm_vs_torch(eng, M, N, K, epi, out_dtype, use_bias, use_tc):
     _gemm_case(eng, M, N, K, epi, out_dtype, use_bias, use_tc)
-
-
-@pytest.mark.parametrize("M,N,K,epi", [(512, 256, 1024, EPI_BIAS_RES), (86, 256, 1024, EPI_BIAS_RES), (86, 512, 512, EPI_GLU_RES), (8, 512, 512, EPI_GLU_RES)])
-def test_cluster_split_k_gemm(eng, M, N, K, epi):
-    """Opt-in split-K over a 2- / 4-CTA cluster (partials through distributed shared memory, fixed summation order)."""
-    eng.set_option("gemm_split_k", 1)
-    try:
-        _gemm_case(eng, M, N, K, epi, torch.float32, True, True)
-    finally:
-        eng.set_option("gemm_split_k", 0)
 
 
 def _gemm_case(eng, M, N, K, epi, out_dtype, use_bias, use_tc):

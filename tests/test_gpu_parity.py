@@ -198,29 +198,6 @@ def test_decode_branches_do_not_change_tokens(m16, golden):
     assert res[0].shape == res[1].shape and torch.equal(res[0], res[1])
 
 
-def test_coupled_step_graph_does_not_change_tokens(m16):
-    """Opt-in coupled mode: all branches of several decode steps in one graph, attention launches chained across branches
-    (attn_fifo).  Same kernels, same tokens; early exit keeps its contract with multi-step graphs."""
-    img = synth.synth_images(64, 32, 128, seed=12).cuda()
-    eng = m16.engine()
-    eng.set_option("decode_branches", 4)
-    ref = m16.generate(img, 37)
-    enc = m16.encoder(img)
-    start = torch.full((64, 1), m16.dims.bos, dtype=torch.long, device="cuda")
-    eos = int(ref[0, 9])
-    ref_e = m16.decoder.generate(start_tokens=start, eos_tok=eos, max_len=37, enc=enc)
-    try:
-        for fifo, spg in ((1, 4), (2, 1), (4, 8)):
-            eng.set_option("attn_fifo", fifo)
-            eng.set_option("steps_per_graph", spg)
-            assert torch.equal(m16.generate(img, 37), ref), (fifo, spg)
-            out_e = m16.decoder.generate(start_tokens=start, eos_tok=eos, max_len=37, enc=enc)
-            assert out_e.shape == ref_e.shape and torch.equal(out_e, ref_e), (fifo, spg)
-    finally:
-        eng.set_option("attn_fifo", 0)
-        eng.set_option("decode_branches", 0)
-
-
 def test_pipeline_of_batches_in_flight_matches_generate(m16):
     """GeneratePipeline (several batches decoded concurrently by replica handles on their own host threads / streams):
     every batch gets exactly the tokens model.generate gives it, for device and for host (pinned) buffers."""
@@ -258,20 +235,6 @@ def test_tma_attention_matches_simple_kernel(m16):
     logits = m16.decoder.net(ids, enc=enc)
     agree = (logits.argmax(-1) == outs[0]).float().mean().item()
     assert agree > 0.97, agree
-
-
-def test_layernorm_fused_gemm_is_bit_identical(m16):
-    """tc_gemm_ln_kernel computes the shared double LayerNorm with the arithmetic of ln2_kernel: same token ids."""
-    img = synth.synth_images(300, 64, 384, seed=31).cuda()
-    eng = m16.engine()
-    outs = []
-    _absorb(eng, 0)         # the fused-LayerNorm path keeps the projected K/V formulation
-    for fuse in (1, 0):
-        eng.set_option("fuse_ln", fuse)
-        outs.append(m16.generate(img, 40))
-    eng.set_option("fuse_ln", 0)
-    _absorb(eng, 1)
-    assert torch.equal(outs[0], outs[1])
 
 
 def test_absorbed_attention_matches_projected_kv(m16, m32):
@@ -314,48 +277,6 @@ def test_absorbed_attention_matches_projected_kv(m16, m32):
         agree = (m16.decoder.net(ids, enc=enc).argmax(-1) == toks[mode]).float().mean().item()
         assert agree > 0.97, (mode, agree)
         assert (toks[mode][:, :8] == toks[(0, 0)][:, :8]).float().mean().item() > 0.9, mode
-
-
-def test_cluster_persistent_decode_kernel_matches_branch_path(m16):
-    """decode_mega.cu (opt-in): whole decode steps inside one kernel, one 16-CTA cluster per group of <= 80 sequences.
-    Same tokens as the per-branch kernel graphs up to near-ties, for ragged groups / ragged memory lengths, any number of
-    steps per launch, and the early-exit contract."""
-    eng = m16.engine()
-    try:
-        for B, T in ((8, 24), (96, 48), (300, 40)):
-            widths = synth.synth_widths(B, seed=B) if B == 96 else [384] * B
-            imgs = [synth.synth_images(1, 64, int(w), seed=1000 * B + i)[0] for i, w in enumerate(widths)]
-            src = [im.cuda() for im in imgs]
-            eng.set_option("decode_mega", 0)
-            _absorb(eng, 0)                  # the cluster kernel implements the projected-K/V formulation
-            ref = m16.generate(src, T)
-            _absorb(eng, 1)
-            eng.set_option("decode_mega", 1)
-            out = m16.generate(src, T)
-            eng.set_option("mega_steps", 5)
-            out2 = m16.generate(src, T)
-            eng.set_option("mega_steps", 16)
-            assert out.shape == ref.shape == (B, T)
-            assert torch.equal(out, out2)                      # steps per launch do not matter
-            assert (out == ref).float().mean().item() > 0.9    # only near-ties may flip (different GEMM summation order)
-            if B != 96:      # teacher-forced check on the rectangular batches
-                enc = m16.encoder(torch.stack(src))
-                ids = torch.cat((torch.full((B, 1), m16.dims.bos, device="cuda"), out[:, :-1]), 1)
-                agree = (m16.decoder.net(ids, enc=enc).argmax(-1) == out).float().mean().item()
-                assert agree > 0.97, agree
-        # early exit: stop at the first step where every row has produced eos (model/decoder.py:110-116)
-        img = synth.synth_images(96, 64, 384, seed=11).cuda()
-        enc = m16.encoder(img)
-        start = torch.full((96, 1), m16.dims.bos, dtype=torch.long, device="cuda")
-        full = m16.decoder.generate(start_tokens=start, eos_tok=None, max_len=48, enc=enc)
-        eos = int(full[0, 20])
-        hit = (full == eos)
-        expect = int(hit.float().argmax(1).max()) + 1 if bool(hit.any(1).all()) else 48
-        res = m16.decoder.generate(start_tokens=start, eos_tok=eos, max_len=48, enc=enc)
-        assert res.shape == (96, expect) and torch.equal(res, full[:, :expect])
-    finally:
-        eng.set_option("decode_mega", 0)
-        eng.set_option("mega_steps", 16)
 
 
 def test_input_validation_raises(m32):

@@ -52,7 +52,7 @@ def load_checkpoint(model, load_path: str, strict: bool = True):
 
 # ------------------------------------------------------------------------------------------------ packed blob
 def _is_bf16_matrix(key: str) -> bool:
-    """2-D weights the bf16 tier converts to bf16 GEMM operands (texocr_b200/csrc/engine.cu, finalize_weights): the
+    """2-D weights the bf16 tier converts to bf16 GEMM operands (texocr_b200/csrc/engine_weights.cu, finalize_weights): the
     q / k / v / output / MLP matrices of both transformer stacks and the vocabulary projection."""
     return key == "decoder.net.to_logits.weight" or (".attn_layers.layers." in key and key.endswith(".weight"))
 

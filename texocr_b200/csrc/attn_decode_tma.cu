@@ -18,8 +18,6 @@
 #include "tc_gemm.h"
 
 int g_attn_full_tail = 0;
-int g_attn_l2_policy = 0;    // attn_abs_kernel TMA loads: bit 0 = self-attention cache rows evict-first (each row is read once per step and layer),
-                             // bit 1 = cross-attention memory rows evict-last (the same [S, 256] rows serve all 4 layers of all 256 steps)
 int g_attn_abs_minb = 3;     // attn_abs_kernel: 3 = 128 registers, no spills (default: 1-3 % better with batches in flight); 4 = 96 registers (small spills), 4 CTAs per SM
 
 namespace {
@@ -70,11 +68,6 @@ TX_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 TX_DEVINL uint64_t l2_evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-TX_DEVINL uint64_t l2_evict_last_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
 TX_DEVINL void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint64_t pol) {
@@ -373,13 +366,7 @@ __global__ void __launch_bounds__(96) attn_decode_tma_kernel(const __grid_consta
 // Self-attention: this step's own latent row (position t) is written into the last stage by the consumers (it is key t of
 // that stage) and appended to the cache for the following steps.
 constexpr int AW = 4;                       // consumer warps = 64-column blocks of a latent row
-#ifndef TEXOCR_ABS_SKIP
-#define TEXOCR_ABS_SKIP 0
-#endif
-#ifndef TEXOCR_ABS_STAGES
-#define TEXOCR_ABS_STAGES 5
-#endif
-constexpr int ANS = TEXOCR_ABS_STAGES;                      // ring stages of the absorbed kernel (40 KB)
+constexpr int ANS = 5;                      // ring stages of the absorbed kernel (40 KB)
 constexpr int XROW = 40;                    // floats per (warp, head) row of the score exchange: 32 keys, padded so that a half-warp's float2 accesses hit 32 distinct banks
 struct AbsArgs {
     const bf16* q; int ldq;            // [batch, ldq]: head h at h*256 (absorbed query, unscaled)
@@ -391,7 +378,6 @@ struct AbsArgs {
     int batch;
     unsigned long long* trace; const int* trace_step; int trace_k;
     unsigned long long* dbg;           // debug: sums over CTAs of [wait for predecessor, first data, stage loop, epilogue] ns + count
-    int l2_policy;                     // 0 = no hint, 1 = evict-first, 2 = evict-last
 };
 
 template <bool SELF, int MINB>
@@ -430,8 +416,6 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         if (lane == 0) {
             int it = 0;
             if (SELF) asm volatile("fence.proxy.async.global;" ::: "memory");     // cache rows were appended by generic-proxy stores of earlier steps
-            const bool hint = a.l2_policy != 0;
-            const uint64_t pol = a.l2_policy == 2 ? l2_evict_last_policy() : l2_evict_first_policy();
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 int row0, nc;      // nc = rows to fetch; self: the t cached rows (this step's own row is added by the consumers)
                 if (SELF) { row0 = u * a.tcap; nc = t; }
@@ -445,19 +429,13 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
                     if (left >= CH) {
                         mbar_expect_tx(&full[s], STAGE);
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) {
-                            if (hint) tma_load_2d(&tm, &full[s], st + cb * HTILE, 64 * cb, r, pol);
-                            else tma_load_2d_nohint(&tm, &full[s], st + cb * HTILE, 64 * cb, r);
-                        }
+                        for (int cb = 0; cb < 4; ++cb) tma_load_2d_nohint(&tm, &full[s], st + cb * HTILE, 64 * cb, r);
                     } else {               // tail: 4-row boxes (none at all when only this step's own row is left)
                         const int n4 = left > 0 ? (left + 3) >> 2 : 0;
                         mbar_expect_tx(&full[s], n4 * 4 * 512);
                         for (int j = 0; j < n4; ++j)
 #pragma unroll
-                            for (int cb = 0; cb < 4; ++cb) {
-                                if (hint) tma_load_2d(&tm4, &full[s], st + cb * HTILE + j * 512, 64 * cb, r + 4 * j, pol);
-                                else tma_load_2d_nohint(&tm4, &full[s], st + cb * HTILE + j * 512, 64 * cb, r + 4 * j);
-                            }
+                            for (int cb = 0; cb < 4; ++cb) tma_load_2d_nohint(&tm4, &full[s], st + cb * HTILE + j * 512, 64 * cb, r + 4 * j);
                     }
                 }
             }
@@ -542,13 +520,9 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
 #pragma unroll
                         for (int s2 = 0; s2 < 2; ++s2) {
                             uint32_t b0, b1, b2, b3;
-#if !(TEXOCR_ABS_SKIP & 1)       /* timing experiment builds only: bit 0 drops the score MMAs, bit 1 the P.Z MMAs (garbage results) */
                             ldsm_x4(kts[q] + off_qk[j][s2], b0, b1, b2, b3);
                             mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2], qa[4 * s2 + 1], b0, b1);
                             mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2 + 2], qa[4 * s2 + 3], b2, b3);
-#else
-                            b0 = b1 = b2 = b3 = 0u; sc[q][j][0] += __uint_as_float(qa[4 * s2] & 0x3f800000u);
-#endif
                         }
                     }
                 }
@@ -613,14 +587,10 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
 #pragma unroll
                     for (int np = 0; np < 4; ++np) {
                         uint32_t b0, b1, b2, b3;
-#if !(TEXOCR_ABS_SKIP & 2)
                         ldsm_x4_t(kts[q] + off_pv[np], b0, b1, b2, b3);
                         if (last) { b0 &= vm_lo[q]; b2 &= vm_lo[q]; b1 &= vm_hi[q]; b3 &= vm_hi[q]; }
                         mma_bf16_top(o[2 * np][0], o[2 * np][1], pa0, pa2, b0, b1);
                         mma_bf16_top(o[2 * np + 1][0], o[2 * np + 1][1], pa0, pa2, b2, b3);
-#else
-                        b0 = b1 = b2 = b3 = 0u; o[2 * np][0] += __uint_as_float(pa0 & 0x3f800000u); o[2 * np + 1][1] += __uint_as_float(pa2 & 0x3f800000u);
-#endif
                     }
                 }
             }
@@ -700,7 +670,6 @@ cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     k.q = (const bf16*)a.q; k.ldq = a.ldq; k.k_off = a.k_off; k.o = (bf16*)a.o; k.ldo = a.ldo; k.batch = a.batch;
     k.znew = (const bf16*)a.znew; k.ldz = a.ldz; k.cache = (bf16*)const_cast<void*>(a.latent); k.tcap = a.tcap; k.step = a.step;
     k.trace = a.trace; k.trace_step = a.trace_step; k.trace_k = a.trace_k; k.dbg = a.dbg;
-    k.l2_policy = a.znew ? ((g_attn_l2_policy & 1) ? 1 : 0) : ((g_attn_l2_policy & 2) ? 2 : 0);
     // persistent grid: never more CTAs than can be resident (the rest would only queue behind them without the cross-unit prefetch)
     static int occ[2][2] = {{0, 0}, {0, 0}};
     static int sms = 0;

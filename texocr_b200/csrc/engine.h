@@ -37,7 +37,7 @@ struct MlpW { void* w1 = nullptr; float* b1 = nullptr; void* w2 = nullptr; float
 enum KClass {
     KC_STEM = 0, KC_GN_STATS, KC_GN_APPLY, KC_CONV, KC_ENC_GEMM, KC_ENC_ATTN, KC_ENC_ROW, KC_CROSSKV_GEMM,
     KC_DEC_GEMM, KC_DEC_ATTN_SELF, KC_DEC_ATTN_CROSS, KC_DEC_ROW, KC_DEC_ARGMAX, KC_TF_GEMM, KC_TF_ATTN, KC_TF_ROW,
-    KC_MISC, KC_DEC_MEGA,
+    KC_MISC, KC_UNUSED,
     // the decode-step GEMMs by role (bench.py sums them into "dec_gemm"; KC_DEC_GEMM itself = the projected-K/V formulation's QKV / q GEMMs)
     KC_DEC_GEMM_Q, KC_DEC_GEMM_VPROJ, KC_DEC_GEMM_WO, KC_DEC_GEMM_W1, KC_DEC_GEMM_W2, KC_DEC_GEMM_LOGITS,
     KC_COUNT
@@ -87,10 +87,8 @@ struct texocr_handle {
     DevBuf ids_stage, mask_stage, enc_stage, tgt_stage, row_loss, scalars;
     DevBuf dec_state;                          // int64 cur_tok[B] | int32 step, done_step, block_counter, pad | int32 seen[B]
     DevBuf out_ids;                            // int64 [B, max_len]
-    DevBuf mega_dbg;
     DevBuf attn_trace; bool attn_trace_on = false;   // debug timeline of the decode attention launches: [branch][3][256 steps][8] u64 ns
     DevBuf prep_meta, prep_in, prep_out;       // texocr_preprocess_u8 staging
-    DevBuf mega_part;                          // cluster-persistent decode kernel: per-CTA argmax partials [B][16] (float | int)
     int* h_poll = nullptr;                     // pinned: done_step polls
     int64_t* h_bos = nullptr; size_t h_bos_cap = 0;   // pinned: the BOS start column of texocr_generate (constant content)
     int last_backbone_pixels = 0;
@@ -102,18 +100,7 @@ struct texocr_handle {
     cudaGraph_t bgraph[16] = {nullptr}; cudaGraphExec_t bgraph_exec[16] = {nullptr};   // one single-step graph per branch
     cudaEvent_t poll_ev[2][16] = {{nullptr}};
     int stagger_us = 30;                        // start offset between consecutive branches
-    // Coupled mode (attn_fifo = m > 0): all branches of `steps_per_graph` decode steps are captured into ONE graph in which
-    // attention launch k of branch i additionally depends on attention launch k of branch i - m, so that at most m branches
-    // stream K/V at a time and the others run their GEMM / LayerNorm chains meanwhile.
-    int decode_priority = 0;                    // 1: decode streams at the highest priority (single branch too); 2: single branch on an own stream at
-                                                // the lowest priority; 0: default streams.  Measured with 6 batches in flight: 1 is 12 % slower than 0
-    int attn_fifo = 0;
-    int steps_per_graph = 4;
-    int fifo_pdl = 1;                           // attention launches that carry a cross-branch dependency keep their programmatic edge
-    cudaGraph_t cgraph[2] = {nullptr, nullptr}; cudaGraphExec_t cgraph_exec[2] = {nullptr, nullptr}; int cgraph_kernels[2] = {0, 0};
-    std::vector<cudaEvent_t> fifo_ev;           // [step in graph][branch][8 attention launches]
-    cudaEvent_t* fifo_wait = nullptr; cudaEvent_t* fifo_rec = nullptr;     // set around enqueue_decode_step while capturing
-    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0; int fifo = 0; int spg = 0; int absorb = 0;
+    struct { int B = 0, tcap = 0, eos = 0, max_s = 0; void* kv = nullptr; void* ckv = nullptr; void* x = nullptr; int kernels = 0; int nb = 0; int ntok = 0; int samp = 0;
              const int* enc_off = nullptr; uint64_t samp_seed = 0; double samp_temp = 0.0; } gkey;   // enc_off: the cross-attention launches bake this device pointer in
 
     // ---- instrumentation
@@ -125,9 +112,6 @@ struct texocr_handle {
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
     bool use_im2col_tma = true;   // bf16 tier, same-size batches: 3x3 / strided convolutions as implicit GEMMs (TMA im2col loads)
-    int decode_mega = 0;      // bf16 tier: 1 = experimental cluster-persistent decode kernel (decode_mega.cu), 0 = per-branch kernel graphs.
-                              // Token-identical to the branch path but ~1.8x slower at B = 512 (issue-bound at 8 warps per SM)
-    int mega_steps = 16;      // decode steps per launch of that kernel (also the early-exit polling interval)
     // bf16 tier generate loop: cross-attention streams the [S,256] encoder memory once for all heads instead of per-head K/V
     // (K / V projections folded into the query / output projections).  0 = projected K/V cache.
     int cross_absorb = 1;
@@ -138,7 +122,6 @@ struct texocr_handle {
     DevBuf latcache;                           // [layer][sequence][position][256] bf16 latent cache of the absorbed self-attention
     const void* dec_enc = nullptr;             // bf16 encoder memory of the current generate call [crosskv_rows, 256]
     int use_tma_attn = 1;     // 0 = simple kernel, 1 = TMA kernel for self + cross, 2 = self only, 3 = cross only
-    bool fuse_ln = false;    // decode step: LayerNorms computed inside the consuming tcgen05 GEMM (bf16 tier)
     bool no_early_exit = false; // texocr_generate runs all max_len steps even when every row has produced an EOS (sub-batches of one large call)
     bool keep_logits = false;   // debug / tests: the decode step also leaves its last-position logits in h->logits (texocr_debug_read "logits")
     bool poison = false;     // debug: NaN-fill all workspaces at the start of texocr_generate

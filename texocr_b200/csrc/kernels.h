@@ -7,7 +7,7 @@
 enum { DT_F32 = 0, DT_BF16 = 1 };
 
 // Launch with programmatic dependent launch enabled (kernels call pdl_wait() before reading their inputs).
-// Programmatic dependent launch per kernel family: bit k of g_texocr_pdl enables it for family k (engine.cu).
+// Programmatic dependent launch per kernel family: bit k of g_texocr_pdl enables it for family k (engine_core.cu).
 enum { PDL_GEMM = 0, PDL_LN = 1, PDL_EMBED = 2, PDL_ARGMAX = 3, PDL_ATTN_TMA = 4, PDL_ATTN_SIMPLE = 5 };
 extern int g_texocr_pdl;
 #ifdef __CUDACC__

@@ -21,17 +21,9 @@
 #include "common.cuh"
 #include "tc_gemm.h"
 
-// texocr_set_option("gemm_split_k"): cluster split-K for the long-K decode GEMMs.  Correct (tests/test_gpu_gemm.py) but measured
-// slower in the decode loop (104.5 vs 95.2 ms per generate at B = 512): cluster launch + DSMEM hand-off cost more than the two
-// or three TMA ring rounds they save.  Off by default.
-int g_tc_split_k = 0;
-int g_tc_persistent = 1;
-int g_tc_deep_ring = 0;          // 8-stage TMA ring for the K >= 2048 decode GEMMs (single batch: -2.5 %; six batches in flight: +7 %, the 160 KB CTAs crowd the SMs)
-int g_tc_shallow_ring = 0;       // 2-stage ring (40 KB at BN = 32) for every one-tile-per-CTA GEMM: smaller shared-memory footprint next to the attention CTAs
+int g_tc_persistent = 1;          // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
 int g_tc_min_ctas = 120;          // tile width rule: narrow the N tile (128 -> 64 -> 32) while the grid would have fewer CTAs than this
-int g_tc_persist_min_tiles = 296; // persistent kernel for GEMMs of at least this many tiles ...
-int g_tc_tiles_per_cta = 0;       // ... on ceil(tiles / this) CTAs (0 = one CTA per SM): decode-sized GEMMs on few, longer-lived CTAs
-int g_tc_persistent_stages = 0;   // 0 = as many ring stages as fit in 200 KB; n > 0 caps them (leaves shared memory to co-resident kernels)     // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
+int g_tc_persistent_stages = 0;   // 0 = as many ring stages as fit in 200 KB; n > 0 caps them (leaves shared memory to co-resident kernels)
 
 namespace {
 
@@ -85,30 +77,6 @@ TX_DEVINL void tma_load_im2col(const CUtensorMap* map, uint64_t* bar, void* dst,
 TX_DEVINL void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-TX_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {       // acquire at cluster scope: data written by peer CTAs
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAITC_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAITC_DONE;\n\t"
-        "bra WAITC_LOOP;\n\t"
-        "WAITC_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-TX_DEVINL uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
-    return r;
-}
-TX_DEVINL void st_cluster_f4(uint32_t raddr, float a, float b, float c, float d) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-TX_DEVINL void mbar_arrive_remote(uint32_t raddr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-TX_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
-TX_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 TX_DEVINL void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 TX_DEVINL void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 TX_DEVINL void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -172,14 +140,9 @@ TX_DEVINL void stage_copy(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int la
     }
 }
 
-// split-K partial tiles in the leader CTA's shared memory: [part][128 rows][PSTR floats]
-constexpr int PSTR = 36;
-constexpr int PART_BYTES = BM * PSTR * 4;
-
 template <int BN, int EPI, typename TC>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
-                             uint8_t* smem_idle, const float* parts = nullptr, int nparts = 0, uint64_t* part_full = nullptr,
-                             uint32_t parity = 0) {
+                             uint8_t* smem_idle, uint32_t parity = 0) {
     const int q = warp & 3;
     uint8_t* stg = smem_idle + q * STG_WARP;
     uint8_t* my = stg + lane * STG_STRIDE;                      // this thread's staged row
@@ -213,7 +176,6 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
     }
     mbar_wait(tmem_full, parity);
     tcgen05_fence_after();
-    if (nparts) mbar_wait_cluster(part_full, 0);                // split-K: the peers' partial tiles have landed in our shared memory
     float am_best = -INFINITY;                                  // EPI_ARGMAX: running maximum of this thread's row over the tile
     int am_idx = 0x7fffffff;
 #pragma unroll 1
@@ -227,14 +189,6 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        for (int pt = 0; pt < nparts; ++pt) {                   // fixed order: deterministic sums (BN == 32 only)
-            const float* pr = parts + (size_t)pt * (PART_BYTES / 4) + (q * 32 + lane) * PSTR;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(pr + i);
-                v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-            }
-        }
         if (p.bias) {
             if (c0 == 0) {
 #pragma unroll
@@ -308,29 +262,21 @@ template <int BN, int SPLIT, int NSTG = 0> struct Smem {
     static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BARS;
 };
 
-// KS > 1: split-K over a cluster of KS CTAs (grid z): CTA kz accumulates k-blocks [kz, kz+1) * nkb / KS in its own TMEM; the
-// peers (kz > 0) ship their fp32 tiles through distributed shared memory to the leader (kz = 0), which adds them in a fixed
-// order and runs the epilogue.  Used for the long-K, latency-bound decode GEMMs (out-projections K = 512, MLP-out K = 1024).
-template <int BN, int EPI, typename TC, int SPLIT, int NSTG, int KS = 1>
+template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
 __global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
     using S = Smem<BN, SPLIT, NSTG>;
-    static_assert(KS == 1 || (BN == 32 && SPLIT == 1), "split-K is instantiated for the narrow decode tiles only");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE);
     uint64_t* empty = full + S::STAGES;
     uint64_t* tmem_full = empty + S::STAGES;
-    uint64_t* part_full = tmem_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(part_full + 1);
-    float* parts = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE + S::BARS);      // [KS - 1][BM][PSTR] (KS > 1 only)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kz = KS > 1 ? (int)blockIdx.z : 0;
-    const int nkb = p.K / BK / KS;                  // k-blocks of this CTA
-    const int kb0 = kz * nkb;
+    const int nkb = p.K / BK;
 
     if (!p.late_trigger) pdl_launch_dependents();
     unsigned long long dbg_t0 = 0ull, dbg_t1 = 0ull;
@@ -340,7 +286,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
-        if (KS > 1) mbar_init(part_full, (KS - 1) * 4);          // one arrival per epilogue warp of every peer
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -350,7 +295,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    if (KS > 1) cluster_arrive();       // the leader's part_full barrier is initialised; the matching wait sits off the critical path
     const uint32_t tmem_base = *tmem_slot;
     // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel, and so do the
     // weight tiles of the first ring round: W never depends on the predecessor, only the activations (A) do.
@@ -360,8 +304,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = 0; kb < npre; ++kb) {
                 uint8_t* st = smem + kb * S::STAGE;
                 mbar_expect_tx(&full[kb], S::STAGE);
-                tma_load_2d(&tmW, &full[kb], st + S::NOPS * S::A_BYTES, (kb0 + kb) * BK, n0);
-                if (SPLIT == 3) tma_load_2d(&tmW2, &full[kb], st + S::NOPS * S::A_BYTES + S::W_BYTES, (kb0 + kb) * BK, n0);
+                tma_load_2d(&tmW, &full[kb], st + S::NOPS * S::A_BYTES, kb * BK, n0);
+                if (SPLIT == 3) tma_load_2d(&tmW2, &full[kb], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
             }
             pdl_wait();
             if (p.dbg) dbg_t1 = gtime_ns();
@@ -380,16 +324,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (kb >= npre) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], S::STAGE);
-                    tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, (kb0 + kb) * BK, n0);
-                    if (SPLIT == 3) tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, (kb0 + kb) * BK, n0);
+                    tma_load_2d(&tmW, &full[s], st + S::NOPS * S::A_BYTES, kb * BK, n0);
+                    if (SPLIT == 3) tma_load_2d(&tmW2, &full[s], st + S::NOPS * S::A_BYTES + S::W_BYTES, kb * BK, n0);
                 }
                 if (p.cv_cpk) {
-                    const int kg = kb0 + kb, tap = kg / p.cv_cpk, cc = (kg - tap * p.cv_cpk) * BK;
+                    const int tap = kb / p.cv_cpk, cc = (kb - tap * p.cv_cpk) * BK;
                     const int ky = tap / p.cv_ksz, kx = tap - ky * p.cv_ksz;
                     tma_load_im2col(&tmA, &full[s], st, cc, cv_w, cv_h, cv_n, kx, ky);
                     if (SPLIT == 3) tma_load_im2col(&tmA2, &full[s], st + S::A_BYTES, cc, cv_w, cv_h, cv_n, kx, ky);
                 } else {
-                    const int ak = (kb0 + kb) * BK + (int)blockIdx.x * p.a_block_k;
+                    const int ak = kb * BK + (int)blockIdx.x * p.a_block_k;
                     tma_load_2d(&tmA, &full[s], st, ak, m0);
                     if (SPLIT == 3) tma_load_2d(&tmA2, &full[s], st + S::A_BYTES, ak, m0);
                 }
@@ -417,26 +361,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             umma_commit(tmem_full);            // accumulator complete
         }
-    } else if (KS > 1 && kz > 0) {
-        // split-K peer: accumulator tile -> the leader's shared memory (thread = row, 32 columns), then one arrival per warp
-        cluster_wait();                                           // leader's barrier initialised (arrived long ago)
-        mbar_wait(tmem_full, 0);
-        tcgen05_fence_after();
-        const int q = warp & 3;
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), raw);
-        const uint32_t row_local = smem_u32(parts) + (uint32_t)(kz - 1) * PART_BYTES + (uint32_t)(q * 32 + lane) * (PSTR * 4);
-        const uint32_t row_remote = mapa_rank(row_local, 0);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-            st_cluster_f4(row_remote + i * 4, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]), __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(mapa_rank(smem_u32(part_full), 0));
     } else {
         pdl_wait();        // the epilogue reads the residual stream
-        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem, parts, KS - 1, part_full);
+        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem);
     }
-    if (KS > 1 && !(kz > 0 && warp >= 2)) cluster_wait();         // pairs with the arrive above (peer epilogue warps waited already)
     tcgen05_fence_before();
     __syncthreads();
     if (p.dbg && threadIdx.x == 0) {
@@ -570,8 +498,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            epilogue_tile<BN, EPI, TC>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, nullptr, 0, nullptr,
-                                       (uint32_t)((i >> 1) & 1));
+            epilogue_tile<BN, EPI, TC>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);              // all of this warp's tcgen05.ld of the buffer have completed
@@ -582,185 +509,6 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ LayerNorm-fused GEMM
-// C = epi( LN2(LN1(S)) . W^T ) for K = 256: the shared double LayerNorm of model/attention.py:242-259 is computed by the
-// CTA itself and written straight into the swizzled A tiles (no xn round trip through HBM, no separate LN launch).
-// Every n-tile CTA of an m-block recomputes the (cheap) LayerNorm of its 128 rows; the n-tile-0 CTA also stores the
-// fp32 residual stream x = LN1(S).  Same arithmetic, in the same order, as ln2_kernel (rowwise.cu) -> identical bits.
-struct LnParams {
-    const float* in;                        // S rows [M, 256]
-    const float* g1; const float* b1;       // nullable: first LN skipped
-    const float* g2; const float* b2;       // nullable: second LN skipped
-    float* x_out;                           // nullable: fp32 copy of the first-stage result (residual stream)
-};
-
-template <int BN> struct SmemLn {
-    static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2, NKB = 4;
-    static constexpr int TOTAL = NKB * (A_BYTES + W_BYTES) + 1024 + 256;
-};
-
-// LayerNorm of 4 rows at once (a row per warp pass, 8 elements per lane); same operation order per row as ln2_kernel
-// (rowwise.cu), so the results are bit-identical; the four shuffle chains are independent and hide each other's latency.
-TX_DEVINL void ln8x4(float (&v)[4][8], const float* g, const float* b) {
-    float s[4], q[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        s[i] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s[i] += v[i][k];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        s[i] *= (1.0f / 256);
-        q[i] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { const float d = v[i][k] - s[i]; q[i] = fmaf(d, d, q[i]); }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float rstd = 1.0f / sqrtf(q[i] * (1.0f / 256) + 1e-5f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[i][k] = (v[i][k] - s[i]) * rstd * g[k] + b[k];
-    }
-}
-
-// LayerNorm-prologue warps of tc_gemm_ln_kernel (warps 2 .. 2 + LN_WARPS - 1; warps 2 .. 5 also run the epilogue).  Measured at
-// B = 512 (8 branch graphs): 4 warps 142 ms, 16 warps 150 ms per generate vs 110 ms with separate ln2_kernel launches -- the
-// big CTAs cannot share an SM with the attention CTAs of other branches, and PDL hides the separate LayerNorm launch anyway.
-constexpr int LN_WARPS = 4;
-
-template <int BN, int EPI, typename TC>
-__global__ void __launch_bounds__(64 + 32 * LN_WARPS, 1)
-tc_gemm_ln_kernel(const __grid_constant__ CUtensorMap tmW, const TcParams p, const LnParams ln) {
-    using S = SmemLn<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_a = smem;                                   // [4 k-blocks][128 rows x 64] swizzled
-    uint8_t* smem_w = smem + S::NKB * S::A_BYTES;             // [4 k-blocks][BN rows x 64]
-    uint64_t* w_full = reinterpret_cast<uint64_t*>(smem_w + S::NKB * S::W_BYTES);
-    uint64_t* a_ready = w_full + S::NKB;
-    uint64_t* tmem_full = a_ready + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-
-    if (!p.late_trigger) pdl_launch_dependents();
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-        for (int s = 0; s < S::NKB; ++s) mbar_init(&w_full[s], 1);
-        mbar_init(a_ready, LN_WARPS);
-        mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
-
-    if (warp == 0) {
-        if (lane == 0) {                    // weights: all four k-blocks at once (they are L2-resident)
-            for (int kb = 0; kb < S::NKB; ++kb) {
-                mbar_expect_tx(&w_full[kb], S::W_BYTES);
-                tma_load_2d(&tmW, &w_full[kb], smem_w + kb * S::W_BYTES, kb * BK, n0);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
-            mbar_wait(a_ready, 0);
-            tcgen05_fence_after();
-            for (int kb = 0; kb < S::NKB; ++kb) {
-                mbar_wait(&w_full[kb], 0);
-                tcgen05_fence_after();
-                const uint32_t a_s = smem_u32(smem_a + kb * S::A_BYTES), w_s = smem_u32(smem_w + kb * S::W_BYTES);
-#pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                    umma_bf16(tmem_base, make_smem_desc(a_s + k * UMMA_K * 2), make_smem_desc(w_s + k * UMMA_K * 2), idesc, (kb | k) != 0);
-            }
-            umma_commit(tmem_full);
-        }
-    } else {
-        // ---------------- LayerNorm prologue: rows are dealt round-robin to the LN warps (row = 4 W g + W i + q), 4 rows per
-        // warp are normalised at once (independent shuffle chains) while the next 4 are in flight; lane owns 8 columns.
-        // Rows past M are left as they are in shared memory: an output row only depends on its own A row.
-        const int q = warp - 2;
-        const int col = lane * 8;
-        const int kb = lane >> 3, chunk = lane & 7;
-        const int nrow = p.M - m0 < BM ? p.M - m0 : BM;
-        constexpr int GR = 4 * LN_WARPS;                   // rows per group
-        const int ngrp = (nrow + GR - 1) / GR;
-        float g1[8], b1[8], g2[8], b2[8];
-        if (ln.g1) { ld8(ln.g1 + col, g1); ld8(ln.b1 + col, b1); }
-        if (ln.g2) { ld8(ln.g2 + col, g2); ld8(ln.b2 + col, b2); }
-        float v[4][8], nx[4][8];
-        auto load_group = [&](int g, float (&dst)[4][8]) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = GR * g + LN_WARPS * i + q;
-                if (r < nrow) ld8cg(ln.in + (size_t)(m0 + r) * 256 + col, dst[i]);
-                else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) dst[i][k] = 0.f;
-                }
-            }
-        };
-        load_group(0, v);
-        for (int g = 0; g < ngrp; ++g) {
-            if (g + 1 < ngrp) load_group(g + 1, nx);
-            if (ln.g1) ln8x4(v, g1, b1);
-            if (ln.x_out && blockIdx.x == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = GR * g + LN_WARPS * i + q;
-                    if (r < nrow) {
-                        st4(ln.x_out + (size_t)(m0 + r) * 256 + col, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
-                        st4(ln.x_out + (size_t)(m0 + r) * 256 + col + 4, make_float4(v[i][4], v[i][5], v[i][6], v[i][7]));
-                    }
-                }
-            }
-            if (ln.g2) ln8x4(v, g2, b2);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = GR * g + LN_WARPS * i + q;
-                if (r < nrow) {
-                    bf16* dst = reinterpret_cast<bf16*>(smem_a + kb * S::A_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-                    st4(dst, make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
-                    st4(dst + 4, make_float4(v[i][4], v[i][5], v[i][6], v[i][7]));
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[i][k] = nx[i][k];
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to the MMA
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_ready)) : "memory");
-        if (warp < 6) epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem_a);
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (p.late_trigger) pdl_launch_dependents();
-    if (warp == 1) {
-        tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
     }
 }
 
@@ -876,30 +624,6 @@ cudaError_t launch_cfg2(const CUtensorMap& a, const CUtensorMap& w, const CUtens
     return launch_pdl(PDL_GEMM, kern, grid, dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
 }
 
-// split-K launch: grid z = cluster of KS CTAs; programmatic dependent launch like every other decode kernel
-template <int EPI, typename TC, int KS>
-cudaError_t launch_cfg_ks(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
-                          cudaStream_t st) {
-    using S = Smem<32, 1, 0>;
-    constexpr int SMEM = S::TOTAL + (KS - 1) * PART_BYTES;
-    static bool attr_set = false;
-    auto kern = tc_gemm_kernel<32, EPI, TC, 1, 0, KS>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((p.N + 31) / 32, (p.M + BM - 1) / BM, KS); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = KS;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = ((g_texocr_pdl >> PDL_GEMM) & 1) ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, a, w, a2, w2, p);
-}
-
 template <int BN, int EPI, typename TC, int SPLIT>
 cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
                               long tiles, cudaStream_t st) {
@@ -915,8 +639,7 @@ cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         attr_set = true;
     }
-    unsigned grid = (unsigned)std::min<long>(tiles, sms);
-    if (g_tc_tiles_per_cta > 0 && tiles < 296) grid = (unsigned)std::min<long>(sms, (tiles + g_tc_tiles_per_cta - 1) / g_tc_tiles_per_cta);
+    const unsigned grid = (unsigned)std::min<long>(tiles, sms);
     TcParams pp = p;
     pp.stages = g_tc_persistent_stages > 0 ? std::max(2, std::min(g_tc_persistent_stages, S::STAGES)) : S::STAGES;
     const size_t smem = (size_t)S::TOTAL - (size_t)(S::STAGES - pp.stages) * S::STAGE;
@@ -929,25 +652,9 @@ cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     // many tiles (encoder / teacher-forced sizes): shallow pipeline, several CTAs per SM; few tiles: deep pipeline
     const long tiles = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
     if constexpr (BN >= 64) {
-        if (g_tc_persistent && tiles >= g_tc_persist_min_tiles && !p.a_block_k) return launch_persistent<BN, EPI, TC, SPLIT>(a, w, a2, w2, p, tiles, st);
+        if (g_tc_persistent && tiles >= 296 && !p.a_block_k) return launch_persistent<BN, EPI, TC, SPLIT>(a, w, a2, w2, p, tiles, st);
     }
     if (SPLIT == 1 && BN >= 64 && tiles >= 592) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
-    if constexpr (SPLIT == 1 && BN == 32 && (EPI == EPI_GLU_RES || EPI == EPI_BIAS_RES)) {
-        // latency-bound decode GEMMs with a long K loop: split K over a 2- / 4-CTA cluster (4 k-blocks per CTA = one ring round)
-        // g_tc_split_k bit 0: K = 512 / 1024 (measured slower than the plain kernel); bit 1: K = 2048 (the folded out-projection of the
-        // absorbed attention: 32 k-blocks in one CTA are 14 us, 4 x 8 k-blocks over a cluster with a DSMEM reduction are shorter)
-        if ((g_tc_split_k & 1) && tiles < 120) {
-            if (p.K == 1024) return launch_cfg_ks<EPI, TC, 4>(a, w, a2, w2, p, st);
-            if (p.K == 512) return launch_cfg_ks<EPI, TC, 2>(a, w, a2, w2, p, st);
-        }
-        if ((g_tc_split_k & 2) && tiles < 120 && p.K == 2048) return launch_cfg_ks<EPI, TC, 4>(a, w, a2, w2, p, st);
-    }
-    if (SPLIT == 1 && g_tc_shallow_ring) return launch_cfg2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, st);
-    if constexpr (SPLIT == 1 && BN == 32 && EPI == EPI_GLU_RES) {
-        // K = 2048 (folded out-projection of the absorbed attention): 32 k-blocks per CTA; an 8-stage ring (160 KB) keeps twice the
-        // bytes in flight per CTA (the grid is 64 CTAs, one per SM anyway)
-        if (g_tc_deep_ring && p.K >= 2048) return launch_cfg2<BN, EPI, TC, SPLIT, 8>(a, w, a2, w2, p, st);
-    }
     return launch_cfg2<BN, EPI, TC, SPLIT, 0>(a, w, a2, w2, p, st);
 }
 
@@ -969,51 +676,6 @@ cudaError_t launch_epi(const GemmArgs& g, const CUtensorMap& a, const CUtensorMa
 }
 
 }  // namespace
-
-namespace {
-template <int BN, int EPI, typename TC>
-cudaError_t launch_ln_cfg(const CUtensorMap& w, const TcParams& p, const LnParams& ln, cudaStream_t st) {
-    using S = SmemLn<BN>;
-    static bool attr_set = false;
-    auto kern = tc_gemm_ln_kernel<BN, EPI, TC>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    return launch_pdl(PDL_GEMM, kern, grid, dim3(64 + 32 * LN_WARPS), (size_t)S::TOTAL, st, w, p, ln);
-}
-template <int BN>
-cudaError_t launch_ln_epi(const GemmArgs& g, const CUtensorMap& w, const TcParams& p, const LnParams& ln, cudaStream_t st) {
-    switch (g.epi) {
-        case EPI_STORE:
-            if (g.dt_c == DT_F32) return launch_ln_cfg<BN, EPI_STORE, float>(w, p, ln, st);
-            return launch_ln_cfg<BN, EPI_STORE, bf16>(w, p, ln, st);
-        case EPI_GEGLU: return launch_ln_cfg<BN, EPI_GEGLU, bf16>(w, p, ln, st);
-        default: return cudaErrorInvalidValue;
-    }
-}
-}  // namespace
-
-// GEMM whose A operand is LN2(LN1(S)) computed in the kernel (K must be 256).  g.A is ignored.
-cudaError_t launch_gemm_tc_ln(const GemmArgs& g, const float* s_in, const float* g1, const float* b1, const float* g2,
-                              const float* b2, float* x_out, cudaStream_t st) {
-    if (g.M <= 0) return cudaSuccess;
-    if (g.K != 256 || g.N % 8 != 0 || g.ldw % 8 != 0 || (g.epi != EPI_STORE && g.epi != EPI_GEGLU)) return cudaErrorInvalidValue;
-    const long mt = (g.M + BM - 1) / BM;
-    int bn = 128;
-    if (mt * ((g.N + 127) / 128) < g_tc_min_ctas) bn = 64;
-    if (mt * ((g.N + 63) / 64) < g_tc_min_ctas && g.N >= 64) bn = 32;
-    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1};
-    LnParams ln{s_in, g1, b1, g2, b2, x_out};
-    CUtensorMap w;
-    cudaError_t e;
-    if ((e = get_map(g.W, g.N, g.K, g.ldw, bn, &w)) != cudaSuccess) return e;
-    if (bn == 128) return launch_ln_epi<128>(g, w, p, ln, st);
-    if (bn == 64) return launch_ln_epi<64>(g, w, p, ln, st);
-    return launch_ln_epi<32>(g, w, p, ln, st);
-}
 
 bool tc_gemm_supported(const GemmArgs& g) {
     if (g.dt_a != DT_BF16 || g.conv) return false;

@@ -8,11 +8,6 @@
 // FFMA kernel otherwise.
 bool tc_gemm_supported(const GemmArgs& g);
 cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
-// Same GEMM with the A operand = LN2(LN1(s_in)) computed inside the kernel (K = 256; shared double LayerNorm of
-// model/attention.py:242-259).  g1/b1 or g2/b2 may be null to skip a stage; x_out (nullable) receives the fp32 first-stage result.
-cudaError_t launch_gemm_tc_ln(const GemmArgs& g, const float* s_in, const float* g1, const float* b1, const float* g2,
-                              const float* b2, float* x_out, cudaStream_t st);
-
 // Shared TMA helper (driver entry point resolved through the runtime; no libcuda link): cached tensor map of a 2-D bf16
 // matrix [rows, cols] (row stride ld elements), box = box_rows x box_cols, optional 128-byte swizzle, zero OOB fill.
 cudaError_t tma_map_2d_bf16(const void* ptr, long rows, int cols, long ld, int box_rows, int box_cols, int swizzle128,
