@@ -13,7 +13,8 @@ T = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 calls = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 opts = sys.argv[5] if len(sys.argv) > 5 else ""
-img = synth.synth_images(B, 64, 384, seed=21).cuda()
+DECODE_ONLY = os.environ.get("SLOT_PROBE_DECODE_ONLY", "0") == "1"      # time decoder.generate over a precomputed memory (any B)
+img = synth.synth_images(min(B, 512), 64, 384, seed=21).cuda()
 models, sd = [], None
 for i in range(n):
     m = create_model(default_config(), precision="bf16")
@@ -28,16 +29,27 @@ for i in range(n):
     e.set_option("attn_trace", 1)
     models.append(m)
 bar = threading.Barrier(n + 1)
+enc = start = None
+if DECODE_ONLY:
+    e512 = models[0].encoder(img)
+    enc = torch.cat([e512] * max(1, B // e512.shape[0]), 0).contiguous()
+    start = torch.full((enc.shape[0], 1), models[0].dims.bos, dtype=torch.long, device="cuda")
+
+def run(m):
+    if DECODE_ONLY:
+        m.decoder.generate(start_tokens=start, eos_tok=None, max_len=T, enc=enc)
+    else:
+        m.generate(img, T)
 
 def work(i):
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
         for _ in range(2):
-            models[i].generate(img, T)
+            run(models[i])
         st.synchronize()
         bar.wait()
         for _ in range(calls):
-            models[i].generate(img, T)
+            run(models[i])
         st.synchronize()
     bar.wait()
 

@@ -88,6 +88,11 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
             LAUNCH(KC_DEC_GEMM_Q, 1, (double)rows * 256 * e + 2048.0 * 256 * e + (double)rows * 2048 * e, gemm_flops(gc), run_gemm(h, gc, st));
             AttnAbsArgs ab{};
             ab.q = qa; ab.ldq = 2048; ab.latent = h->dec_enc; ab.latent_rows = h->crosskv_rows; ab.k_off = d_enc_off + row0; ab.o = ca; ab.ldo = 2048; ab.batch = rows;
+            // equal memory lengths (B x max_s tokens in total <=> every sequence has max_s): sequence b's rows start at b * max_s
+            if ((long)B * max_s == (long)h->crosskv_rows) {
+                ab.uni_nk = max_s;
+                ab.latent = (const char*)h->dec_enc + (size_t)row0 * max_s * 256 * e; ab.latent_rows = (long)rows * max_s;
+            }
             if (h->attn_trace_on && h->attn_trace.p && 2 * l + 1 < 8) {
                 ab.trace = h->attn_trace.as<unsigned long long>() + (size_t)branch * 3 * 2048; ab.trace_step = step; ab.trace_k = 2 * l + 1;
                 ab.dbg = h->attn_trace.as<unsigned long long>() + (size_t)MAX_BRANCH * 3 * 2048 + 8;

@@ -196,6 +196,7 @@ struct AttnAbsArgs {
     const void* q; int ldq;
     const void* latent; long latent_rows;
     const int* k_off;
+    int uni_nk;                   // cross: > 0 when every sequence has uni_nk memory tokens laid out back to back FROM ROW 0 OF `latent` (k_off[b] = b * uni_nk)
     const void* znew; int ldz; int tcap; const int* step;
     void* o; int ldo;
     int batch;
