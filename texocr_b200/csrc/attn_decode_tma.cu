@@ -401,292 +401,9 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int units = a.batch;
     // cross: the producer only reads the encoder memory and the token offsets, both written before the generate loop started
     if (SELF || warp != 0) pdl_wait();
-
-    const int units = a.batch * 4;
-    const int t = SELF ? ldcg_i32(a.step) : 0;
-    unsigned long long* tr = nullptr;
-    if (a.trace && threadIdx.x == 32) {
-        const int ts = min(ldcg_i32(a.trace_step), 255);
-        tr = a.trace + (size_t)ts * 8 + a.trace_k;
-        atomicMin(tr, t_entry);
-        atomicMin(tr + 2048, gtime());
-    }
-
-    if (warp == 0) {
-        // ------------------------------------------------------------ producer
-        if (lane == 0) {
-            int it = 0;
-            const uint64_t pol = l2_evict_first_policy();
-            asm volatile("fence.proxy.async.global;" ::: "memory");     // K/V rows were appended by generic-proxy stores of earlier kernels
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int b = u >> 2, hp = u & 3;
-                int row0, nk;
-                if (SELF) { row0 = b * a.row_b; nk = t; }
-                else { row0 = ldcg_i32(a.k_off + b); nk = ldcg_i32(a.k_off + b + 1) - row0; }
-                const int nchunk = (nk + CH - 1) / CH;
-                const int h0 = 2 * hp, h1 = h0 + 1;
-                const int kc0 = a.col0 + h0 * a.col_h, kc1 = a.col0 + h1 * a.col_h;
-                const int r0 = row0 + h0 * a.row_h, r1 = row0 + h1 * a.row_h;
-                for (int c = 0; c < nchunk; ++c, ++it) {
-                    const int s = it % NS, ph = (it / NS) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* st = ring + s * STAGE;
-                    const int left = nk - c * CH;
-                    const int rc = c * CH;
-                    if (left >= CH || (a.full_tail & 1)) {
-                        mbar_expect_tx(&full[s], STAGE);
-                        tma_load_2d(&tm, &full[s], st, kc0, r0 + rc, pol);
-                        tma_load_2d(&tm, &full[s], st + HTILE, kc1, r1 + rc, pol);
-                        tma_load_2d(&tm, &full[s], st + 2 * HTILE, kc0 + a.v_col, r0 + rc, pol);
-                        tma_load_2d(&tm, &full[s], st + 3 * HTILE, kc1 + a.v_col, r1 + rc, pol);
-                    } else {               // tail: 4-row boxes, at most 3 rows fetched beyond the sequence
-                        const int n4 = (left + 3) >> 2;
-                        mbar_expect_tx(&full[s], n4 * 4 * 512);
-                        for (int j = 0; j < n4; ++j) {
-                            tma_load_2d(&tm4, &full[s], st + j * 512, kc0, r0 + rc + 4 * j, pol);
-                            tma_load_2d(&tm4, &full[s], st + HTILE + j * 512, kc1, r1 + rc + 4 * j, pol);
-                            tma_load_2d(&tm4, &full[s], st + 2 * HTILE + j * 512, kc0 + a.v_col, r0 + rc + 4 * j, pol);
-                            tma_load_2d(&tm4, &full[s], st + 3 * HTILE + j * 512, kc1 + a.v_col, r1 + rc + 4 * j, pol);
-                        }
-                    }
-                }
-            }
-        }
-        return;
-    }
-    // ---------------------------------------------------------------- consumers: warp 1 -> head 2*hp, warp 2 -> head 2*hp+1
-    const int hd = warp - 1;
-    const int g = lane >> 2, tq = lane & 3;             // mma fragment coordinates: row group / thread-in-group
-    const bool row0_lane = g == 0;                       // the single query lives in row 0 of the 16-row A operand
-    // ldmatrix address pieces (thread i supplies row i&7 of matrix i>>3)
-    const int lm_r = lane & 7, lm_m = lane >> 3;
-    int it = 0;
-    // header: q, this step's k and v for (b, head); lanes 0..3 hold the words of their fragment positions
-    uint32_t q_w[8], kn_w[8], vn_w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { q_w[i] = 0; kn_w[i] = 0; vn_w[i] = 0; }
-    auto load_header = [&](int u) {
-        const int b = u >> 2, h = (u & 3) * 2 + hd;
-        if (row0_lane) {
-            const uint32_t* qp = reinterpret_cast<const uint32_t*>(a.q + (size_t)b * a.ldq + h * 64);
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { q_w[2 * s] = ldcg_u32(qp + 8 * s + tq); q_w[2 * s + 1] = ldcg_u32(qp + 8 * s + 4 + tq); }   // dims 16s+2t, 16s+8+2t
-            if (SELF) {
-                const uint32_t* kp = reinterpret_cast<const uint32_t*>(a.knew + (size_t)b * a.ldnew + h * 64);
-                const uint32_t* vp = reinterpret_cast<const uint32_t*>(a.vnew + (size_t)b * a.ldnew + h * 64);
-#pragma unroll
-                for (int s = 0; s < 4; ++s) { kn_w[2 * s] = ldcg_u32(kp + 8 * s + tq); kn_w[2 * s + 1] = ldcg_u32(kp + 8 * s + 4 + tq); }
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) vn_w[nt] = ldcg_u32(vp + 4 * nt + tq);                            // dims 8nt+2t, +1
-            }
-        }
-    };
-    if ((int)blockIdx.x < units) load_header(blockIdx.x);
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int b = u >> 2, h = (u & 3) * 2 + hd;
-        // A fragments of q (scaled by 0.125, exact in bf16): a0 = (row g, k 2t..), a2 = (row g, k 2t+8..); rows 8..15 zero
-        uint32_t qa[8];
-        float kn_f[16], vn_f[16], q_f[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float2 f = unpack_bf16x2(q_w[i]);
-            q_f[2 * i] = f.x * SCALE; q_f[2 * i + 1] = f.y * SCALE;
-            qa[i] = row0_lane ? pack_bf16x2(q_f[2 * i], q_f[2 * i + 1]) : 0u;
-            if (SELF) {
-                const float2 kf = unpack_bf16x2(kn_w[i]), vf = unpack_bf16x2(vn_w[i]);
-                kn_f[2 * i] = kf.x; kn_f[2 * i + 1] = kf.y; vn_f[2 * i] = vf.x; vn_f[2 * i + 1] = vf.y;
-            }
-        }
-        if (SELF && lane < 8) {      // append this step's k / v row to the cache (16 B per lane), K at h*64, V at 512 + h*64
-            const uint4 kr = ldcg_u4(a.knew + (size_t)b * a.ldnew + h * 64 + lane * 8);
-            const uint4 vr = ldcg_u4(a.vnew + (size_t)b * a.ldnew + h * 64 + lane * 8);
-            bf16* row = a.cache + ((size_t)b * a.row_b + (size_t)h * a.row_h + t) * a.ld + a.col0 + h * a.col_h + lane * 8;
-            *reinterpret_cast<uint4*>(row) = kr;
-            *reinterpret_cast<uint4*>(row + a.v_col) = vr;
-            // the next step reads this row through the async proxy (TMA): order the generic-proxy stores against it
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-        }
-        const int un = u + gridDim.x;
-        if (un < units) load_header(un);          // prefetch the next unit's header while this one streams
-        int nk;
-        if (SELF) nk = t; else nk = ldcg_i32(a.k_off + b + 1) - ldcg_i32(a.k_off + b);
-        const int nchunk = (nk + CH - 1) / CH;
-        float m = -INFINITY, l = 0.f;
-        float o[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
-        for (int c = 0; c < nchunk; ++c, ++it) {
-            const int s = it % NS, ph = (it / NS) & 1;
-            mbar_wait(&full[s], ph);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t kt = smem_u32(ring + s * STAGE + hd * HTILE);
-            const uint32_t vt = kt + 2 * HTILE;
-            // ---- S = q.K^T : 2 n-tiles of 8 keys, 4 k-steps of 16 dims
-            float sc[2][4];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-                const int r = 8 * j + lm_r;
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    uint32_t b0, b1, b2, b3;
-                    ldsm_x4(kt + r * 128 + (((4 * s2 + lm_m) ^ (r & 7)) << 4), b0, b1, b2, b3);
-                    mma_bf16(sc[j], qa[4 * s2], 0u, qa[4 * s2 + 1], 0u, b0, b1);
-                    mma_bf16(sc[j], qa[4 * s2 + 2], 0u, qa[4 * s2 + 3], 0u, b2, b3);
-                }
-            }
-            // row 0 scores: lane tq holds keys 8j+2tq, 8j+2tq+1
-            const int kbase = c * CH + 2 * tq;
-            float p[2][2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                p[j][0] = (kbase + 8 * j < nk) ? sc[j][0] : -INFINITY;
-                p[j][1] = (kbase + 8 * j + 1 < nk) ? sc[j][1] : -INFINITY;
-            }
-            float cm = fmaxf(fmaxf(p[0][0], p[0][1]), fmaxf(p[1][0], p[1][1]));
-            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
-            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
-            const float mn = fmaxf(m, cm);                 // finite on row 0: every stage holds at least one valid key
-            const float corr = __expf(m - mn);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) { p[j][0] = __expf(p[j][0] - mn); p[j][1] = __expf(p[j][1] - mn); }
-            l = l * corr + (p[0][0] + p[0][1]) + (p[1][0] + p[1][1]);
-            m = mn;
-            const uint32_t pa0 = row0_lane ? pack_bf16x2(p[0][0], p[0][1]) : 0u;     // keys 2t, 2t+1
-            const uint32_t pa2 = row0_lane ? pack_bf16x2(p[1][0], p[1][1]) : 0u;     // keys 8+2t, 9+2t
-            // ---- O = O*corr + P.V : 8 n-tiles of 8 dims, one k-step of 16 keys
-            const int vr = (lane & 7) + 8 * ((lane >> 3) & 1);
-            // V rows past the end of the sequence were fetched (<= 3 of them) or are stale: they carry p = 0, but 0 * NaN = NaN,
-            // so their halves of the B fragments (keys 2t, 2t+1 | 2t+8, 2t+9) are cleared in the last, partial stage.
-            uint32_t vm_lo = 0xffffffffu, vm_hi = 0xffffffffu;
-            if (nk - c * CH < CH) {
-                const int k0 = c * CH + 2 * tq;
-                vm_lo = (k0 < nk ? 0x0000ffffu : 0u) | (k0 + 1 < nk ? 0xffff0000u : 0u);
-                vm_hi = (k0 + 8 < nk ? 0x0000ffffu : 0u) | (k0 + 9 < nk ? 0xffff0000u : 0u);
-            }
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4_t(vt + vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4), b0, b1, b2, b3);
-                b0 &= vm_lo; b2 &= vm_lo; b1 &= vm_hi; b3 &= vm_hi;
-                o[2 * np][0] *= corr; o[2 * np][1] *= corr;
-                o[2 * np + 1][0] *= corr; o[2 * np + 1][1] *= corr;
-                mma_bf16(o[2 * np], pa0, 0u, pa2, 0u, b0, b1);
-                mma_bf16(o[2 * np + 1], pa0, 0u, pa2, 0u, b2, b3);
-            }
-            // The stage is about to be handed back to the TMA producer: order this warp's generic-proxy reads (ldmatrix) before
-            // the async-proxy overwrite.  Without the cross-proxy fence the refill of a reused stage occasionally overtook the
-            // last V reads (1-3 % error in one head of one sequence, a few times per thousand launches under concurrency).
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-        if (SELF) {
-            // this step's own key / value: dot over the lane's 16 dims, folded over the 4 lanes of row 0
-            float d = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) d = fmaf(q_f[i], kn_f[i], d);
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            const float mn = fmaxf(m, d);
-            const float corr = __expf(m - mn), pn = __expf(d - mn);
-            l = l * corr;
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                o[nt][0] = fmaf(pn, vn_f[2 * nt], o[nt][0] * corr);
-                o[nt][1] = fmaf(pn, vn_f[2 * nt + 1], o[nt][1] * corr);
-            }
-            l += (tq == 0) ? pn : 0.f;         // l is a per-lane partial, summed over the 4 lanes below
-        }
-        l += __shfl_xor_sync(0xffffffffu, l, 1);
-        l += __shfl_xor_sync(0xffffffffu, l, 2);
-        if (row0_lane) {
-            const float inv = 1.0f / l;
-            uint32_t* op = reinterpret_cast<uint32_t*>(a.o + (size_t)b * a.ldo + h * 64);
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) op[4 * nt + tq] = pack_bf16x2(o[nt][0] * inv, o[nt][1] * inv);
-        }
-    }
-    if (tr) atomicMax(tr + 4096, gtime());
-}
-
-
-// ------------------------------------------------------------------------------------------------ absorbed ("latent") attention
-// Decode-step attention of the bf16 generate loop with the key / value projections absorbed into the query and output
-// projections.  For a head h with key / value weights Wk_h, Wv_h [64 x 256] and latent rows z_j [256] (cross-attention:
-// z_j = encoder memory token j; self-attention: z_j = the layer's LayerNorm'd input at position j, i.e. what the reference
-// feeds to to_k / to_v, model/attention.py:114-126):
-//   q_h . K_h[j] = q_h . (Wk_h z_j) = (q_h Wk_h) . z_j                   Q'_h = q_h Wk_h       (256 wide; folded query GEMM)
-//   sum_j p_h[j] V_h[j] = (sum_j p_h[j] z_j) Wv_h^T                      C_h = P_h . Z         (256 wide; folded out-projection)
-// so all 8 heads of a sequence stream the SAME [n, 256] bf16 latent rows instead of their own [n, 64 | 64] K/V slices:
-// 512 bytes per key and layer instead of 2,048 -- 4x less HBM traffic for the loop's dominant stream, and the self-attention
-// cache holds 256 instead of 1,024 values per position (model/attention.py:148-173 computes the left-hand sides).
-// Work unit = sequence.  The 8 heads are rows 0..7 of the 16-row mma.sync A operand.  Stage = 16 latent rows x 256 columns as
-// four 64-column TMA boxes (128B swizzle), 8 KB.  Four consumer warps, warp w owns column block w: it computes the partial
-// scores Q'[:, 64w..64w+63] . Z[:, 64w..]^T (8 MMAs, k = 64), the partials are summed through shared memory (one named barrier per
-// stage, double-buffered), every warp runs the identical online softmax, and accumulates C[:, 64w..64w+63] += P . Z[:, 64w..] (8 MMAs).
-// Self-attention: this step's own latent row (position t) is written into the last stage by the consumers (it is key t of
-// that stage) and appended to the cache for the following steps.
-constexpr int AW = 4;                       // consumer warps = 64-column blocks of a latent row
-constexpr int ANS = 5;                      // ring stages of the absorbed kernel (40 KB)
-constexpr int XROW = 40;                    // floats per (warp, head) row of the score exchange: 32 keys, padded so that a half-warp's float2 accesses hit 32 distinct banks
-struct AbsArgs {
-    const bf16* q; int ldq;            // [batch, ldq]: head h at h*256 (absorbed query, unscaled)
-    const int* k_off;                  // cross: token offsets [batch + 1] into the latent matrix the tensor maps cover
-    int uni_nk;                        // cross: > 0 = every sequence has this many memory tokens and sequence b starts at row b * uni_nk (k_off is not read)
-    const bf16* znew; int ldz;         // self: this step's latent rows [batch, ldz]
-    bf16* cache; int tcap;             // self: latent cache [batch][tcap][256] (row b*tcap + j); the tensor maps cover it
-    const int* step;                   // self: positions already cached (= index of this step's row)
-    bf16* o; int ldo;                  // [batch, ldo]: head h at h*256
-    int batch;
-    unsigned long long* trace; const int* trace_step; int trace_k;
-    unsigned long long* dbg;           // debug: sums over CTAs of [wait for predecessor, first data, stage loop, epilogue] ns + count
-};
-
-template <bool SELF, int MINB>
-__global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __grid_constant__ CUtensorMap tm,
-                                                                 const __grid_constant__ CUtensorMap tm4, const AbsArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float* xbuf = reinterpret_cast<float*>(ring + ANS * STAGE);           // [2][AW][8 heads][XROW] partial scores of two stages (32 keys)
-    uint64_t* full = reinterpret_cast<uint64_t*>(xbuf + 2 * AW * 8 * XROW);
-    uint64_t* empty = full + ANS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    pdl_launch_dependents();
-    const unsigned long long t_entry = a.trace ? gtime() : 0ull;
-    const unsigned long long t_entry0 = a.dbg ? gtime() : 0ull;
-    if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm4) : "memory");
-        for (int s = 0; s < ANS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], AW); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
     const int units = a.batch;
-    // The producer thread does not wait for the predecessor grid (the query GEMM) before it starts streaming:
-    //   cross: it only reads the encoder memory and the token offsets, both written before the generate loop started;
-    //   self : it reads the step counter -- written LAST by a decode step (token kernel), after every kernel that appended cache rows
-    //          of that step has completed -- so whatever value v it sees, rows 0 .. v-1 of every sequence are complete and
-    //          visible; it prefetches up to a ring of full 16-row boxes below v, then waits and reads the true t >= v.
-    int pre_it = 0;
-    if (SELF && threadIdx.x == 0 && (int)blockIdx.x < units) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");     // cache rows were appended by generic-proxy stores of earlier steps
-        const int v = ldcg_i32(a.step);
-        const int nfull = min(v / CH, ANS);
-        const int row0 = (int)blockIdx.x * a.tcap;
-        for (int c = 0; c < nfull; ++c) {
-            uint8_t* st = ring + c * STAGE;
-            mbar_expect_tx(&full[c], STAGE);
-#pragma unroll
-            for (int cb = 0; cb < 4; ++cb) tma_load_2d_nohint(&tm, &full[c], st + cb * HTILE, 64 * cb, row0 + c * CH);
-        }
-        pre_it = nfull;
-    }
-    if (SELF || warp != 0) pdl_wait();
     const int t = SELF ? ldcg_i32(a.step) : 0;
     unsigned long long* tr = nullptr;
     if (a.trace && threadIdx.x == 32) {
