@@ -103,6 +103,16 @@ TX_DEVINL float2 lds_f2(uint32_t addr) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
     return v;
 }
+TX_DEVINL void sts_f1(uint32_t addr, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory"); }
+TX_DEVINL void sts_h1(uint32_t addr, float x) {
+    const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
+}
+TX_DEVINL uint32_t lds_u1(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 TX_DEVINL void sts_u4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -449,13 +459,15 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
     const int g = lane >> 2, tq = lane & 3;               // fragment row (= head) / thread-in-group
     const int lm_r = lane & 7, lm_m = lane >> 3;
     const uint32_t ring_u32 = smem_u32(ring), xbuf_u32 = smem_u32(xbuf);
-    uint32_t off_qk[2][2], off_pv[4];         // swizzled ldmatrix offsets inside a 16 x 64 tile: the same for every stage
+    // Both contractions put the KEYS / latent columns on the 16-row M side of mma.sync.m16n8k16 and the 8 heads on its 8-wide N
+    // side, so no MMA row is padding:  S^T[16 keys x 8 heads] = Z[16 keys x 16 cols] . Q'^T[16 cols x 8 heads]  (A = Z by ldmatrix),
+    //                                  C^T[16 cols x 8 heads] += Z^T[16 cols x 16 keys] . P^T[16 keys x 8 heads] (A = Z by ldmatrix.trans).
+    // Swizzled ldmatrix offsets inside a 16 x 64 tile, the same for every stage.  Matrix m of an x4 load is addressed by lanes 8m..8m+7:
+    //   scores, k-step ks: m0 = keys 0-7 / chunk 2ks, m1 = keys 8-15 / chunk 2ks, m2 = keys 0-7 / chunk 2ks+1, m3 = keys 8-15 / chunk 2ks+1  (= a0..a3)
+    //   P.Z, m-tile mt   : the same four 8 x 8 blocks, transposed on load: (m0, m2, m1, m3) = (a0, a1, a2, a3)
+    uint32_t off_z[4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) { const int r = 8 * j + lm_r; off_qk[j][s2] = r * 128 + (((4 * s2 + lm_m) ^ (r & 7)) << 4); }
-#pragma unroll
-    for (int np = 0; np < 4; ++np) { const int vr = (lane & 7) + 8 * ((lane >> 3) & 1); off_pv[np] = vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4); }
+    for (int ks = 0; ks < 4; ++ks) { const int r = (lm_m & 1) * 8 + lm_r; off_z[ks] = r * 128 + (((2 * ks + (lm_m >> 1)) ^ (r & 7)) << 4); }
     int it = 0;
     uint32_t qn[8];
     auto load_header = [&](int u) {       // words of row g, columns 64cw..: k-step s holds dims 16s+2t,+1 and 16s+8+2t,+1
@@ -488,9 +500,9 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         else nk = ldcg_i32(a.k_off + u + 1) - ldcg_i32(a.k_off + u);
         const int nchunk = (nk + CH - 1) / CH;
         float m = -INFINITY, l = 0.f;
-        float o[8][2];
+        float o[4][4];       // m-tile mt (columns 16mt + g, 16mt + g + 8 of the warp's block) x heads (2tq, 2tq + 1)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = 0.f; }
+        for (int mt = 0; mt < 4; ++mt) { o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f; }
         // Two stages (32 keys) per iteration: one score exchange / barrier / softmax update for both, two independent MMA chains.
         for (int c = 0; c < nchunk; c += 2) {
             const bool two = c + 1 < nchunk;
@@ -513,30 +525,33 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
                 if (lane < 8) sts_u4(kts[two ? 1 : 0] + r * 128 + ((lane ^ (r & 7)) << 4), zrow);
                 __syncwarp();
             }
-            // ---- partial S = Q'[:, block] . Z[:, block]^T : rows = heads; per stage 2 n-tiles of 8 keys, 4 k-steps of 16 columns
-            float sc[2][2][2];
+            // ---- partial S^T = Z[:, block] . Q'[:, block]^T : per stage one 16-key m-tile, 4 k-steps of 16 columns, N = the 8 heads
+            float sc[2][4];      // (key g, head 2tq), (key g, head 2tq+1), (key g+8, head 2tq), (key g+8, head 2tq+1)
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 2; ++q) {
+                sc[q][0] = sc[q][1] = sc[q][2] = sc[q][3] = 0.f;
+                if (q == 0 || two) {
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    sc[q][j][0] = sc[q][j][1] = 0.f;
-                    if (q == 0 || two) {
-#pragma unroll
-                        for (int s2 = 0; s2 < 2; ++s2) {
-                            uint32_t b0, b1, b2, b3;
-                            ldsm_x4(kts[q] + off_qk[j][s2], b0, b1, b2, b3);
-                            mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2], qa[4 * s2 + 1], b0, b1);
-                            mma_bf16_top(sc[q][j][0], sc[q][j][1], qa[4 * s2 + 2], qa[4 * s2 + 3], b2, b3);
-                        }
+                    for (int ks = 0; ks < 4; ++ks) {
+                        uint32_t a0, a1, a2, a3;
+                        ldsm_x4(kts[q] + off_z[ks], a0, a1, a2, a3);
+                        mma_bf16(sc[q], a0, a1, a2, a3, qa[2 * ks], qa[2 * ks + 1]);
                     }
                 }
-            // exchange: row g (= head g), lane tq holds keys 16q+8j+2tq, +1
-            const uint32_t xb = xbuf_u32 + (xiter & 1) * (AW * 8 * XROW * 4) + (g * XROW + 2 * tq) * 4;
+            }
+            // exchange buffer: [warp][head][key of the iteration]; this thread READS row g (= head g), keys 16q+8j+2tq, +1 ...
+            const uint32_t xbase = xbuf_u32 + (xiter & 1) * (AW * 8 * XROW * 4);
+            const uint32_t xb = xbase + (g * XROW + 2 * tq) * 4;
             ++xiter;
+            // ... and WRITES its partials for heads 2tq, 2tq+1 and keys g, g+8 of both stages
+            const uint32_t xw = xbase + cw * (8 * XROW * 4) + (2 * tq * XROW + g) * 4;
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) sts_f2(xb + cw * (8 * XROW * 4) + (16 * q + 8 * j) * 4, sc[q][j][0], sc[q][j][1]);
+            for (int q = 0; q < 2; ++q) {
+                sts_f1(xw + (16 * q) * 4, sc[q][0]);
+                sts_f1(xw + (XROW + 16 * q) * 4, sc[q][1]);
+                sts_f1(xw + (16 * q + 8) * 4, sc[q][2]);
+                sts_f1(xw + (XROW + 16 * q + 8) * 4, sc[q][3]);
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * AW) : "memory");
             float p[2][2][2];
 #pragma unroll
@@ -580,21 +595,23 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
                 }
             l = l * corr + ps;
             m = mn;
+            {      // the accumulators belong to heads 2tq, 2tq+1; their softmax state lives in the lanes of rows g = 2tq, 2tq+1
+                const float c0 = __shfl_sync(0xffffffffu, corr, 8 * tq), c1 = __shfl_sync(0xffffffffu, corr, 8 * tq + 4);
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= corr; o[nt][1] *= corr; }
-            // ---- C[:, block] += P . Z[:, block] : per stage 8 n-tiles of 8 columns, one k-step of 16 keys
+                for (int mt = 0; mt < 4; ++mt) { o[mt][0] *= c0; o[mt][1] *= c1; o[mt][2] *= c0; o[mt][3] *= c1; }
+            }
+            // ---- C^T[block, :] += Z[:, block]^T . P^T : per stage 4 m-tiles of 16 columns, one k-step of 16 keys, N = the 8 heads
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 if (q == 0 || two) {
-                    const uint32_t pa0 = pack_bf16x2(p[q][0][0], p[q][0][1]);     // keys 2t, 2t+1 of the stage
-                    const uint32_t pa2 = pack_bf16x2(p[q][1][0], p[q][1][1]);     // keys 8+2t, 9+2t
+                    const uint32_t pb0 = pack_bf16x2(p[q][0][0], p[q][0][1]);     // (keys 2t, 2t+1; head g)
+                    const uint32_t pb1 = pack_bf16x2(p[q][1][0], p[q][1][1]);     // (keys 8+2t, 9+2t; head g)
 #pragma unroll
-                    for (int np = 0; np < 4; ++np) {
-                        uint32_t b0, b1, b2, b3;
-                        ldsm_x4_t(kts[q] + off_pv[np], b0, b1, b2, b3);
-                        if (last) { b0 &= vm_lo[q]; b2 &= vm_lo[q]; b1 &= vm_hi[q]; b3 &= vm_hi[q]; }
-                        mma_bf16_top(o[2 * np][0], o[2 * np][1], pa0, pa2, b0, b1);
-                        mma_bf16_top(o[2 * np + 1][0], o[2 * np + 1][1], pa0, pa2, b2, b3);
+                    for (int mt = 0; mt < 4; ++mt) {
+                        uint32_t z0, z1, z2, z3;        // transposed blocks: keys 0-7 / chunk 2mt, keys 8-15 / 2mt, keys 0-7 / 2mt+1, keys 8-15 / 2mt+1
+                        ldsm_x4_t(kts[q] + off_z[mt], z0, z1, z2, z3);
+                        if (last) { z0 &= vm_lo[q]; z2 &= vm_lo[q]; z1 &= vm_hi[q]; z3 &= vm_hi[q]; }
+                        mma_bf16(o[mt], z0, z2, z1, z3, pb0, pb1);
                     }
                 }
             }
@@ -607,9 +624,23 @@ __global__ void __launch_bounds__(32 * (AW + 1), MINB) attn_abs_kernel(const __g
         l += __shfl_xor_sync(0xffffffffu, l, 1);
         l += __shfl_xor_sync(0xffffffffu, l, 2);
         const float inv = 1.0f / l;
-        uint32_t* op = reinterpret_cast<uint32_t*>(a.o + (size_t)u * a.ldo + g * 256 + cw * 64);
+        {   // normalise, transpose through this warp's own slice of the exchange buffer the NEXT iteration would use (every warp is past
+            // the barrier that followed its last reads of it), then store 128-byte row segments: out[u][head * 256 + 64cw ..]
+            const float i0 = __shfl_sync(0xffffffffu, inv, 8 * tq), i1 = __shfl_sync(0xffffffffu, inv, 8 * tq + 4);
+            const uint32_t ow = xbuf_u32 + (xiter & 1) * (AW * 8 * XROW * 4) + cw * (8 * XROW * 4);      // [8 heads][64 cols] bf16, head rows 136 B apart (conflict-free 16-bit stores)
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) op[4 * nt + tq] = pack_bf16x2(o[nt][0] * inv, o[nt][1] * inv);
+            for (int mt = 0; mt < 4; ++mt) {
+                sts_h1(ow + (2 * tq) * 136 + (16 * mt + g) * 2, o[mt][0] * i0);
+                sts_h1(ow + (2 * tq + 1) * 136 + (16 * mt + g) * 2, o[mt][1] * i1);
+                sts_h1(ow + (2 * tq) * 136 + (16 * mt + g + 8) * 2, o[mt][2] * i0);
+                sts_h1(ow + (2 * tq + 1) * 136 + (16 * mt + g + 8) * 2, o[mt][3] * i1);
+            }
+            __syncwarp();
+            uint32_t* op = reinterpret_cast<uint32_t*>(a.o + (size_t)u * a.ldo + g * 256 + cw * 64);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) op[4 * nt + tq] = lds_u1(ow + g * 136 + (4 * nt + tq) * 4);
+            __syncwarp();        // the next unit's first exchange writes this slice again
+        }
         if (a.dbg && threadIdx.x == 32 && u == (int)blockIdx.x) {
             atomicAdd(a.dbg + 0, t_ready - t_entry0); atomicAdd(a.dbg + 1, t_first - t_ready); atomicAdd(a.dbg + 2, t_loop - t_first);
             atomicAdd(a.dbg + 3, gtime() - t_loop); atomicAdd(a.dbg + 4, 1ull);
