@@ -497,8 +497,11 @@ def main():
         top = max(rows, key=lambda r: r["ms"])
         tc = by_class[top["name"]]
         tensor_bound = top["flops"] > 0 and top["name"] not in HBM_CLASSES
-        t_key = {"dec_gemm_q": "tc_gemm_kernel_64_store_bf16", "dec_attn_self": "attn_abs_kernel", "dec_attn_cross": "attn_abs_kernel"}.get(top["name"])
-        ratio = (traffic_db.get(t_key) or {}).get("dram_bytes_over_algorithmic") if t_key else None
+        # measured DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/roofline_traffic.json)
+        t_ent = traffic_db.get({"dec_attn_self": "attn_abs_kernel", "dec_attn_cross": "attn_abs_kernel"}.get(top["name"], top["name"])) or {}
+        ratio = t_ent.get("dram_bytes_over_algorithmic")
+        if ratio is None and t_ent.get("dram_bytes_per_launch"):
+            ratio = t_ent["dram_bytes_per_launch"] / (top["bytes"] / max(1, top["launches"]))
         roofline = {"bound": "tensor" if tensor_bound else "hbm", "kernel": kernel_of.get(top["name"], top["name"]), "class": top["name"],
                     "achieved": tc["tflops"] if tensor_bound else tc["gbs"],
                     "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) if tensor_bound else peaks["hbm_gbs"],
