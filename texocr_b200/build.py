@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libtexocr_b200.so")
-SOURCES = ["engine_core.cu", "engine_weights.cu", "engine_encoder.cu", "engine_decode.cu", "engine_api.cu", "gemm_simt.cu", "tc_gemm.cu", "conv_gn.cu", "rowwise.cu", "attention.cu", "attn_decode_tma.cu", "attn_enc_mma.cu", "preprocess.cu"]
+SOURCES = ["engine_core.cu", "engine_weights.cu", "engine_encoder.cu", "engine_decode.cu", "engine_api.cu", "gemm_simt.cu", "tc_gemm.cu", "conv_gn.cu", "rowwise.cu", "attention.cu", "attn_decode_tma.cu", "attn_decode_seq.cu", "attn_enc_mma.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -398,6 +398,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!h || !name) return TEXOCR_ERR_ARG;
     if (!strcmp(name, "cuda_graph")) { h->use_graph = value != 0; return 0; }
     if (!strcmp(name, "stagger_us")) { h->stagger_us = (int)value; return 0; }
+    if (!strcmp(name, "attn_seq")) { g_attn_seq = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "attn_abs_minb")) { g_attn_abs_minb = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "absorb_two_stage")) { h->absorb_two_stage = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "self_absorb")) { h->self_absorb = (int)value; drop_graphs(h); return 0; }
@@ -520,7 +521,7 @@ int texocr_debug_attn_abs(texocr_handle* h, const void* q, void* latent, int64_t
     AttnAbsArgs ab{};
     ab.q = q; ab.ldq = 2048; ab.latent = latent; ab.latent_rows = (long)latent_rows; ab.k_off = k_off_dev; ab.o = out; ab.ldo = 2048; ab.batch = batch;
     if (znew) { ab.znew = znew; ab.ldz = 256; ab.tcap = tcap; ab.step = step_dev; }
-    CK(launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
+    CK(g_attn_seq ? launch_attn_seq(ab, h->num_sms * h->attn_ctas_per_sm, st) : launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
     CK(cudaStreamSynchronize(st));
     return 0;
 }

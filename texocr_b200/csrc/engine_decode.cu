@@ -52,7 +52,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
             }
             if (!(h->dbg_skip & 1))
                 LAUNCH(KC_DEC_ATTN_SELF, 1, (double)rows * tkeys * 256 * e, 4.0 * rows * tkeys * 2048,
-                       launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
+                       (g_attn_seq ? launch_attn_seq(ab, h->num_sms * h->attn_ctas_per_sm, st) : launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st)));
             if ((r = sub_abs_out(h, rc, h->dec_self[l], ca, st))) return r;
         } else {
         // ---- causal self-attention over the KV cache
@@ -99,7 +99,7 @@ static int enqueue_decode_step(texocr_handle* h, int B, int row0, int rows, int 
             }
             if (!(h->dbg_skip & 2))
                 LAUNCH(KC_DEC_ATTN_CROSS, 1, sum_s * rows / B * 256 * e, 4.0 * sum_s * rows / B * 2048,
-                       launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st));
+                       (g_attn_seq ? launch_attn_seq(ab, h->num_sms * h->attn_ctas_per_sm, st) : launch_attn_abs(ab, h->num_sms * h->attn_ctas_per_sm, st)));
             if ((r = sub_abs_out(h, rc, h->dec_cross[l], ca, st))) return r;
         } else {
         // ---- cross-attention over the (pre-projected) encoder memory; q goes to the first 512 columns of this branch's qkv rows

@@ -204,6 +204,9 @@ struct AttnAbsArgs {
     unsigned long long* dbg;      // debug phase timers (5 words), null = off
 };
 cudaError_t launch_attn_abs(const AttnAbsArgs& a, int max_ctas, cudaStream_t st);
+// the same attention with one warp per sequence (attn_decode_seq.cu); g_attn_seq selects it for the generate loop
+cudaError_t launch_attn_seq(const AttnAbsArgs& a, int max_ctas, cudaStream_t st);
+extern int g_attn_seq;
 cudaError_t launch_attn_decode_tma(const AttnDecodeArgs& a, const KvLayout& lay, int max_ctas, cudaStream_t st);
 // [tok][L*1024] (per layer: K 512 | V 512, heads side by side; the cross-K/V GEMM output) -> [L][8][tok][K 64 | V 64]
 cudaError_t launch_crosskv_head_major(const void* in, void* out, int ntok, int layers, int dt, cudaStream_t st);
