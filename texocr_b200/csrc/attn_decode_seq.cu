@@ -71,6 +71,9 @@ TX_DEVINL void ldsm_x4(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, 
 TX_DEVINL void ldsm_x4_t(uint32_t addr, uint32_t& d0, uint32_t& d1, uint32_t& d2, uint32_t& d3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(addr));
 }
+TX_DEVINL void stsm_x4_t(uint32_t addr, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(d0), "r"(d1), "r"(d2), "r"(d3) : "memory");
+}
 TX_DEVINL void mma_bf16(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -176,11 +179,32 @@ __global__ void __launch_bounds__(32 * SW, 2) attn_seq_kernel(const __grid_const
     int it = 0;
     for (int u = gw; u < units; u += nw) {
         // B fragments of Q'^T, scaled by 1/8 (exact): k-step ks (16 columns): (cols 16ks+2tq,+1; head g), (cols 16ks+8+2tq,+1; head g)
+        // The 8 x 256 query block (4 KB) comes in with 16-byte coalesced loads, goes through the warp's staging tile (two halves of 128
+        // columns, head rows 272 bytes apart) and is picked up by ldmatrix in fragment layout: one L2 round trip instead of 32 scattered ones.
         uint32_t qa[32];
         {
-            const uint32_t* qp = reinterpret_cast<const uint32_t*>(a.q + (size_t)u * a.ldq + g * 256);
+            const bf16* qp = a.q + (size_t)u * a.ldq;
+            uint4 qv[8];
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks) { qa[2 * ks] = ldcg_u32(qp + 8 * ks + tq); qa[2 * ks + 1] = ldcg_u32(qp + 8 * ks + 4 + tq); }
+            for (int i = 0; i < 8; ++i) {      // chunk id = i*32 + lane of 256 chunks: head = id >> 5, 16-byte chunk of the head row = id & 31
+                const int id = i * 32 + lane;
+                qv[i] = ldcg_u4(qp + (id >> 5) * 256 + (id & 31) * 8);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int id = i * 32 + lane, hd = id >> 5, ch = id & 31;
+                    if ((ch >> 4) == half) sts_u4(ostg + hd * OSTG_ROW + (ch & 15) * 16, qv[i]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {      // x4: the 8 x 8 blocks of columns 32j .. 32j+31 of this half = k-steps 8*half + 2j, +1
+                    const int kk = 8 * half + 2 * j;
+                    ldsm_x4(ostg + lm_r * OSTG_ROW + (4 * j + lm_m) * 16, qa[2 * kk], qa[2 * kk + 1], qa[2 * kk + 2], qa[2 * kk + 3]);
+                }
+                __syncwarp();
+            }
         }
         uint4 zrow = make_uint4(0u, 0u, 0u, 0u);
         if (SELF) {      // this step's latent row, columns 8*lane .. +7: append to the cache, keep for the last stage
@@ -282,18 +306,18 @@ __global__ void __launch_bounds__(32 * SW, 2) attn_seq_kernel(const __grid_const
             l1 += __shfl_xor_sync(0xffffffffu, l1, sh);
         }
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        // output: normalise, transpose through the warp's staging tile (two halves of 128 columns), store 16 bytes per lane:
-        // out[u][head * 256 + col]
+        // output: normalise, transpose through the warp's staging tile with stmatrix.trans (the accumulator fragment of an m-tile is an
+        // 8 x 8 block [column][head]; stored transposed it is 8 head rows of 8 columns = 16 bytes), two halves of 128 columns, then
+        // 16 bytes per lane to out[u][head * 256 + col]
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int m8 = 0; m8 < 8; ++m8) {
-                const int mt = half * 8 + m8;
-                const int col = 16 * m8 + g;
-                sts_h1(ostg + (2 * tq) * OSTG_ROW + col * 2, o[mt][0] * i0);
-                sts_h1(ostg + (2 * tq + 1) * OSTG_ROW + col * 2, o[mt][1] * i1);
-                sts_h1(ostg + (2 * tq) * OSTG_ROW + (col + 8) * 2, o[mt][2] * i0);
-                sts_h1(ostg + (2 * tq + 1) * OSTG_ROW + (col + 8) * 2, o[mt][3] * i1);
+            for (int m2 = 0; m2 < 4; ++m2) {      // two m-tiles (32 columns) per stmatrix.x4
+                const int mt = half * 8 + 2 * m2;
+                const uint32_t r0 = pack_bf16x2(o[mt][0] * i0, o[mt][1] * i1), r1 = pack_bf16x2(o[mt][2] * i0, o[mt][3] * i1);
+                const uint32_t r2 = pack_bf16x2(o[mt + 1][0] * i0, o[mt + 1][1] * i1), r3 = pack_bf16x2(o[mt + 1][2] * i0, o[mt + 1][3] * i1);
+                // matrix i (lanes 8i .. 8i+7 give the addresses of its 8 head rows): columns 32*m2 + 8i .. +7 of this half
+                stsm_x4_t(ostg + lm_r * OSTG_ROW + (4 * m2 + lm_m) * 16, r0, r1, r2, r3);
             }
             __syncwarp();
 #pragma unroll
