@@ -25,7 +25,8 @@ constexpr int CH = 16;                 // keys per stage
 constexpr int STAGE = CH * 512;        // 16 latent rows x 256 bf16
 constexpr int HTILE = CH * 128;        // one 64-column block of a stage, TMA 128B-swizzle layout: (row r, 16-byte chunk c) at r*128 + ((c ^ (r&7)) << 4)
 constexpr int SW = 4;                  // warps = sequences in flight per CTA
-constexpr int SNS = 3;                 // ring stages per warp (24 KB in flight per sequence)
+constexpr int SNS = 2;                 // ring stages per warp (16 KB in flight per sequence; 3 stages measured no better)
+constexpr int SEQ_MINB = 3;            // CTAs per SM: 168 registers (no spills), 74 KB of shared memory -> 12 sequences in flight per SM
 constexpr int OSTG_ROW = 272;          // output staging: 128 columns + 8 pad, bf16 (conflict-free 16-bit stores)
 constexpr int OSTG = 8 * OSTG_ROW;     // bytes per warp: 8 heads x half of the 256 columns
 constexpr float SCALE = 0.125f;
@@ -97,7 +98,7 @@ TX_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 TX_DEVINL float2 unpack_bf16x2(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w)); }
 
 template <bool SELF>
-__global__ void __launch_bounds__(32 * SW, 2) attn_seq_kernel(const __grid_constant__ CUtensorMap tm,
+__global__ void __launch_bounds__(32 * SW, SEQ_MINB) attn_seq_kernel(const __grid_constant__ CUtensorMap tm,
                                                             const __grid_constant__ CUtensorMap tm4, const SeqArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
