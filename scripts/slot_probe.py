@@ -73,8 +73,10 @@ for m in models:
         for k in range(7):
             a[k] += float(d[o + k])
     a = tot.setdefault("dec_gemm", [0.0] * 8)
-    for k in range(3):
+    for k in range(7):
         a[k] += float(d[16 + k])
+    gx = tot.setdefault("gemm_x", [0.0, 0.0])
+    gx[0] += float(d[16 + 7]); gx[1] += float(d[16 + 8])
 # the buffers hold the sums of each engine's LAST generate call = one batch per engine
 slot_total = 0.0
 for name in ("attn_self", "attn_cross"):
@@ -87,5 +89,7 @@ a = tot["dec_gemm"]
 c = max(1.0, a[2])
 print(f"dec_gemm  : CTAs/batch {c / n:9.0f}  wait {a[0] / c / 1e3:6.2f} us  work {a[1] / c / 1e3:6.2f} us  | residency {(a[0] + a[1]) / c / 1e3:6.2f} us per CTA, "
       f"{(a[0] + a[1]) / n / 1e6:8.2f} ms-CTA per batch (work only {a[1] / n / 1e6:8.2f})")
+print(f"            per CTA from entry: first k-block landed {a[3] / c / 1e3:5.2f} us, last k-block landed {a[4] / c / 1e3:5.2f} us, accumulator complete {a[6] / c / 1e3:5.2f} us, "
+      f"first chunk in registers {tot['gemm_x'][0] / c / 1e3:5.2f} us, first chunk staged {tot['gemm_x'][1] / c / 1e3:5.2f} us, epilogue warp done {a[5] / c / 1e3:5.2f} us")
 slot_total += (a[0] + a[1]) / n / 1e6
 print(f"sum of residency: {slot_total:.1f} ms-CTA per batch; wall {ms_batch:.2f} ms per batch -> {slot_total / ms_batch:.0f} CTAs resident on average ({slot_total / ms_batch / 148:.2f} per SM)")

@@ -94,6 +94,18 @@ TX_DEVINL float warp_max(float v) {
 
 TX_DEVINL float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)); }
 TX_DEVINL float sigmoidf_(float g) { return 1.0f / (1.0f + expf(-g)); }
+// bf16 tier epilogues (tcgen05 GEMM): the result is rounded to 8 mantissa bits (GeGLU -> bf16 hidden) or added to an O(1) residual, so
+// the exact-erf GELU (model/attention.py:17) and the sigmoid of nn.GLU are evaluated with hardware ex2 / rcp and the
+// Abramowitz-Stegun 7.1.26 rational erf (|error| <= 1.5e-7): ~12 instead of ~50 instructions per value in a one-thread-per-row
+// epilogue that is on the critical path of every decode GEMM.  The fp32 parity tier (FFMA kernels) keeps erff / expf.
+TX_DEVINL float sigmoid_fast(float g) { return __fdividef(1.0f, 1.0f + __expf(-g)); }
+TX_DEVINL float gelu_erf_fast(float g) {
+    const float x = fabsf(g) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    const float erf_abs = 1.0f - poly * __expf(-x * x);
+    return 0.5f * g * (1.0f + copysignf(erf_abs, g));
+}
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor drains.  pdl_launch_dependents() lets the successor be scheduled early; pdl_wait() blocks until

@@ -142,7 +142,7 @@ TX_DEVINL void stage_copy(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int la
 
 template <int BN, int EPI, typename TC>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
-                             uint8_t* smem_idle, uint32_t parity = 0) {
+                             uint8_t* smem_idle, uint32_t parity = 0, unsigned long long dbg_t0 = 0ull) {
     const int q = warp & 3;
     uint8_t* stg = smem_idle + q * STG_WARP;
     uint8_t* my = stg + lane * STG_STRIDE;                      // this thread's staged row
@@ -175,6 +175,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         bpre[i] = b.x; bpre[i + 1] = b.y; bpre[i + 2] = b.z; bpre[i + 3] = b.w;
     }
     mbar_wait(tmem_full, parity);
+    if (dbg_t0) atomicAdd(p.dbg + 6, gtime_ns() - dbg_t0);      // debug: epilogue warp entry -> accumulator complete
     tcgen05_fence_after();
     float am_best = -INFINITY;                                  // EPI_ARGMAX: running maximum of this thread's row over the tile
     int am_idx = 0x7fffffff;
@@ -182,6 +183,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+        if (dbg_t0 && c0 == 0) atomicAdd(p.dbg + 7, gtime_ns() - dbg_t0);      // debug: -> first accumulator chunk in registers
         const int n = n0 + c0;
         if (rows_ok <= 0 || n >= p.N) continue;                 // warp-uniform
         const int nvalid = min(32, p.N - n);                    // multiple of 8
@@ -213,7 +215,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         if (PRE_RES) {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i)
-                o[i] = (EPI == EPI_BIAS_RES) ? v[i] + rpre[PRE_RES ? i : 0] : v[2 * i] * sigmoidf_(v[2 * i + 1]) + rpre[PRE_RES ? i : 0];
+                o[i] = (EPI == EPI_BIAS_RES) ? v[i] + rpre[PRE_RES ? i : 0] : v[2 * i] * sigmoid_fast(v[2 * i + 1]) + rpre[PRE_RES ? i : 0];
         } else if (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES) {
             // residual tile -> staging (coalesced), then every thread picks up its own row
             stage_copy<NOUT * 4, false>(stg, reinterpret_cast<uint8_t*>(const_cast<float*>(p.res) + (size_t)mrow0 * p.ldres + ncol),
@@ -228,10 +230,10 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < NOUT; ++i)
-                o[i] = (EPI == EPI_BIAS_RES) ? v[i] + r[i] : v[2 * i] * sigmoidf_(v[2 * i + 1]) + r[i];
+                o[i] = (EPI == EPI_BIAS_RES) ? v[i] + r[i] : v[2 * i] * sigmoid_fast(v[2 * i + 1]) + r[i];
         } else if (EPI == EPI_GEGLU) {
 #pragma unroll
-            for (int i = 0; i < NOUT; ++i) o[i] = v[2 * i] * gelu_erf(v[2 * i + 1]);
+            for (int i = 0; i < NOUT; ++i) o[i] = v[2 * i] * gelu_erf_fast(v[2 * i + 1]);
         } else {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) o[i] = v[i];
@@ -240,6 +242,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         TO* mine = reinterpret_cast<TO*>(my);
 #pragma unroll
         for (int i = 0; i < NOUT; i += 4) st4(mine + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+        if (dbg_t0 && c0 == 0) atomicAdd(p.dbg + 8, gtime_ns() - dbg_t0);      // debug: -> first chunk computed and staged
         __syncwarp();
         stage_copy<RB, true>(stg, reinterpret_cast<uint8_t*>(reinterpret_cast<TO*>(p.C) + (size_t)mrow0 * p.ldc + ncol),
                              (size_t)p.ldc * sizeof(TO), lane, rows_ok, nvalid_out * (int)sizeof(TO));
@@ -342,9 +345,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
+            const unsigned long long m_t0 = p.dbg ? gtime_ns() : 0ull;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % S::STAGES, ph = (kb / S::STAGES) & 1;
                 mbar_wait(&full[s], ph);
+                if (p.dbg && kb == 0) atomicAdd(p.dbg + 3, gtime_ns() - m_t0);           // MMA thread: entry -> first k-block landed
+                if (p.dbg && kb == nkb - 1) atomicAdd(p.dbg + 4, gtime_ns() - m_t0);     // ... -> last k-block landed
                 tcgen05_fence_after();
                 const uint32_t a_hi = smem_u32(smem + s * S::STAGE);
                 const uint32_t w_hi = a_hi + S::NOPS * S::A_BYTES;
@@ -362,8 +368,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_commit(tmem_full);            // accumulator complete
         }
     } else {
+        const unsigned long long e_t0 = (p.dbg && threadIdx.x == 64) ? gtime_ns() : 0ull;
         pdl_wait();        // the epilogue reads the residual stream
-        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem);
+        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem, 0, e_t0);
+        if (p.dbg && threadIdx.x == 64) atomicAdd(p.dbg + 5, gtime_ns() - e_t0);          // epilogue warp: entry -> its rows stored
     }
     tcgen05_fence_before();
     __syncthreads();
