@@ -490,15 +490,15 @@ def main():
                      "dec_gemm_w1": "tc_gemm_kernel<64, EPI_GEGLU, bf16> (MLP in + GeGLU, N = 2048; 4 per step)",
                      "dec_gemm_w2": "tc_gemm_kernel<32, EPI_BIAS_RES, float> (MLP out + residual, K = 1024; 4 per step)",
                      "dec_gemm_vproj": "tc_gemm_kernel<64, EPI_STORE, bf16> block-diagonal (per-head value projection; 8 per step)",
-                     "dec_attn_self": "attn_abs_kernel<self> (absorbed decode self-attention; 4 per step)",
-                     "dec_attn_cross": "attn_abs_kernel<cross> (absorbed decode cross-attention; 4 per step)",
+                     "dec_attn_self": "attn_seq_kernel<self> (absorbed decode self-attention, one warp per sequence; 4 per step)",
+                     "dec_attn_cross": "attn_seq_kernel<cross> (absorbed decode cross-attention, one warp per sequence; 4 per step)",
                      "conv_gemm": "tc_gemm_persistent_kernel<128, EPI_STORE, float, bf16x3> (backbone convolutions)",
                      "gn_apply": "gn_apply_kernel (GroupNorm apply + residual + ReLU, split-bf16 out)"}
         top = max(rows, key=lambda r: r["ms"])
         tc = by_class[top["name"]]
         tensor_bound = top["flops"] > 0 and top["name"] not in HBM_CLASSES
         # measured DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/roofline_traffic.json)
-        t_ent = traffic_db.get({"dec_attn_self": "attn_abs_kernel", "dec_attn_cross": "attn_abs_kernel"}.get(top["name"], top["name"])) or {}
+        t_ent = traffic_db.get({"dec_attn_self": "attn_seq_kernel", "dec_attn_cross": "attn_seq_kernel"}.get(top["name"], top["name"])) or {}
         ratio = t_ent.get("dram_bytes_over_algorithmic")
         if ratio is None and t_ent.get("dram_bytes_per_launch"):
             ratio = t_ent["dram_bytes_per_launch"] / (top["bytes"] / max(1, top["launches"]))
@@ -522,8 +522,8 @@ def main():
         a_n = sum(r["launches"] for r in attn)
         if a_n:
             ach = a_bytes / (a_ms / 1e3) / 1e9
-            ratio = (traffic_db.get("attn_abs_kernel") or {}).get("dram_bytes_over_algorithmic")
-            roofline_attn = {"bound": "hbm", "kernel": "attn_abs_kernel<self> + attn_abs_kernel<cross> (absorbed decode attention, 8 launches per decode step)",
+            ratio = (traffic_db.get("attn_seq_kernel") or {}).get("dram_bytes_over_algorithmic")
+            roofline_attn = {"bound": "hbm", "kernel": "attn_seq_kernel<self> + attn_seq_kernel<cross> (absorbed decode attention, one warp per sequence, 8 launches per decode step)",
                              "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                              "traffic": ratio * a_bytes / a_n if ratio else None, "launches": a_n, "avg_us": a_ms * 1e3 / a_n,
                              "algorithmic_bytes_per_launch": a_bytes / a_n, "share_of_batch_kernel_time": round(a_ms / tot, 4),
@@ -577,6 +577,32 @@ def main():
                    "note": "frac_of_bf16_peak is on ALGORITHMIC FLOPs; the backbone issues 3 MMAs per product (bf16x3), ceiling 0.41 (SURVEY.md 8d)"}
         encoder["value"] = encoder["config2_ragged"]["value"]
         next_rows = measure_next_rows(model, img_dev, peaks, stream)
+
+    # ---- what each kernel class costs a batch WITH the batches in flight (the eager per-launch figures above carry ~5 us of launch
+    # latency each and say little about the pipelined path): the same pipelined run with classes of decode kernels switched off
+    # (engine option dbg_skip: 1 self-attention, 2 cross-attention, 4 LayerNorm, 8 decode GEMMs; results are garbage, timing only)
+    if rank == 0 and not args.no_extras and n_fly > 1 and world == 1 and roofline_attn is not None:
+        from texocr_b200.pipeline import GeneratePipeline
+        ab = {}
+        with GeneratePipeline(model, in_flight=n_fly, branches=args.branches) as p2:
+            p2.warm_up(img_dev, MAX_LEN)
+            for name, skip in (("all", 0), ("no_attention", 3), ("no_gemm_ln", 12), ("encoder_and_token_kernels_only", 15)):
+                for e_ in p2.engines:
+                    e_.set_option("dbg_skip", skip)
+                k = 2 * n_fly
+                list(p2.generate_batches([img_dev] * n_fly, MAX_LEN))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                list(p2.generate_batches([img_dev] * k, MAX_LEN))
+                torch.cuda.synchronize()
+                ab[name] = (time.perf_counter() - t0) * 1e3 / k
+        attn_ms = ab["no_gemm_ln"] - ab["encoder_and_token_kernels_only"]
+        a_total = sum(r["bytes"] for r in rows if r["name"] in ("dec_attn_self", "dec_attn_cross"))
+        roofline_attn["in_flight"] = {
+            "ms_per_batch": ab, "attention_ms_per_batch": attn_ms, "gemm_ln_chain_ms_per_batch": ab["no_attention"] - ab["encoder_and_token_kernels_only"],
+            "attention_gbs": a_total / (attn_ms / 1e3) / 1e9, "attention_frac_hbm": a_total / (attn_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+            "method": f"{n_fly} batches in flight, wall clock per batch with decode kernel classes switched off; attention = (attention only) - (neither); "
+                      "bytes = the algorithmic latent-row bytes of one batch's attention launches"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
