@@ -10,6 +10,10 @@ cfg = spec.default_config(max_length=256); cfg["device"] = "cuda:0"
 d = spec.dims_from_config(cfg)
 m = texocr_b200.create_model(cfg, precision="bf16"); m.load_state_dict(synth.seeded_state_dict(d, seed=0))
 eng = m.engine()
+if len(sys.argv) > 2:
+    for kv in sys.argv[2].split(','):
+        k, v = kv.split('='); eng.set_option(k, int(v))
+    print('options:', sys.argv[2])
 img = synth.synth_images(B, 64, 384, seed=1234).cuda()
 for _ in range(2): m.encoder(img)
 torch.cuda.synchronize()

@@ -136,3 +136,13 @@ def test_vocab_gemm_with_argmax_epilogue(eng, M, N):
     t2 = ref.topk(2, dim=-1).values
     ok = (t2[:, 0] - t2[:, 1]) > 1e-4 * ref.abs().max()
     assert bool((row_idx.long() == ref.argmax(-1))[ok].all())
+
+
+@pytest.mark.parametrize("M,N,K,epi,out_dtype,use_bias", [CASES[0], CASES[3], CASES[4], CASES[5], CASES[8], CASES[10]])
+def test_bf16_gemm_four_epilogue_warps(eng, M, N, K, epi, out_dtype, use_bias):
+    """The default is two epilogue warpgroups per CTA (every other column chunk each); option gemm_epi_warps = 4 keeps one."""
+    eng.set_option("gemm_epi_warps", 4)
+    try:
+        _gemm_case(eng, M, N, K, epi, out_dtype, use_bias, True)
+    finally:
+        eng.set_option("gemm_epi_warps", 8)

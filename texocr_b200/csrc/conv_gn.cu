@@ -4,6 +4,7 @@
 // Activations are ragged NHWC pixel batches [sum_i h_i*w_i, C] (see ImgGeom in common.cuh).
 // All of these are HBM-bound: coalesced float4 rows, fp32 math, deterministic reductions.
 #include "common.cuh"
+#include "gn_block.cuh"
 #include "kernels.h"
 
 namespace {
@@ -131,6 +132,69 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partial, const int
         a += in[0]; q += in[1];
     }
     const double n = (double)((img_off[b + 1] >> (2 * level)) - (img_off[b] >> (2 * level))) * cpg;
+    const double mean = a / n;
+    double var = q / n - mean * mean;       // biased variance (F.group_norm)
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)b * 32 + g) * 2 + 0] = (float)mean;
+    stats[((size_t)b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics, bf16 tier: block partial sums
+// Stand-alone producer of the partials of gn_block.cuh (the convolution GEMM's epilogue is the other one): warp = one
+// (32-row block of an image, 32-channel chunk), coalesced 16-byte loads in exactly the lane mapping of the GEMM epilogue.
+// slot = (first row of the block >> 5) + image index; slots that belong to no image are skipped.
+__global__ void __launch_bounds__(256) gn_stats_blocks_kernel(const float* __restrict__ raw, const int* __restrict__ img_off, int nimg,
+                                                              int level, int C, int nslots, float* __restrict__ part) {
+    const int chunks = C >> 5;
+    const long w = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)(w / chunks), chunk = (int)(w - (long)slot * chunks);
+    if (slot >= nslots) return;
+    // largest b with (row0_b >> 5) + b <= slot
+    int lo = 0, hi = nimg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (((img_off[mid] >> (2 * level)) >> 5) + mid <= slot) lo = mid; else hi = mid - 1;
+    }
+    const int b = lo;
+    const int p0 = img_off[b] >> (2 * level), p1 = img_off[b + 1] >> (2 * level);
+    const int blk = slot - ((p0 >> 5) + b);
+    const int r0 = p0 + blk * 32;
+    if (blk < 0 || r0 >= p1) return;
+    const int rows_ok = min(32, p1 - r0);
+    const int rr = lane >> 3, ch = lane & 7;
+    const float* src = raw + (size_t)r0 * C + chunk * 32 + ch * 4;
+    float4 f[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rr;
+        f[it] = row < rows_ok ? ld4(src + (size_t)row * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+        if (it * 4 + rr < rows_ok) gn_block_acc(s, q, f[it]);
+    gn_block_finish(s, q, lane, C >> 5, chunk * 32, part + (size_t)slot * 64);
+}
+
+// stats[b][g] = (mean, rstd) from the image's block partials, added in block order in double
+__global__ void __launch_bounds__(32) gn_finalize_blocks_kernel(const float* __restrict__ part, const int* __restrict__ img_off, int level,
+                                                                int cpg, float* __restrict__ stats) {
+    const int b = blockIdx.x, g = threadIdx.x;
+    const int p0 = img_off[b] >> (2 * level), p1 = img_off[b + 1] >> (2 * level);
+    const int nblk = (p1 - p0 + 31) >> 5;
+    const float2* in = reinterpret_cast<const float2*>(part) + ((size_t)((p0 >> 5) + b)) * 32 + g;
+    double a = 0.0, q = 0.0;
+    int k = 0;
+    for (; k + 8 <= nblk; k += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = in[(size_t)(k + u) * 32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a += (double)v[u].x; q += (double)v[u].y; }
+    }
+    for (; k < nblk; ++k) { const float2 v = in[(size_t)k * 32]; a += (double)v.x; q += (double)v.y; }
+    const double n = (double)(p1 - p0) * cpg;
     const double mean = a / n;
     double var = q / n - mean * mean;       // biased variance (F.group_norm)
     if (var < 0.0) var = 0.0;
@@ -331,6 +395,20 @@ cudaError_t launch_gn_stats(const float* raw, int C, int level, const int* img_o
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     gn_finalize_kernel<<<nimg, 32, 0, st>>>(partial, img_off, level, nchunk, C / 32, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_stats_blocks(const float* raw, int C, int level, const int* img_off, int nimg, long total_rows, float* part,
+                                   cudaStream_t st) {
+    if (C % 64 != 0 || C > 1024 || ((C >> 5) & ((C >> 5) - 1))) return cudaErrorInvalidValue;
+    const long nslots = (total_rows >> 5) + nimg + 1;
+    const long warps = nslots * (C >> 5);
+    gn_stats_blocks_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(raw, img_off, nimg, level, C, (int)nslots, part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gn_finalize_blocks(const float* part, int C, int level, const int* img_off, int nimg, float* stats, cudaStream_t st) {
+    gn_finalize_blocks_kernel<<<nimg, 32, 0, st>>>(part, img_off, level, C / 32, stats);
     return cudaGetLastError();
 }
 

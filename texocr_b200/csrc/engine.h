@@ -79,6 +79,7 @@ struct texocr_handle {
     DevBuf img_stage;                          // device copy of host images
     DevBuf raw1, act2, actA, actB, rawMid, actMid, rawMid2, actMid2, raw3, rawDs;
     DevBuf gn_partial, gn_stats[4];
+    DevBuf gn_part;                            // bf16 tier: per-32-row-block GroupNorm partial sums (gn_block.cuh)
     DevBuf proj_out, patch_cols, backbone_a, col;
     DevBuf x, s, xn, qkv, o, hid, logits;
     DevBuf amax_part;                          // decode step, bf16 tier greedy: [B][ceil(V/32)] {max, index} partials of the vocabulary GEMM (no logits in HBM)
@@ -111,6 +112,8 @@ struct texocr_handle {
     double prof_ms[KC_COUNT] = {0}; double prof_bytes[KC_COUNT] = {0}; double prof_flops[KC_COUNT] = {0};
     int64_t prof_n[KC_COUNT] = {0};
     bool use_tcgen05 = true;
+    int gn_fused = 1;             // bf16 tier: GroupNorm partial sums in the epilogue of the producing convolution GEMM (same-size batches whose
+                                  // images have a multiple of 32 pixel rows at every level); 0 = always the stand-alone block kernel
     bool use_im2col_tma = true;   // bf16 tier, same-size batches: 3x3 / strided convolutions as implicit GEMMs (TMA im2col loads)
     // bf16 tier generate loop: cross-attention streams the [S,256] encoder memory once for all heads instead of per-head K/V
     // (K / V projections folded into the query / output projections).  0 = projected K/V cache.

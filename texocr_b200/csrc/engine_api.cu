@@ -428,6 +428,8 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "gemm_persistent")) { g_tc_persistent = (int)value; return 0; }
     if (!strcmp(name, "gemm_min_ctas")) { g_tc_min_ctas = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "gemm_persistent_stages")) { g_tc_persistent_stages = (int)value; return 0; }
+    if (!strcmp(name, "gemm_epi_warps")) { g_tc_epi_warps = value == 4 ? 4 : 8; drop_graphs(h); return 0; }
+    if (!strcmp(name, "gn_fused")) { h->gn_fused = (int)value; return 0; }
     if (!strcmp(name, "im2col_tma")) { h->use_im2col_tma = value != 0; return 0; }
     if (!strcmp(name, "tcgen05")) {
         h->use_tcgen05 = value != 0;

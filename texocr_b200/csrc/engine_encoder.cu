@@ -153,6 +153,7 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
     ENSURE(h->rawDs, (size_t)g.P[2] * 256 * 4);
     ENSURE(h->col, (size_t)g.P[2] * 576 * 4);
     ENSURE(h->gn_partial, (size_t)B * 32 * 32 * 2 * 8);
+    ENSURE(h->gn_part, (size_t)((g.P[2] >> 5) + B + 1) * 64 * 4);
     for (int i = 0; i < 4; ++i) ENSURE(h->gn_stats[i], (size_t)B * 32 * 2 * 4);
     float* stats[4] = {h->gn_stats[0].as<float>(), h->gn_stats[1].as<float>(), h->gn_stats[2].as<float>(), h->gn_stats[3].as<float>()};
     double* partial = h->gn_partial.as<double>();
@@ -173,7 +174,11 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
     size_t ci = 0;
     const int depths[3] = {2, 4, 6};
     // conv: split GEMM, through im2col unless 1x1/s1
-    auto conv = [&](const ConvW& cw, Pair in, int lin, int lout, float* out) -> int {
+    // GroupNorm statistics of a convolution's fp32 output: block partial sums (gn_block.cuh) left by the GEMM epilogue when
+    // every image has the same size and a multiple of 32 pixel rows at the output level, by the stand-alone kernel otherwise
+    // (identical bits either way), then one small kernel that adds an image's blocks in order.
+    auto fused_ok = [&](int level) { return h->gn_fused && g.uni_h > 0 && (((long)(g.uni_h >> level) * (g.uni_w >> level)) % 32) == 0; };
+    auto conv = [&](const ConvW& cw, Pair in, int lin, int lout, float* out, float* stt) -> int {
         const long M = g.P[lout];
         const int K = cw.k * cw.k * cw.cin;
         const void *a_hi = in.hi, *a_lo = in.lo;
@@ -192,13 +197,15 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
             ga.lda = cw.cin;
             ga.im2col = {cw.k, cw.stride, pad_lo, cw.cin, g.uni_w >> lin, g.uni_h >> lin, B, g.uni_w >> lout, g.uni_h >> lout};
         }
+        const bool fused = fused_ok(lout);
+        if (fused) { ga.gn_part = h->gn_part.as<float>(); ga.gn_rpi = (g.uni_h >> lout) * (g.uni_w >> lout); }
         if (!tc_gemm_supported(ga)) return fail(h, TEXOCR_ERR_ARG, "backbone conv %s not supported by the tcgen05 GEMM", cw.name.c_str());
         LAUNCH(KC_CONV, 1, gemm_bytes(ga, 4), gemm_flops(ga), launch_gemm_tc(ga, st));
-        return 0;
-    };
-    auto gstats = [&](const float* raw, int C, int level, float* stt) -> int {
-        LAUNCH(KC_GN_STATS, 2, (double)g.P[level] * C * 4, 0.0,
-               launch_gn_stats(raw, C, level, g.d_img_off, B, nchunk_for(g.P[level], B), partial, stt, st));
+        if (!fused)
+            LAUNCH(KC_GN_STATS, 1, (double)M * cw.cout * 4, 0.0,
+                   launch_gn_stats_blocks(out, cw.cout, lout, g.d_img_off, B, M, h->gn_part.as<float>(), st));
+        LAUNCH(KC_GN_STATS, 1, (double)((M >> 5) + B) * 256, 0.0,
+               launch_gn_finalize_blocks(h->gn_part.as<float>(), cw.cout, lout, g.d_img_off, B, stt, st));
         return 0;
     };
     auto gapply = [&](GnApplyArgs& a, Pair out, int level, double bytes_per) -> int {
@@ -216,27 +223,23 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
             const ConvW& c3 = h->convs[ci++];
             const int Lout = Lx + (c2.stride == 2 ? 1 : 0);
             if (ds) {
-                if ((r = conv(*ds, x, Lx, Lout, h->rawDs.as<float>()))) return r;
-                if ((r = gstats(h->rawDs.as<float>(), ds->cout, Lout, stats[3]))) return r;
+                if ((r = conv(*ds, x, Lx, Lout, h->rawDs.as<float>(), stats[3]))) return r;
             }
-            if ((r = conv(c1, x, Lx, Lx, h->rawMid.as<float>()))) return r;
-            if ((r = gstats(h->rawMid.as<float>(), c1.cout, Lx, stats[0]))) return r;
+            if ((r = conv(c1, x, Lx, Lx, h->rawMid.as<float>(), stats[0]))) return r;
             Pair m1 = pair_of(h->actMid, (size_t)g.P[Lx] * c1.cout);
             {
                 GnApplyArgs a{};
                 a.raw = h->rawMid.as<float>(); a.stats = stats[0]; a.gamma = c1.gamma; a.beta = c1.beta; a.C = c1.cout; a.relu = 1;
                 if ((r = gapply(a, m1, Lx, 8))) return r;
             }
-            if ((r = conv(c2, m1, Lx, Lout, h->rawMid2.as<float>()))) return r;
-            if ((r = gstats(h->rawMid2.as<float>(), c2.cout, Lout, stats[1]))) return r;
+            if ((r = conv(c2, m1, Lx, Lout, h->rawMid2.as<float>(), stats[1]))) return r;
             Pair m2 = pair_of(h->actMid2, (size_t)g.P[Lout] * c2.cout);
             {
                 GnApplyArgs a{};
                 a.raw = h->rawMid2.as<float>(); a.stats = stats[1]; a.gamma = c2.gamma; a.beta = c2.beta; a.C = c2.cout; a.relu = 1;
                 if ((r = gapply(a, m2, Lout, 8))) return r;
             }
-            if ((r = conv(c3, m2, Lout, Lout, h->raw3.as<float>()))) return r;
-            if ((r = gstats(h->raw3.as<float>(), c3.cout, Lout, stats[2]))) return r;
+            if ((r = conv(c3, m2, Lout, Lout, h->raw3.as<float>(), stats[2]))) return r;
             Pair out = pair_of(*pingpong[pp], (size_t)g.P[Lout] * c3.cout);
             {
                 GnApplyArgs a{};

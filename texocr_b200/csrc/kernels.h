@@ -61,6 +61,10 @@ struct GemmArgs {
     // [64j, 64j+64) (W is [N, K]); A has N/64 * a_block_k columns.  0 = ordinary GEMM.  (per-head value projection of the absorbed
     // attention: C_h [256] -> 64 values with Wv_h)
     int a_block_k;
+    // tcgen05 path, EPI_STORE / fp32 output of a convolution over same-size images of gn_rpi pixel rows each (gn_rpi % 32 == 0):
+    // the epilogue also leaves the GroupNorm(32) partial sums of every 32-row block, gn_part[(row >> 5) + image][32][2]
+    // (gn_block.cuh; summed per image by launch_gn_finalize_blocks).  null = off
+    float* gn_part; int gn_rpi;
     // debug (engine option attn_trace): per-CTA residency sums of the launch: [0] ns waiting for the predecessor grid,
     // [1] ns from there to CTA exit, [2] CTAs.  null = off
     unsigned long long* dbg;
@@ -72,6 +76,12 @@ cudaError_t launch_stem_conv(const float* img, const float* w /*[49][64] std*/, 
                              const int* img_hw, int nimg, int total_p1, cudaStream_t st);
 cudaError_t launch_gn_stats(const float* raw, int C, int level, const int* img_off, int nimg, int nchunk,
                             double* partial, float* stats, cudaStream_t st);
+// bf16 tier: block-partial statistics (gn_block.cuh).  launch_gn_stats_blocks is the stand-alone producer of the partials
+// (ragged batches, or images whose row count is not a multiple of 32); launch_gn_finalize_blocks turns an image's partials
+// into stats[b][32] = (mean, rstd).  part holds ((total rows >> 5) + nimg + 1) * 64 floats.
+cudaError_t launch_gn_stats_blocks(const float* raw, int C, int level, const int* img_off, int nimg, long total_rows, float* part,
+                                   cudaStream_t st);
+cudaError_t launch_gn_finalize_blocks(const float* part, int C, int level, const int* img_off, int nimg, float* stats, cudaStream_t st);
 struct GnApplyArgs {
     const float* raw; const float* stats; const float* gamma; const float* beta;       // main input
     const float* raw2; const float* stats2; const float* gamma2; const float* beta2;   // optional normalised residual

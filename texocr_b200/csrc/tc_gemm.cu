@@ -2,11 +2,13 @@
 //
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring (STAGES x {A 128x64, W BNx64})
 //   -> tcgen05.mma.cta_group::1.kind::f16 issued by one thread, accumulator 128 lanes x BN columns in TMEM
-//   -> tcgen05.ld (32x32b) by four epilogue warps, one accumulator row per thread, fused epilogue
-//      (bias / GLU+residual / GeGLU / bias+residual), vectorised row-segment stores.
+//   -> tcgen05.ld (32x32b) by four or eight epilogue warps, one accumulator row per thread, fused epilogue
+//      (bias / GLU+residual / GeGLU / bias+residual / GroupNorm partial sums), vectorised row-segment stores.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (warp w may only touch TMEM lanes 32*(w%4)..+31, so four consecutive warps cover the 128 rows).
+// Warp roles (64 + 128 * EW threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = epilogue
+// (warp w may only touch TMEM lanes 32*(w%4)..+31, so four consecutive warps cover the 128 rows).  EW = 2: a second
+// epilogue warpgroup (warps 6..9) takes every other column chunk of the tile (halves of the single chunk when BN = 32) --
+// the epilogue, not the MMA loop, bounds the K <= 1024 GEMMs of this model.
 //
 // SPLIT = 3 is the "bf16x3" mode used for the ill-conditioned ResNet backbone: both operands are
 // given as hi + lo bf16 pairs and every k-slice issues hi.hi + hi.lo + lo.hi into the same accumulator, which
@@ -19,11 +21,13 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "gn_block.cuh"
 #include "tc_gemm.h"
 
 int g_tc_persistent = 1;          // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
 int g_tc_min_ctas = 120;          // tile width rule: narrow the N tile (128 -> 64 -> 32) while the grid would have fewer CTAs than this
 int g_tc_persistent_stages = 0;   // 0 = as many ring stages as fit in 200 KB; n > 0 caps them (leaves shared memory to co-resident kernels)
+int g_tc_epi_warps = 8;           // texocr_set_option("gemm_epi_warps"): 4 or 8 epilogue warps per CTA
 
 namespace {
 
@@ -38,6 +42,9 @@ struct TcParams {
     int stages;       // persistent kernel: ring stages actually used (<= SmemP::STAGES)
     int a_block_k;    // block-diagonal GEMM (one-tile-per-CTA kernel, BN = 64): n-tile j reads A columns from j * a_block_k
     unsigned long long* dbg;      // debug residency sums (GemmArgs::dbg)
+    // GroupNorm partial sums of the fp32 output (EPI_STORE, M rows = same-size images of gn_rpi rows each, gn_rpi % 32 == 0):
+    // gn_part[(row >> 5) + image][32][2], see gn_block.cuh.  null = off
+    float* gn_part; int gn_cpg, gn_rpi;
 };
 TX_DEVINL unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -103,6 +110,16 @@ TX_DEVINL void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+TX_DEVINL void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), LBO unused (=1).
 // Bit layout: cute::UMMA::SmemDescriptor (start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
 TX_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
@@ -140,24 +157,43 @@ TX_DEVINL void stage_copy(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int la
     }
 }
 
-template <int BN, int EPI, typename TC>
+// [32 rows x 128 bytes] of fp32 outputs, staging -> global like stage_copy<128, true>, and on the way the lane's column sums /
+// sums of squares over its 8 rows (gn_block.cuh)
+TX_DEVINL void stage_copy_gn(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int lane, int rows_ok, float* s, float* q) {
+    const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rr;
+        if (row < rows_ok) {
+            const float4 f = *reinterpret_cast<const float4*>(stg + row * STG_STRIDE + ch * 16);
+            *reinterpret_cast<float4*>(gptr + (size_t)row * grow_bytes + ch * 16) = f;
+            gn_block_acc(s, q, f);
+        }
+    }
+}
+
+template <int BN, int EPI, typename TC, int EW>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
                              uint8_t* smem_idle, uint32_t parity = 0, unsigned long long dbg_t0 = 0ull) {
-    const int q = warp & 3;
-    uint8_t* stg = smem_idle + q * STG_WARP;
+    constexpr int CW = (EW == 2 && BN == 32) ? 16 : 32;         // columns per tcgen05.ld chunk
+    const int q = warp & 3;                                     // TMEM lane quarter of this warp
+    const int ew = warp - 2, eg = ew >> 2;                      // epilogue warp / warpgroup index
+    uint8_t* stg = smem_idle + ew * STG_WARP;
     uint8_t* my = stg + lane * STG_STRIDE;                      // this thread's staged row
     const int mrow0 = m0 + q * 32;
     const int rows_ok = min(32, p.M - mrow0);                   // <= 0: nothing of this warp's rows is inside the matrix
     constexpr bool PAIRS = (EPI == EPI_GLU_RES || EPI == EPI_GEGLU);
-    constexpr int NOUT = PAIRS ? 16 : 32;
+    constexpr int NOUT = PAIRS ? CW / 2 : CW;
     using TO = typename std::conditional<EPI == EPI_STORE, TC, typename std::conditional<EPI == EPI_GEGLU, bf16, float>::type>::type;
     constexpr int RB = NOUT * (int)sizeof(TO);
+    const int cfirst = eg * CW;                                 // this warp's first chunk
     // Narrow tiles (the latency-bound decode GEMMs): fetch the thread's residual row while the MMAs are still running --
     // it does not depend on the accumulator, and its L2 round trip would otherwise sit behind the tmem_full wait.
     constexpr bool PRE_RES = BN == 32 && (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES);
     float rpre[PRE_RES ? NOUT : 1];
     if (PRE_RES) {
-        const int ncol = PAIRS ? (n0 >> 1) : n0, nvalid_out = PAIRS ? (min(32, p.N - n0) >> 1) : min(32, p.N - n0);
+        const int nf = n0 + cfirst;
+        const int ncol = PAIRS ? (nf >> 1) : nf, nvalid_out = PAIRS ? (max(0, min(CW, p.N - nf)) >> 1) : max(0, min(CW, p.N - nf));
         const float* rp = p.res + (size_t)(mrow0 + lane) * p.ldres + ncol;
 #pragma unroll
         for (int i = 0; i < (PRE_RES ? NOUT : 0); i += 4) {
@@ -166,12 +202,13 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
             rpre[i] = t.x; rpre[i + 1] = t.y; rpre[i + 2] = t.z; rpre[i + 3] = t.w;
         }
     }
-    // bias of the tile's first 32 columns: a weight, fetched before the wait as well
-    float bpre[32];
+    // bias of the warp's first chunk: a weight, fetched before the wait as well (narrow tiles only: 32 more live registers)
+    constexpr bool PRE_BIAS = BN == 32 || EW == 1;
+    float bpre[PRE_BIAS ? CW : 4];
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
+    for (int i = 0; i < (PRE_BIAS ? CW : 0); i += 4) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && n0 + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+        if (p.bias && n0 + cfirst + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cfirst + i));
         bpre[i] = b.x; bpre[i + 1] = b.y; bpre[i + 2] = b.z; bpre[i + 3] = b.w;
     }
     mbar_wait(tmem_full, parity);
@@ -180,24 +217,25 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
     float am_best = -INFINITY;                                  // EPI_ARGMAX: running maximum of this thread's row over the tile
     int am_idx = 0x7fffffff;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
-        if (dbg_t0 && c0 == 0) atomicAdd(p.dbg + 7, gtime_ns() - dbg_t0);      // debug: -> first accumulator chunk in registers
+    for (int c0 = cfirst; c0 < BN; c0 += EW * CW) {
+        uint32_t raw[CW];
+        if constexpr (CW == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+        else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, raw);
+        if (dbg_t0 && c0 == cfirst) atomicAdd(p.dbg + 7, gtime_ns() - dbg_t0);      // debug: -> first accumulator chunk in registers
         const int n = n0 + c0;
         if (rows_ok <= 0 || n >= p.N) continue;                 // warp-uniform
-        const int nvalid = min(32, p.N - n);                    // multiple of 8
+        const int nvalid = min(CW, p.N - n);                    // multiple of 8
         const int ncol = PAIRS ? (n >> 1) : n, nvalid_out = PAIRS ? (nvalid >> 1) : nvalid;
-        float v[32];
+        float v[CW];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
         if (p.bias) {
-            if (c0 == 0) {
+            if (PRE_BIAS && c0 == cfirst) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += bpre[i];
+                for (int i = 0; i < CW; ++i) v[i] += bpre[PRE_BIAS ? i : 0];
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
+                for (int i = 0; i < CW; i += 4) {
                     if (i < nvalid) {
                         const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
                         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
@@ -207,7 +245,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         }
         if constexpr (EPI == EPI_ARGMAX) {                      // ascending scan, strict >: the first maximum wins (torch argmax)
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 0; i < CW; ++i)
                 if (i < nvalid && v[i] > am_best) { am_best = v[i]; am_idx = n + i; }
             continue;
         }
@@ -242,10 +280,20 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         TO* mine = reinterpret_cast<TO*>(my);
 #pragma unroll
         for (int i = 0; i < NOUT; i += 4) st4(mine + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
-        if (dbg_t0 && c0 == 0) atomicAdd(p.dbg + 8, gtime_ns() - dbg_t0);      // debug: -> first chunk computed and staged
+        if (dbg_t0 && c0 == cfirst) atomicAdd(p.dbg + 8, gtime_ns() - dbg_t0);      // debug: -> first chunk computed and staged
         __syncwarp();
-        stage_copy<RB, true>(stg, reinterpret_cast<uint8_t*>(reinterpret_cast<TO*>(p.C) + (size_t)mrow0 * p.ldc + ncol),
-                             (size_t)p.ldc * sizeof(TO), lane, rows_ok, nvalid_out * (int)sizeof(TO));
+        uint8_t* gdst = reinterpret_cast<uint8_t*>(reinterpret_cast<TO*>(p.C) + (size_t)mrow0 * p.ldc + ncol);
+        bool done = false;
+        if constexpr (EPI == EPI_STORE && std::is_same<TC, float>::value && CW == 32) {
+            if (p.gn_part && nvalid == 32) {                    // convolution output: GroupNorm partial sums of the tile on its way out
+                float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+                stage_copy_gn(stg, gdst, (size_t)p.ldc * 4, lane, rows_ok, gs, gq);
+                const int slot = (mrow0 >> 5) + mrow0 / p.gn_rpi;
+                gn_block_finish(gs, gq, lane, p.gn_cpg, n, p.gn_part + (size_t)slot * 64);
+                done = true;
+            }
+        }
+        if (!done) stage_copy<RB, true>(stg, gdst, (size_t)p.ldc * sizeof(TO), lane, rows_ok, nvalid_out * (int)sizeof(TO));
         __syncwarp();
     }
     if constexpr (EPI == EPI_ARGMAX) {
@@ -265,8 +313,8 @@ template <int BN, int SPLIT, int NSTG = 0> struct Smem {
     static constexpr int TOTAL = STAGES * STAGE + 1024 /*align slack*/ + BARS;
 };
 
-template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int EPI, typename TC, int SPLIT, int NSTG, int EW>
+__global__ void __launch_bounds__(64 + 128 * EW, EW)         // EW = 2: <= 102 registers, so that two 320-thread CTAs still share an SM
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
     using S = Smem<BN, SPLIT, NSTG>;
@@ -370,7 +418,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         const unsigned long long e_t0 = (p.dbg && threadIdx.x == 64) ? gtime_ns() : 0ull;
         pdl_wait();        // the epilogue reads the residual stream
-        epilogue_tile<BN, EPI, TC>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem, 0, e_t0);
+        epilogue_tile<BN, EPI, TC, EW>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem, 0, e_t0);
         if (p.dbg && threadIdx.x == 64) atomicAdd(p.dbg + 5, gtime_ns() - e_t0);          // epilogue warp: entry -> its rows stored
     }
     tcgen05_fence_before();
@@ -396,14 +444,14 @@ template <int BN, int SPLIT> struct SmemP {
     static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
     static constexpr int NOPS = SPLIT == 3 ? 2 : 1;
     static constexpr int STAGE = NOPS * (A_BYTES + W_BYTES);
-    static constexpr int STG = 4 * STG_WARP;                                   // dedicated epilogue staging (the ring never idles)
+    static constexpr int STG = 8 * STG_WARP;                                   // dedicated epilogue staging (the ring never idles)
     static constexpr int STAGES = (200 * 1024 - STG) / STAGE > 8 ? 8 : (200 * 1024 - STG) / STAGE;
     static constexpr int BARS = 256;
     static constexpr int TOTAL = STAGES * STAGE + STG + 1024 + BARS;
 };
 
-template <int BN, int EPI, typename TC, int SPLIT>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int EPI, typename TC, int SPLIT, int EW>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
     using S = SmemP<BN, SPLIT>;
@@ -427,7 +475,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4 * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -506,7 +554,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            epilogue_tile<BN, EPI, TC>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
+            epilogue_tile<BN, EPI, TC, EW>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);              // all of this warp's tcgen05.ld of the buffer have completed
@@ -617,28 +665,37 @@ static cudaError_t tma_map_im2col_bf16(const void* ptr, const GemmArgs::Im2col& 
 
 namespace {
 
-template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
-cudaError_t launch_cfg2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+template <int BN, int EPI, typename TC, int SPLIT, int NSTG, int EW>
+cudaError_t launch_cfg3(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
                         cudaStream_t st) {
     using S = Smem<BN, SPLIT, NSTG>;
+    static_assert(S::STAGES * S::STAGE >= 4 * EW * STG_WARP, "epilogue staging lives in the idle pipeline stages");
     static bool attr_set = false;
-    auto kern = tc_gemm_kernel<BN, EPI, TC, SPLIT, NSTG>;
+    auto kern = tc_gemm_kernel<BN, EPI, TC, SPLIT, NSTG, EW>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    return launch_pdl(PDL_GEMM, kern, grid, dim3(192), (size_t)S::TOTAL, st, a, w, a2, w2, p);
+    return launch_pdl(PDL_GEMM, kern, grid, dim3(64 + 128 * EW), (size_t)S::TOTAL, st, a, w, a2, w2, p);
+}
+template <int BN, int EPI, typename TC, int SPLIT, int NSTG>
+cudaError_t launch_cfg2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                        cudaStream_t st) {
+    if constexpr (EPI != EPI_ARGMAX) {
+        if (g_tc_epi_warps == 8) return launch_cfg3<BN, EPI, TC, SPLIT, NSTG, 2>(a, w, a2, w2, p, st);
+    }
+    return launch_cfg3<BN, EPI, TC, SPLIT, NSTG, 1>(a, w, a2, w2, p, st);
 }
 
-template <int BN, int EPI, typename TC, int SPLIT>
-cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
-                              long tiles, cudaStream_t st) {
+template <int BN, int EPI, typename TC, int SPLIT, int EW>
+cudaError_t launch_persistent2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                               long tiles, cudaStream_t st) {
     using S = SmemP<BN, SPLIT>;
     static bool attr_set = false;
     static int sms = 0;
-    auto kern = tc_gemm_persistent_kernel<BN, EPI, TC, SPLIT>;
+    auto kern = tc_gemm_persistent_kernel<BN, EPI, TC, SPLIT, EW>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) return e;
@@ -651,7 +708,13 @@ cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const 
     TcParams pp = p;
     pp.stages = g_tc_persistent_stages > 0 ? std::max(2, std::min(g_tc_persistent_stages, S::STAGES)) : S::STAGES;
     const size_t smem = (size_t)S::TOTAL - (size_t)(S::STAGES - pp.stages) * S::STAGE;
-    return launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(192), smem, st, a, w, a2, w2, pp);
+    return launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(64 + 128 * EW), smem, st, a, w, a2, w2, pp);
+}
+template <int BN, int EPI, typename TC, int SPLIT>
+cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
+                              long tiles, cudaStream_t st) {
+    if (g_tc_epi_warps == 8) return launch_persistent2<BN, EPI, TC, SPLIT, 2>(a, w, a2, w2, p, tiles, st);
+    return launch_persistent2<BN, EPI, TC, SPLIT, 1>(a, w, a2, w2, p, tiles, st);
 }
 
 template <int BN, int EPI, typename TC, int SPLIT>
@@ -712,7 +775,14 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     }
     if (g.epi == EPI_ARGMAX) bn = 32;      // the partial layout is defined on 32-column tiles
     TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1, 0, 0, 0, 0, 0, 0};
+    p.stages = 0; p.gn_part = nullptr; p.gn_cpg = 0; p.gn_rpi = 0;
     p.a_block_k = g.a_block_k; p.dbg = g.dbg;
+    if (g.gn_part) {
+        if (g.epi != EPI_STORE || g.dt_c != DT_F32 || g.bias || g.N % 32 != 0 || g.gn_rpi <= 0 || g.gn_rpi % 32 != 0 || g.M % g.gn_rpi != 0 ||
+            g.N / 32 > 32 || (g.N / 32) & (g.N / 32 - 1))
+            return cudaErrorInvalidValue;
+        p.gn_part = g.gn_part; p.gn_cpg = g.N / 32; p.gn_rpi = g.gn_rpi;
+    }
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
     const bool conv = g.im2col.ksz > 0;
