@@ -395,21 +395,25 @@ def test_tma_im2col_convolutions_bit_identical_to_explicit_im2col(m16):
 def test_groupnorm_partials_from_gemm_epilogue_bit_identical_to_block_kernel(m16):
     """bf16 tier: the GroupNorm statistics come from per-32-row-block partial sums with one summation order (csrc/gn_block.cuh),
     produced either by the epilogue of the convolution GEMM (same-size batches, rows per image a multiple of 32 at that level)
-    or by the stand-alone block kernel (everything else).  Same bits from both, for 4 and 8 epilogue warps, and a ragged batch
-    containing the same images gives the same rows."""
+    or by the stand-alone block kernel (everything else).  Same bits from both, for 4 and 8 epilogue warps, with and without the
+    128 x 256 tiles of the wide convolutions (same k order per output element), and a ragged batch containing the same images
+    gives the same rows."""
     eng = m16.engine()
     try:
-        for (B, H, W) in ((3, 64, 384), (2, 160, 1008), (2, 48, 208), (4, 32, 128), (130, 64, 384)):
+        for (B, H, W) in ((3, 64, 384), (2, 160, 1008), (2, 48, 208), (4, 32, 128), (200, 64, 384)):
             img = synth.synth_images(B, H, W, seed=11 + B).cuda()
             outs = []
-            for fused, warps in ((0, 8), (1, 8), (1, 4)):
+            for fused, warps, bn256 in ((0, 8, 0), (1, 8, 1), (1, 4, 1), (1, 8, 0), (0, 4, 1)):
                 eng.set_option("gn_fused", fused)
                 eng.set_option("gemm_epi_warps", warps)
+                eng.set_option("gemm_bn256", bn256)
                 outs.append(m16.encoder(img))
             assert torch.isfinite(outs[0]).all(), (B, H, W)
-            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (B, H, W)
+            for o in outs[1:]:
+                assert torch.equal(outs[0], o), (B, H, W)
         eng.set_option("gn_fused", 1)
         eng.set_option("gemm_epi_warps", 8)
+        eng.set_option("gemm_bn256", 1)
         a = synth.synth_images(2, 64, 384, seed=3).cuda()
         b = synth.synth_images(1, 48, 208, seed=4).cuda()
         uni = m16.encoder(a)                                              # fused partials
@@ -419,3 +423,4 @@ def test_groupnorm_partials_from_gemm_epilogue_bit_identical_to_block_kernel(m16
     finally:
         eng.set_option("gn_fused", 1)
         eng.set_option("gemm_epi_warps", 8)
+        eng.set_option("gemm_bn256", 1)

@@ -39,6 +39,7 @@ struct SeqArgs {
     const int* step;                   // self: positions already cached (= index of this step's row)
     bf16* o; int ldo;                  // [batch, ldo]: head h at h*256
     int batch;
+    int mid_trigger;                   // programmatic dependent released when the warp's last chunk has been issued instead of at entry
     unsigned long long* dbg;           // debug: [0] wait, [1] first stage, [2] loop, [3] epilogue ns of every warp's first unit, [4] count; [5] warp residency, [6] warps
 };
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(32 * SW, SEQ_MINB) attn_seq_kernel(const __gri
     const uint32_t ostg = smem_u32(base + SW * SNS * STAGE + warp * OSTG);          // this warp's output staging
     uint64_t* full = reinterpret_cast<uint64_t*>(base + SW * SNS * STAGE + SW * OSTG) + warp * SNS;
 
-    pdl_launch_dependents();
+    if (!a.mid_trigger) pdl_launch_dependents();
     const unsigned long long t_entry = a.dbg ? gtime() : 0ull;
     if (lane == 0) {
         if (warp == 0) {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(32 * SW, SEQ_MINB) attn_seq_kernel(const __gri
         }
     };
     int iu = gw, ic = 0, i_row0 = 0, i_nc = 0, i_nch = 0, issued = 0;       // issue cursor (every lane tracks it, lane 0 acts)
+    bool released = !a.mid_trigger;
     auto refill = [&](int consumed) {       // chunks below `consumed` are released: up to SNS chunks may be in the ring
         while (iu < units && issued < consumed + SNS) {
             if (ic == 0) { unit_rows(iu, i_row0, i_nc); i_nch = ((SELF ? i_nc + 1 : i_nc) + CH - 1) / CH; }
@@ -154,6 +156,8 @@ __global__ void __launch_bounds__(32 * SW, SEQ_MINB) attn_seq_kernel(const __gri
             ++issued;
             if (++ic == i_nch) { ic = 0; iu += nw; }
         }
+        // the warp's last chunk is on its way: at most SNS stages and the output are left -- about the dependent's launch + prologue
+        if (!released && iu >= units && consumed > 0) { pdl_launch_dependents(); released = true; }
     };
     // cross: the memory rows and the token offsets were written before the generate loop started -- stream before the wait
     if (!SELF) refill(0);
@@ -364,7 +368,7 @@ cudaError_t launch_attn_seq(const AttnAbsArgs& a, int max_ctas, cudaStream_t st)
     SeqArgs k{};
     k.q = (const bf16*)a.q; k.ldq = a.ldq; k.k_off = a.k_off; k.uni_nk = a.znew ? 0 : a.uni_nk; k.o = (bf16*)a.o; k.ldo = a.ldo; k.batch = a.batch;
     k.znew = (const bf16*)a.znew; k.ldz = a.ldz; k.cache = (bf16*)const_cast<void*>(a.latent); k.tcap = a.tcap; k.step = a.step;
-    k.dbg = a.dbg;
+    k.dbg = a.dbg; k.mid_trigger = (g_texocr_pdl_mid >> 1) & 1;
     const int want = (a.batch + SW - 1) / SW;
     const int cap = std::max(1, std::min(max_ctas, occ[si] * (sms > 0 ? sms : 148)));
     const int grid = want < cap ? want : cap;

@@ -410,6 +410,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "poison")) { h->poison = value != 0; return 0; }
     if (!strcmp(name, "attn_ctas_per_sm")) { h->attn_ctas_per_sm = (int)std::max<int64_t>(1, std::min<int64_t>(8, value)); drop_graphs(h); return 0; }
     if (!strcmp(name, "dbg_skip")) { h->dbg_skip = (int)value; drop_graphs(h); return 0; }
+    if (!strcmp(name, "pdl_mid")) { g_texocr_pdl_mid = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "pdl")) {
         g_texocr_pdl = (int)value;
         drop_graphs(h);
@@ -428,6 +429,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "gemm_persistent")) { g_tc_persistent = (int)value; return 0; }
     if (!strcmp(name, "gemm_min_ctas")) { g_tc_min_ctas = (int)value; drop_graphs(h); return 0; }
     if (!strcmp(name, "gemm_persistent_stages")) { g_tc_persistent_stages = (int)value; return 0; }
+    if (!strcmp(name, "gemm_bn256")) { g_tc_bn256 = (int)value; return 0; }
     if (!strcmp(name, "gemm_epi_warps")) { g_tc_epi_warps = value == 4 ? 4 : 8; drop_graphs(h); return 0; }
     if (!strcmp(name, "gn_fused")) { h->gn_fused = (int)value; return 0; }
     if (!strcmp(name, "im2col_tma")) { h->use_im2col_tma = value != 0; return 0; }

@@ -6,6 +6,10 @@ std::recursive_mutex g_dev_mu;
 // bits 0..5: programmatic dependent launch per kernel family (kernels.h); bit 8 / 9: LayerNorm / GEMM kernels release their
 // dependents only after their stores (experiment switches; the default is an early trigger everywhere).
 int g_texocr_pdl = 0x3f;
+// where a kernel releases its programmatic dependent: bit set = late in the kernel (1.5-2 us before its end: the dependent's CTAs are
+// scheduled when their launch + prologue just fits, instead of sitting in SM slots for the kernel's whole run); 0 = at entry.
+// 1 = tcgen05 GEMM (accumulator complete), 2 = decode attention (warp's last chunk issued), 4 = LayerNorm (row loaded), 8 = token kernel
+int g_texocr_pdl_mid = 7;
 
 int fail(texocr_handle* h, int code, const char* fmt, ...) {
     char buf[512];

@@ -15,6 +15,7 @@ extern int g_tc_persistent;
 extern int g_tc_persistent_stages;
 extern int g_tc_min_ctas;
 extern int g_tc_epi_warps;
+extern int g_tc_bn256;
 extern int g_attn_full_tail;
 extern int g_attn_abs_minb;
 

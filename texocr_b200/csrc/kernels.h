@@ -10,6 +10,7 @@ enum { DT_F32 = 0, DT_BF16 = 1 };
 // Programmatic dependent launch per kernel family: bit k of g_texocr_pdl enables it for family k (engine_core.cu).
 enum { PDL_GEMM = 0, PDL_LN = 1, PDL_EMBED = 2, PDL_ARGMAX = 3, PDL_ATTN_TMA = 4, PDL_ATTN_SIMPLE = 5 };
 extern int g_texocr_pdl;
+extern int g_texocr_pdl_mid;      // engine_core.cu
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(int family, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

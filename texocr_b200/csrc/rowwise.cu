@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
     if (row >= a.rows) { if (a.late_trigger) pdl_launch_dependents(); return; }
     float v[8];
     ld8cg(a.in + (size_t)row * D + col, v);
+    if (a.late_trigger == 2 && v[0] == v[0]) pdl_launch_dependents();      // once the row has arrived: the predicate makes the release wait for the load (a NaN row releases at exit)
     if (a.g1) layer_norm8(v, g1, b1);
     if (a.o1f) store8(a.o1f + (size_t)row * D + col, v);
     if (a.o1a) store8(reinterpret_cast<TAct*>(a.o1a) + (size_t)row * D + col, v);
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) ln2_kernel(Ln2Args a) {
         layer_norm8(v, g2, b2);
         if (a.o2a) store8(reinterpret_cast<TAct*>(a.o2a) + (size_t)row * D + col, v);
     }
-    if (a.late_trigger) pdl_launch_dependents();
+    if (a.late_trigger == 1) pdl_launch_dependents();
 }
 
 template <typename TAct>
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 
 cudaError_t launch_ln2(const Ln2Args& a_in, cudaStream_t st) {
     Ln2Args a = a_in;
-    a.late_trigger = (g_texocr_pdl >> 8) & 1;
+    a.late_trigger = (g_texocr_pdl_mid & 4) ? 2 : ((g_texocr_pdl >> 8) & 1);
     if (a.rows <= 0) return cudaSuccess;
     const int blocks = (a.rows + 7) / 8;
     if (a.dt_a == DT_F32) return launch_pdl(PDL_LN, ln2_kernel<float>, dim3(blocks), dim3(256), 0, st, a);

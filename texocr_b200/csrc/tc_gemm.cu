@@ -27,6 +27,7 @@
 int g_tc_persistent = 1;          // texocr_set_option("gemm_persistent"): persistent double-buffered kernel for GEMMs of >= 296 tiles
 int g_tc_min_ctas = 120;          // tile width rule: narrow the N tile (128 -> 64 -> 32) while the grid would have fewer CTAs than this
 int g_tc_persistent_stages = 0;   // 0 = as many ring stages as fit in 200 KB; n > 0 caps them (leaves shared memory to co-resident kernels)
+int g_tc_bn256 = 1;               // texocr_set_option("gemm_bn256"): 128 x 256 tiles for the wide split-operand convolutions
 int g_tc_epi_warps = 8;           // texocr_set_option("gemm_epi_warps"): 4 or 8 epilogue warps per CTA
 
 namespace {
@@ -212,6 +213,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         bpre[i] = b.x; bpre[i + 1] = b.y; bpre[i + 2] = b.z; bpre[i + 3] = b.w;
     }
     mbar_wait(tmem_full, parity);
+    if (p.late_trigger == 2) pdl_launch_dependents();           // one-tile kernel: what is left of this CTA is about as long as the dependent's launch + prologue
     if (dbg_t0) atomicAdd(p.dbg + 6, gtime_ns() - dbg_t0);      // debug: epilogue warp entry -> accumulator complete
     tcgen05_fence_after();
     float am_best = -INFINITY;                                  // EPI_ARGMAX: running maximum of this thread's row over the tile
@@ -421,13 +423,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epilogue_tile<BN, EPI, TC, EW>(tmem_full, tmem_base, warp, lane, m0, n0, p, smem, 0, e_t0);
         if (p.dbg && threadIdx.x == 64) atomicAdd(p.dbg + 5, gtime_ns() - e_t0);          // epilogue warp: entry -> its rows stored
     }
+    if (p.late_trigger == 2 && warp < 2) { mbar_wait(tmem_full, 0); pdl_launch_dependents(); }      // every thread of the CTA releases at the same point
     tcgen05_fence_before();
     __syncthreads();
     if (p.dbg && threadIdx.x == 0) {
         const unsigned long long t2 = gtime_ns();
         atomicAdd(p.dbg, dbg_t1 - dbg_t0); atomicAdd(p.dbg + 1, t2 - dbg_t1); atomicAdd(p.dbg + 2, 1ull);
     }
-    if (p.late_trigger) pdl_launch_dependents();
+    if (p.late_trigger == 1) pdl_launch_dependents();
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
@@ -440,12 +443,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // while the four epilogue warps drain buffer i & 1, and the TMA ring keeps running across tile boundaries.  In the
 // one-tile-per-CTA kernel above the tensor pipe sat idle during every epilogue (ncu: 20 % tensor-pipe active on the conv
 // GEMMs); here the epilogue is off the critical path as long as it is shorter than a tile's MMA loop.
-template <int BN, int SPLIT> struct SmemP {
+template <int BN, int SPLIT, int EW> struct SmemP {
     static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
     static constexpr int NOPS = SPLIT == 3 ? 2 : 1;
     static constexpr int STAGE = NOPS * (A_BYTES + W_BYTES);
-    static constexpr int STG = 8 * STG_WARP;                                   // dedicated epilogue staging (the ring never idles)
-    static constexpr int STAGES = (200 * 1024 - STG) / STAGE > 8 ? 8 : (200 * 1024 - STG) / STAGE;
+    static constexpr int STG = 4 * EW * STG_WARP;                              // dedicated epilogue staging (the ring never idles)
+    static constexpr int BUDGET = (BN == 256 ? 225 : 200) * 1024;             // 128 x 256 tiles of split operands: two 96 KB stages
+    static constexpr int STAGES = (BUDGET - STG) / STAGE > 8 ? 8 : (BUDGET - STG) / STAGE;
+    static_assert(STAGES >= 2, "the ring needs two stages");
     static constexpr int BARS = 256;
     static constexpr int TOTAL = STAGES * STAGE + STG + 1024 + BARS;
 };
@@ -454,7 +459,7 @@ template <int BN, int EPI, typename TC, int SPLIT, int EW>
 __global__ void __launch_bounds__(64 + 128 * EW, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
-    using S = SmemP<BN, SPLIT>;
+    using S = SmemP<BN, SPLIT, EW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nst = p.stages;
@@ -692,7 +697,7 @@ cudaError_t launch_cfg2(const CUtensorMap& a, const CUtensorMap& w, const CUtens
 template <int BN, int EPI, typename TC, int SPLIT, int EW>
 cudaError_t launch_persistent2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
                                long tiles, cudaStream_t st) {
-    using S = SmemP<BN, SPLIT>;
+    using S = SmemP<BN, SPLIT, EW>;
     static bool attr_set = false;
     static int sms = 0;
     auto kern = tc_gemm_persistent_kernel<BN, EPI, TC, SPLIT, EW>;
@@ -769,12 +774,15 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (mt * ((g.N + 63) / 64) < g_tc_min_ctas && g.N >= 64) bn = 32;
     const bool split = g.A2 != nullptr;
     if (split) bn = g.N <= 64 ? 64 : 128;
+    // 128 x 256 tiles (one MMA reads A once for 256 columns: the shared-memory operand reads of a 128 x 128 x 16 MMA take as long as
+    // the MMA itself) for the wide, deep convolutions; short-K ones are bound by the epilogue, which has four warps here
+    if (split && g_tc_bn256 && g.epi == EPI_STORE && g.dt_c == DT_F32 && !g.bias && g.N % 256 == 0 && g.K >= 256 && mt * (g.N / 256) >= 148 && g_tc_persistent) bn = 256;
     if (g.a_block_k) {
         if (split || g.im2col.ksz > 0 || g.N % 64 != 0) return cudaErrorInvalidValue;
         bn = 64;
     }
     if (g.epi == EPI_ARGMAX) bn = 32;      // the partial layout is defined on 32-column tiles
-    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl >> 9) & 1, 0, 0, 0, 0, 0, 0};
+    TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl_mid & 1) ? 2 : ((g_texocr_pdl >> 9) & 1), 0, 0, 0, 0, 0, 0};
     p.stages = 0; p.gn_part = nullptr; p.gn_cpg = 0; p.gn_rpi = 0;
     p.a_block_k = g.a_block_k; p.dbg = g.dbg;
     if (g.gn_part) {
@@ -799,6 +807,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
         else if ((e = get_map(g.A2, g.M, g.K, g.lda, BM, &a2)) != cudaSuccess) return e;
         if ((e = get_map(g.W2, g.N, g.K, g.ldw, bn, &w2)) != cudaSuccess) return e;
         if (bn == 64) return launch_epi<64, 3>(g, a, w, a2, w2, p, st);
+        if (bn == 256) return launch_persistent2<256, EPI_STORE, float, 3, 1>(a, w, a2, w2, p, mt * (g.N / 256), st);
         return launch_epi<128, 3>(g, a, w, a2, w2, p, st);
     }
     if (bn == 128) return launch_epi<128, 1>(g, a, w, a2, w2, p, st);
