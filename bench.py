@@ -65,6 +65,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.lo, self.hi = 0, None
+
+    def mark_begin(self):      # the timed region starts here: only samples between mark_begin and mark_end are reported
+        self.lo = len(self.lines)
+
+    def mark_end(self):
+        self.hi = len(self.lines)
 
     def start(self):
         try:
@@ -89,7 +96,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.lo:self.hi]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -278,7 +285,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="equations per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--in-flight", type=int, default=6, help="batches decoded concurrently per GPU (1 = one at a time)")
+    ap.add_argument("--in-flight", type=int, default=0, help="batches decoded concurrently per GPU (1 = one at a time; 0 = choose 5..8 so "
+                    "that the job's batches divide evenly over the replicas: a last round with idle replicas costs more than one replica more or less)")
     ap.add_argument("--branches", type=int, default=1, help="decode branches per batch when several batches are in flight")
     ap.add_argument("--total", type=int, default=0, help="strong scaling (BASELINE configs[4]): a fixed job of this many equations in "
                     "batches of --batch, contiguous runs of batches per rank; --steps is then the number of batches per rank")
@@ -335,12 +343,19 @@ def main():
     rows_per_batch = img_host.shape[0]
     out_host = torch.empty((rows_per_batch, MAX_LEN), dtype=torch.int64).pin_memory()
     stream = torch.cuda.current_stream()
+    if args.in_flight <= 0:          # 6 unless another count in 5..8 leaves fewer replicas idle in the last round (ties: nearest to 6)
+        def idle(n):
+            return (-args.steps) % n
+        args.in_flight = min((5, 6, 7, 8), key=lambda n: (idle(n), abs(n - 6)))
     n_fly = max(1, min(args.in_flight, args.steps))
     pipe = None
     if n_fly > 1:
         from texocr_b200.pipeline import GeneratePipeline
         pipe = GeneratePipeline(model, in_flight=n_fly, branches=args.branches)
         outs_host = [torch.empty((rows_per_batch, MAX_LEN), dtype=torch.int64).pin_memory() for _ in range(args.steps)]
+        # result buffers of the device-resident pass, allocated once: a cudaMalloc from a worker thread in the middle of the timed
+        # region (the caching allocator growing its pool for 20 kept results) serialises against the batches in flight
+        outs_dev = [torch.empty((rows_per_batch, MAX_LEN), dtype=torch.int64, device="cuda") for _ in range(args.steps)]
 
     def barrier():
         if dist is not None:
@@ -375,7 +390,7 @@ def main():
             gather_tokens(tok.cuda(non_blocking=True), world)
 
     def steps_device(k):       # k batches resident in HBM through the pipeline (public API: GeneratePipeline.generate_batches)
-        for i, tok in enumerate(pipe.generate_batches(dev_batches[:k], MAX_LEN)):
+        for i, tok in enumerate(pipe.generate_batches(dev_batches[:k], MAX_LEN, outs=outs_dev[:k])):
             gathered[i] = gather_tokens(tok, world)
 
     def steps_e2e(k):          # k batches from pinned HOST memory, token ids back to pinned host memory
@@ -383,31 +398,36 @@ def main():
             if world > 1:
                 gather_tokens(tok.cuda(non_blocking=True), world)
 
+    # one sampler per job (rank 0's GPU), not per rank: eight nvidia-smi pollers next to eight ranks perturb the launch path.  It is
+    # started before the warm-up (nvidia-smi's own start-up takes driver locks for several hundred ms, which used to land inside the
+    # timed region and cost up to 20 % of it) and keeps polling until after the end-to-end region; the reported samples are those
+    # taken between the two marks around the device-timed region.
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         step_device(i)
     if pipe is not None:
         pipe.warm_up(img_dev, MAX_LEN)
         for _ in range(args.warmup):
             steps_device(n_fly)
-    # one sampler per job (rank 0's GPU), not per rank: eight nvidia-smi pollers next to eight ranks perturb the launch path
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     serial = None
     if pipe is None:
         l0 = eng.kernel_launches()
         ms = timed(step_device, args.steps)
+        clocks.mark_end()
         launches = eng.kernel_launches() - l0
     else:
         l0 = pipe.kernel_launches()
         ms = timed(steps_device, args.steps, whole=True)
+        clocks.mark_end()
         launches = pipe.kernel_launches() - l0
         if not strong:
             ms_1 = timed(step_device, min(args.steps, 6))
             serial = {"value": world * B * min(args.steps, 6) / (ms_1 / 1e3), "unit": UNIT, "ms_per_step": ms_1 / min(args.steps, 6),
                       "note": "the same batches, one model.generate call at a time (6 decode branches per batch): what a caller of the "
                               "reference's own loop (test.py:27-40) gets without the pipeline"}
-    clk = clocks.stop()
     done_eq = sum(len(job_plan(args.total, B, r, world)) for r in range(world)) * B if strong else world * B * args.steps
     value = done_eq / (ms / 1e3)
 
@@ -444,6 +464,7 @@ def main():
             ms_e = timed(steps_e2e, args.steps, whole=True)
         e2e = {"value": done_eq / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(img_host.numel() * 4 * world), "d2h_bytes_per_step": int(out_host.numel() * 8 * world)}
+    clk = clocks.stop()
     if pipe is not None:
         pipe.close()
 

@@ -62,6 +62,11 @@ TX_DEVINL void store_split4(bf16* hi, bf16* lo, const float* r) {
     st4(lo, make_float4(l[0], l[1], l[2], l[3]));
 }
 
+TX_DEVINL uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
 // chunks an image of `npix` pixels is split into: depends on the image alone (batch-composition independent)
 TX_DEVINL int image_chunks(int npix, int nchunk) { return max(1, min(nchunk, (npix + 63) / 64)); }
 
@@ -254,6 +259,84 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a, const int*
     }
 }
 
+// bf16 tier (split-bf16 output, one raw input, optional split-bf16 residual): eight channels per thread, so that every access
+// of the bf16 planes is 16 bytes per lane (the four-channel kernel above reads / writes them 8 bytes at a time: the residual-pair
+// variant ran at 62-80 % of the bytes-per-second of the two-raw-inputs variant on the same byte count).  Two rows in flight per
+// thread, the residual kept packed until it is used.  Same arithmetic per element as gn_apply_kernel.
+template <bool RES>
+__global__ void __launch_bounds__(256, 3) gn_apply8_kernel(GnApplyArgs a, const int* __restrict__ img_off, int nchunk) {
+    const int C = a.C, C8 = C / 8, cpg = C / 32;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int p0 = img_off[b] >> (2 * a.level), p1 = img_off[b + 1] >> (2 * a.level);
+    const int used = image_chunks(p1 - p0, nchunk);
+    if (chunk >= used) return;
+    const int per = (p1 - p0 + used - 1) / used;
+    const int lo = p0 + chunk * per, hi = min(p1, lo + per);
+    const int rpp = 256 / C8;                                   // C8 <= 128
+    const int c8 = threadIdx.x % C8, rl = threadIdx.x / C8;
+    const int c = c8 * 8;
+    float mean[8], sc[8], be[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gi = (c + i) / cpg;
+        mean[i] = a.stats[((size_t)b * 32 + gi) * 2];
+        sc[i] = a.stats[((size_t)b * 32 + gi) * 2 + 1] * a.gamma[c + i];
+        be[i] = a.beta[c + i];
+    }
+    const bf16* res_hi = reinterpret_cast<const bf16*>(a.res_hi);
+    const bf16* res_lo = reinterpret_cast<const bf16*>(a.res_lo);
+    bf16* out_hi = reinterpret_cast<bf16*>(a.out_hi);
+    bf16* out_lo = reinterpret_cast<bf16*>(a.out_lo);
+    const bool relu = a.relu;
+    auto one = [&](const float4 va, const float4 vb, const uint4 rh, const uint4 rl2, size_t o) {
+        const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = (v[i] - mean[i]) * sc[i] + be[i];
+        if (RES) {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&rh);
+            const __nv_bfloat162* ll = reinterpret_cast<const __nv_bfloat162*>(&rl2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fh = __bfloat1622float2(hh[i]), fl = __bfloat1622float2(ll[i]);
+                r[2 * i] += fh.x + fl.x; r[2 * i + 1] += fh.y + fl.y;
+            }
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
+        }
+        float h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h[i] = __bfloat162float(__float2bfloat16_rn(r[i])); l[i] = r[i] - h[i]; }
+        uint4 ph, pl;
+        ph.x = pack2(h[0], h[1]); ph.y = pack2(h[2], h[3]); ph.z = pack2(h[4], h[5]); ph.w = pack2(h[6], h[7]);
+        pl.x = pack2(l[0], l[1]); pl.y = pack2(l[2], l[3]); pl.z = pack2(l[4], l[5]); pl.w = pack2(l[6], l[7]);
+        *reinterpret_cast<uint4*>(out_hi + o) = ph;
+        *reinterpret_cast<uint4*>(out_lo + o) = pl;
+    };
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    int p = lo + rl;
+    for (; p + rpp < hi; p += 2 * rpp) {                      // two rows in flight
+        const size_t o0 = (size_t)p * C + c, o1 = (size_t)(p + rpp) * C + c;
+        const float4 a0 = ld4(a.raw + o0), b0 = ld4(a.raw + o0 + 4), a1 = ld4(a.raw + o1), b1 = ld4(a.raw + o1 + 4);
+        uint4 h0 = z, l0 = z, h1 = z, l1 = z;
+        if (RES) {
+            h0 = *reinterpret_cast<const uint4*>(res_hi + o0); l0 = *reinterpret_cast<const uint4*>(res_lo + o0);
+            h1 = *reinterpret_cast<const uint4*>(res_hi + o1); l1 = *reinterpret_cast<const uint4*>(res_lo + o1);
+        }
+        one(a0, b0, h0, l0, o0);
+        one(a1, b1, h1, l1, o1);
+    }
+    for (; p < hi; p += rpp) {
+        const size_t o0 = (size_t)p * C + c;
+        const float4 a0 = ld4(a.raw + o0), b0 = ld4(a.raw + o0 + 4);
+        uint4 h0 = z, l0 = z;
+        if (RES) { h0 = *reinterpret_cast<const uint4*>(res_hi + o0); l0 = *reinterpret_cast<const uint4*>(res_lo + o0); }
+        one(a0, b0, h0, l0, o0);
+    }
+}
+
 // ------------------------------------------------------------------ stem: GN + ReLU + maxpool 3x3 s2
 // model/resnet.py:69-79: SAME pad (0,1) filled with -inf => out-of-range taps are skipped.
 __global__ void __launch_bounds__(256) gn_apply_maxpool_kernel(const float* __restrict__ raw1, const float* __restrict__ stats,
@@ -415,7 +498,11 @@ cudaError_t launch_gn_finalize_blocks(const float* part, int C, int level, const
 cudaError_t launch_gn_apply(const GnApplyArgs& a, const int* img_off, int nimg, int nchunk, cudaStream_t st) {
     if (a.C % 4 != 0 || a.C / 4 > 256) return cudaErrorInvalidValue;
     dim3 grid(nchunk, nimg);
-    gn_apply_kernel<<<grid, 256, 0, st>>>(a, img_off, nchunk);
+    // split-bf16 output, one raw input (the bf16 tier's backbone away from the down-sampling blocks): eight channels per thread
+    if (a.out_hi && !a.out && !a.res && !a.raw2 && a.C % 64 == 0 && a.C / 8 <= 128) {
+        if (a.res_hi) gn_apply8_kernel<true><<<grid, 256, 0, st>>>(a, img_off, nchunk);
+        else gn_apply8_kernel<false><<<grid, 256, 0, st>>>(a, img_off, nchunk);
+    } else gn_apply_kernel<<<grid, 256, 0, st>>>(a, img_off, nchunk);
     return cudaGetLastError();
 }
 
