@@ -48,6 +48,8 @@ CASES = [
     (49664, 1536, 256, EPI_STORE, torch.bfloat16, False),   # encoder-sized
     (49152, 256, 1024, EPI_STORE, torch.float32, True),     # patch projection
     (20000, 2048, 256, EPI_GEGLU, torch.bfloat16, True),
+    (40000, 512, 512, EPI_GLU_RES, torch.float32, True),      # encoder-sized with a residual: persistent kernel, residual fetched a chunk ahead
+    (39990, 256, 1024, EPI_BIAS_RES, torch.float32, True),    # ... with an M tail
 ]
 
 

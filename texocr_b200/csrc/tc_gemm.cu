@@ -173,7 +173,27 @@ TX_DEVINL void stage_copy_gn(uint8_t* stg, uint8_t* gptr, size_t grow_bytes, int
     }
 }
 
-template <int BN, int EPI, typename TC, int EW>
+// the two halves of stage_copy<RB, false>: global -> registers (issued early, the latency overlaps other work), registers -> staging
+template <int RB>
+TX_DEVINL void stage_fetch(const uint8_t* gptr, size_t grow_bytes, int lane, int rows_ok, int bytes_ok, uint4* rq) {
+    constexpr int CPR = RB / 16, RPI = 32 / CPR;
+    const int rr = lane / CPR, ch = lane % CPR;
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) {
+        const int row = it * RPI + rr;
+        rq[it] = make_uint4(0, 0, 0, 0);
+        if (row < rows_ok && ch * 16 < bytes_ok) rq[it] = __ldcg(reinterpret_cast<const uint4*>(gptr + (size_t)row * grow_bytes + ch * 16));
+    }
+}
+template <int RB>
+TX_DEVINL void stage_put(uint8_t* stg, int lane, const uint4* rq) {
+    constexpr int CPR = RB / 16, RPI = 32 / CPR;
+    const int rr = lane / CPR, ch = lane % CPR;
+#pragma unroll
+    for (int it = 0; it < CPR; ++it) *reinterpret_cast<uint4*>(stg + (it * RPI + rr) * STG_STRIDE + ch * 16) = rq[it];
+}
+
+template <int BN, int EPI, typename TC, int EW, bool AHEAD = false>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
                              uint8_t* smem_idle, uint32_t parity = 0, unsigned long long dbg_t0 = 0ull) {
     constexpr int CW = (EW == 2 && BN == 32) ? 16 : 32;         // columns per tcgen05.ld chunk
@@ -212,6 +232,19 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
         if (p.bias && n0 + cfirst + i < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + cfirst + i));
         bpre[i] = b.x; bpre[i + 1] = b.y; bpre[i + 2] = b.z; bpre[i + 3] = b.w;
     }
+    // Wide tiles with a residual: the residual tile of a chunk is fetched (coalesced, into registers) one chunk ahead -- the first one
+    // before the accumulator wait, the next one before the current chunk's math and stores -- so that its L2 / HBM round trip is
+    // never exposed (ncu: the 128 x 128 GLU + residual epilogue of the ViT blocks took 9.6 us per tile against 0.5 us of MMAs)
+    constexpr bool RES_AHEAD = AHEAD && !PRE_RES && (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES);      // persistent kernel (register budget of one CTA per SM)
+    uint4 rq[RES_AHEAD ? NOUT * 4 / 16 : 1];
+    auto res_fetch = [&](int c0) {
+        const int n = n0 + c0;
+        if (rows_ok <= 0 || n >= p.N) return;
+        const int nv = min(CW, p.N - n);
+        stage_fetch<NOUT * 4>(reinterpret_cast<const uint8_t*>(p.res + (size_t)mrow0 * p.ldres + (PAIRS ? (n >> 1) : n)), (size_t)p.ldres * 4, lane,
+                              rows_ok, (PAIRS ? (nv >> 1) : nv) * 4, rq);
+    };
+    if (RES_AHEAD) res_fetch(cfirst);
     mbar_wait(tmem_full, parity);
     if (p.late_trigger == 2) pdl_launch_dependents();           // one-tile kernel: what is left of this CTA is about as long as the dependent's launch + prologue
     if (dbg_t0) atomicAdd(p.dbg + 6, gtime_ns() - dbg_t0);      // debug: epilogue warp entry -> accumulator complete
@@ -257,9 +290,10 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
             for (int i = 0; i < NOUT; ++i)
                 o[i] = (EPI == EPI_BIAS_RES) ? v[i] + rpre[PRE_RES ? i : 0] : v[2 * i] * sigmoid_fast(v[2 * i + 1]) + rpre[PRE_RES ? i : 0];
         } else if (EPI == EPI_BIAS_RES || EPI == EPI_GLU_RES) {
-            // residual tile -> staging (coalesced), then every thread picks up its own row
-            stage_copy<NOUT * 4, false>(stg, reinterpret_cast<uint8_t*>(const_cast<float*>(p.res) + (size_t)mrow0 * p.ldres + ncol),
-                                        (size_t)p.ldres * 4, lane, rows_ok, nvalid_out * 4);
+            // residual tile (fetched a chunk ahead, or now) -> staging, then every thread picks up its own row
+            if (RES_AHEAD) stage_put<NOUT * 4>(stg, lane, rq);
+            else stage_copy<NOUT * 4, false>(stg, reinterpret_cast<uint8_t*>(const_cast<float*>(p.res) + (size_t)mrow0 * p.ldres + ncol),
+                                             (size_t)p.ldres * 4, lane, rows_ok, nvalid_out * 4);
             __syncwarp();
             float r[NOUT];
 #pragma unroll
@@ -268,6 +302,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
                 r[i] = t.x; r[i + 1] = t.y; r[i + 2] = t.z; r[i + 3] = t.w;
             }
             __syncwarp();
+            if (RES_AHEAD && c0 + EW * CW < BN) res_fetch(c0 + EW * CW);
 #pragma unroll
             for (int i = 0; i < NOUT; ++i)
                 o[i] = (EPI == EPI_BIAS_RES) ? v[i] + r[i] : v[2 * i] * sigmoid_fast(v[2 * i + 1]) + r[i];
@@ -559,7 +594,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            epilogue_tile<BN, EPI, TC, EW>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
+            epilogue_tile<BN, EPI, TC, EW, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);              // all of this warp's tcgen05.ld of the buffer have completed
@@ -775,8 +810,9 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     const bool split = g.A2 != nullptr;
     if (split) bn = g.N <= 64 ? 64 : 128;
     // 128 x 256 tiles (one MMA reads A once for 256 columns: the shared-memory operand reads of a 128 x 128 x 16 MMA take as long as
-    // the MMA itself) for the wide, deep convolutions; short-K ones are bound by the epilogue, which has four warps here
-    if (split && g_tc_bn256 && g.epi == EPI_STORE && g.dt_c == DT_F32 && !g.bias && g.N % 256 == 0 && g.K >= 256 && mt * (g.N / 256) >= 148 && g_tc_persistent) bn = 256;
+    // the MMA itself) for the wide, deep convolutions; K <= 256 ones are bound by the epilogue, which has four warps here
+    // (ncu: 9.4 us per 128 x 256 tile at K = 256 against 3.2 us of MMAs)
+    if (split && g_tc_bn256 && g.epi == EPI_STORE && g.dt_c == DT_F32 && !g.bias && g.N % 256 == 0 && g.K >= 512 && mt * (g.N / 256) >= 148 && g_tc_persistent) bn = 256;
     if (g.a_block_k) {
         if (split || g.im2col.ksz > 0 || g.N % 64 != 0) return cudaErrorInvalidValue;
         bn = 64;
