@@ -368,28 +368,34 @@ def test_wrapper_image_to_latex_end_to_end(tmp_path, sd, golden):
 
 
 def test_tma_im2col_convolutions_bit_identical_to_explicit_im2col(m16):
-    """bf16 tier, same-size batches: the 3x3 / strided backbone convolutions run as implicit GEMMs whose A tiles come from
-    TMA im2col loads (stride-1 SAME, stride-2 TF-SAME (0,1) padding, 1x1 stride-2 subsampling, M tails).  Same operand
-    values in the same k order as the explicit im2col buffer -> identical bits; a ragged batch (explicit path) containing
-    the same images gives the same rows."""
+    """bf16 tier: the 3x3 / strided backbone convolutions run as implicit GEMMs -- same-size batches fetch their A tiles with TMA
+    im2col loads, ragged batches gather them with cp.async in the GEMM's producer warps (stride-1 SAME, stride-2 TF-SAME (0,1)
+    padding, 1x1 stride-2 subsampling, M tails).  Same operand values in the same k order as the explicit im2col buffer -> identical
+    bits from all three; a ragged batch containing the same images gives the same rows."""
     eng = m16.engine()
     try:
-        for (B, H, W) in ((2, 64, 384), (3, 48, 208), (1, 160, 1008), (5, 16, 16)):
+        for (B, H, W) in ((2, 64, 384), (3, 48, 208), (1, 160, 1008), (5, 16, 16), (40, 64, 384)):
             img = synth.synth_images(B, H, W, seed=5 + B).cuda()
             outs = []
-            for flag in (0, 1):
-                eng.set_option("im2col_tma", flag)
+            for tma, gather in ((0, 0), (0, 1), (1, 1)):
+                eng.set_option("im2col_tma", tma)
+                eng.set_option("conv_gather", gather)
                 outs.append(m16.encoder(img))
-            assert torch.isfinite(outs[1]).all() and torch.equal(outs[0], outs[1]), (B, H, W)
+            assert torch.isfinite(outs[1]).all(), (B, H, W)
+            assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (B, H, W)
         eng.set_option("im2col_tma", 1)
         a = synth.synth_images(2, 64, 384, seed=3).cuda()
         b = synth.synth_images(1, 32, 128, seed=4).cuda()
-        uni = m16.encoder(a)                                              # implicit path
-        rag = eng.encode_packed([a[0], b[0], a[1]])                       # ragged -> explicit path
+        c = synth.synth_images(1, 160, 1008, seed=6).cuda()
+        uni = m16.encoder(a)                                              # TMA im2col path
         n = uni.shape[1]
-        assert torch.equal(rag[0][:n], uni[0]) and torch.equal(rag[0][-n:], uni[1])
+        for gather in (0, 1):                                             # ragged -> explicit im2col buffer / gathered A tiles
+            eng.set_option("conv_gather", gather)
+            rag = eng.encode_packed([a[0], b[0], c[0], a[1]])
+            assert torch.equal(rag[0][:n], uni[0]) and torch.equal(rag[0][-n:], uni[1]), gather
     finally:
         eng.set_option("im2col_tma", 1)
+        eng.set_option("conv_gather", 1)
 
 
 def test_groupnorm_partials_from_gemm_epilogue_bit_identical_to_block_kernel(m16):

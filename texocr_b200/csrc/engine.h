@@ -114,6 +114,7 @@ struct texocr_handle {
     bool use_tcgen05 = true;
     int gn_fused = 1;             // bf16 tier: GroupNorm partial sums in the epilogue of the producing convolution GEMM (same-size batches whose
                                   // images have a multiple of 32 pixel rows at every level); 0 = always the stand-alone block kernel
+    bool use_conv_gather = true;  // bf16 tier, ragged batches: 3x3 / strided convolutions as implicit GEMMs with cp.async-gathered A tiles
     bool use_im2col_tma = true;   // bf16 tier, same-size batches: 3x3 / strided convolutions as implicit GEMMs (TMA im2col loads)
     // bf16 tier generate loop: cross-attention streams the [S,256] encoder memory once for all heads instead of per-head K/V
     // (K / V projections folded into the query / output projections).  0 = projected K/V cache.

@@ -185,8 +185,10 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
         const int pad_lo = (cw.k == 3 && cw.stride == 1) ? 1 : 0;
         // same-size batch: the GEMM fetches its A tiles straight from the NHWC activation with TMA im2col loads
         const bool implicit = h->use_im2col_tma && g.uni_h > 0 && cw.cin % 64 == 0 && !(cw.k == 1 && cw.stride == 1);
-        if (!(cw.k == 1 && cw.stride == 1) && !implicit) {
-            ConvGather cg{g.d_img_off, g.d_img_hw, B, lin, lout, cw.k, cw.stride, pad_lo, cw.cin};
+        // ragged batch: the GEMM's producer warps gather the A tiles from the NHWC activation (tc_conv_gather_kernel)
+        const bool gather = !implicit && h->use_conv_gather && cw.cin % 64 == 0 && !(cw.k == 1 && cw.stride == 1);
+        ConvGather cg{g.d_img_off, g.d_img_hw, B, lin, lout, cw.k, cw.stride, pad_lo, cw.cin};
+        if (!(cw.k == 1 && cw.stride == 1) && !implicit && !gather) {
             Pair c = pair_of(h->col, (size_t)M * K);
             LAUNCH(KC_GN_APPLY, 1, (double)M * K * 8, 0.0, launch_im2col_split(in.hi, in.lo, c.hi, c.lo, cg, M, st));
             a_hi = c.hi; a_lo = c.lo;
@@ -197,6 +199,7 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
             ga.lda = cw.cin;
             ga.im2col = {cw.k, cw.stride, pad_lo, cw.cin, g.uni_w >> lin, g.uni_h >> lin, B, g.uni_w >> lout, g.uni_h >> lout};
         }
+        if (gather) { ga.lda = cw.cin; ga.gather = &cg; }
         const bool fused = fused_ok(lout);
         if (fused) { ga.gn_part = h->gn_part.as<float>(); ga.gn_rpi = (g.uni_h >> lout) * (g.uni_w >> lout); }
         if (!tc_gemm_supported(ga)) return fail(h, TEXOCR_ERR_ARG, "backbone conv %s not supported by the tcgen05 GEMM", cw.name.c_str());

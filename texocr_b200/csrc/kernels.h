@@ -58,6 +58,9 @@ struct GemmArgs {
     // activation, K = ksz*ksz*C, k order (ky, kx, c)): the A tiles are fetched with TMA im2col loads, no im2col buffer.
     // pad_lo = padding before (TF-SAME, utils.py:93-123); M = N * Ho * Wo output pixels.  ksz == 0: plain GEMM.
     struct Im2col { int ksz, stride, pad_lo, C, W, H, N, Wo, Ho; } im2col;
+    // tcgen05 path, bf16x3, ragged batch: implicit GEMM of the convolution `gather` describes over the split-bf16 NHWC activation
+    // (A, A2) = (hi, lo) -- the A tiles are gathered row by row with cp.async (tc_conv_gather_kernel), no im2col buffer.  null = off
+    const ConvGather* gather;
     // tcgen05 path, block-diagonal GEMM: output columns [64j, 64j+64) contract A[:, j*a_block_k .. j*a_block_k + K) with W rows
     // [64j, 64j+64) (W is [N, K]); A has N/64 * a_block_k columns.  0 = ordinary GEMM.  (per-head value projection of the absorbed
     // attention: C_h [256] -> 64 values with Wv_h)

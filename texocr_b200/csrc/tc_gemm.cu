@@ -46,6 +46,8 @@ struct TcParams {
     // GroupNorm partial sums of the fp32 output (EPI_STORE, M rows = same-size images of gn_rpi rows each, gn_rpi % 32 == 0):
     // gn_part[(row >> 5) + image][32][2], see gn_block.cuh.  null = off
     float* gn_part; int gn_cpg, gn_rpi;
+    // ragged implicit-GEMM convolution (tc_conv_gather_kernel): the split-bf16 NHWC activation and the batch geometry
+    const bf16* g_hi; const bf16* g_lo; const int* g_img_off; const int* g_img_hw; int g_nimg, g_lin, g_lout, g_pad;
 };
 TX_DEVINL unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -608,6 +610,174 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ ragged implicit-GEMM convolution
+// Batches of different-size images cannot use the TMA im2col loads (one regular [N][H][W][C] box per tensor map).  Same persistent
+// kernel, bf16x3 operands, fp32 store epilogue -- but the A tiles are gathered by four producer warps, thread = output pixel of
+// the tile: the pixel's image is located once per tile (binary search over the offset table), then every k-block (filter tap,
+// 64-channel chunk) is one 128-byte row per operand half, copied with eight 16-byte cp.async (zero-fill for taps outside the
+// image: TF-SAME padding) straight into the 128-byte-swizzled layout the MMA descriptors expect.  A stage is published
+// STAGES - 2 k-blocks late (cp.async.wait_group -> fence.proxy.async -> mbarrier arrive): the copies of the following k-blocks are
+// in flight while it lands, and one stage of slack stays between the MMA issuer and the producers.  W tiles still come by TMA.  Replaces the explicit im2col buffer (72 bytes of traffic per input element of a
+// 3x3 convolution) for ragged batches.
+template <int BN> struct SmemG {
+    static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+    static constexpr int STAGE = 2 * (A_BYTES + W_BYTES);
+    static constexpr int STG = 4 * STG_WARP;
+    static constexpr int STAGES = (225 * 1024 - STG) / STAGE > 6 ? 6 : (225 * 1024 - STG) / STAGE;
+    static constexpr int BARS = 256;
+    static constexpr int TOTAL = STAGES * STAGE + STG + 1024 + BARS;
+};
+
+TX_DEVINL void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1)
+tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
+    using S = SmemG<BN>;
+    constexpr int NST = S::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stg = smem + NST * S::STAGE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stg + S::STG);
+    uint64_t* empty = full + NST;
+    uint64_t* tmem_full = empty + NST;             // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.K / BK;
+    const int n_tiles = (p.N + BN - 1) / BN, m_tiles = (p.M + BM - 1) / BM;
+    const int tiles = n_tiles * m_tiles;
+
+    pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1 + 128); mbar_init(&empty[s], 1); }      // W producer + 128 gather threads
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % NST, ph = (it / NST) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * S::STAGE;
+                    mbar_expect_tx(&full[s], 2 * S::W_BYTES);
+                    tma_load_2d(&tmW, &full[s], st + 2 * S::A_BYTES, kb * BK, n0);
+                    tma_load_2d(&tmW2, &full[s], st + 2 * S::A_BYTES + S::W_BYTES, kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int it = 0, i = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % NST, ph = (it / NST) & 1;
+                    mbar_wait(&full[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * S::STAGE);
+                    const uint32_t w_hi = a_hi + 2 * S::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t koff = k * UMMA_K * 2;
+                        umma_bf16(acc, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + koff), idesc, (kb | k) != 0);
+                        umma_bf16(acc, make_smem_desc(a_hi + koff), make_smem_desc(w_hi + S::W_BYTES + koff), idesc, 1);
+                        umma_bf16(acc, make_smem_desc(a_hi + S::A_BYTES + koff), make_smem_desc(w_hi + koff), idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else if (warp < 6) {
+        int i = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
+            const int buf = i & 1;
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+            epilogue_tile<BN, EPI_STORE, float, 1, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    } else {
+        // ---- gather producers: thread r owns row r of every A tile
+        const int r = (int)threadIdx.x - 192;
+        const uint32_t row_off = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
+        const int cin = p.cv_cpk * BK, ksz = p.cv_ksz, stride = p.cv_stride;
+        // k-blocks between issue and publication.  NST - 1 would keep every stage in flight but couples the MMA of k-block j to the
+        // release of k-block j - 1 (measured: 6.5 ms of convolutions per config-2 batch against 5.7 ms with one stage of slack)
+        constexpr int LAG = NST > 2 ? NST - 2 : 1;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m = (tile / n_tiles) * BM + r;
+            int oy = 0, ox = 0, hin = 0, win = 0;
+            size_t base = 0;
+            const bool row_ok = m < p.M;
+            if (row_ok) {
+                const int b = find_image(p.g_img_off, p.g_nimg, p.g_lout, m);
+                const int H = p.g_img_hw[2 * b], W = p.g_img_hw[2 * b + 1];
+                const int wo = W >> p.g_lout;
+                hin = H >> p.g_lin; win = W >> p.g_lin;
+                const int local = m - (p.g_img_off[b] >> (2 * p.g_lout));
+                oy = local / wo; ox = local - oy * wo;
+                base = (size_t)(p.g_img_off[b] >> (2 * p.g_lin)) * cin;
+            }
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % NST, ph = (it / NST) & 1;
+                const int tap = kb / p.cv_cpk, cc = (kb - tap * p.cv_cpk) * BK;
+                const int ky = tap / ksz, kx = tap - ky * ksz;
+                const int iy = oy * stride + ky - p.g_pad, ix = ox * stride + kx - p.g_pad;
+                const bool ok = row_ok && iy >= 0 && iy < hin && ix >= 0 && ix < win;
+                const size_t src = ok ? base + ((size_t)iy * win + ix) * cin + cc : 0;
+                const uint32_t nbytes = ok ? 16u : 0u;
+                mbar_wait(&empty[s], ph ^ 1);
+                const uint32_t d_hi = smem_u32(smem + s * S::STAGE) + row_off, d_lo = d_hi + S::A_BYTES;
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) {
+                    cp_async16(d_hi + ((j ^ sw) << 4), p.g_hi + src + j * 8, nbytes);
+                    cp_async16(d_lo + ((j ^ sw) << 4), p.g_lo + src + j * 8, nbytes);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (it >= LAG) {       // publish k-block it - LAG: its copies have landed once at most LAG groups are pending
+                    asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&full[(it - LAG) % NST]);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // the last LAG k-blocks
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int j = it > LAG ? it - LAG : 0; j < it; ++j) mbar_arrive(&full[j % NST]);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -757,6 +927,25 @@ cudaError_t launch_persistent(const CUtensorMap& a, const CUtensorMap& w, const 
     return launch_persistent2<BN, EPI, TC, SPLIT, 1>(a, w, a2, w2, p, tiles, st);
 }
 
+template <int BN>
+cudaError_t launch_gather(const CUtensorMap& w, const CUtensorMap& w2, const TcParams& p, cudaStream_t st) {
+    using S = SmemG<BN>;
+    static bool attr_set = false;
+    static int sms = 0;
+    auto kern = tc_conv_gather_kernel<BN>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    const long tiles = (long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
+    const unsigned grid = (unsigned)std::min<long>(tiles, sms);
+    return launch_pdl(PDL_GEMM, kern, dim3(grid), dim3(320), (size_t)S::TOTAL, st, w, w2, p);
+}
+
 template <int BN, int EPI, typename TC, int SPLIT>
 cudaError_t launch_cfg(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& a2, const CUtensorMap& w2, const TcParams& p,
                        cudaStream_t st) {
@@ -790,6 +979,7 @@ cudaError_t launch_epi(const GemmArgs& g, const CUtensorMap& a, const CUtensorMa
 
 bool tc_gemm_supported(const GemmArgs& g) {
     if (g.dt_a != DT_BF16 || g.conv) return false;
+    if (g.gather) return g.A2 && g.W2 && g.gather->cin % BK == 0 && g.N % 8 == 0 && g.ldw % 8 == 0 && g.ldc % 4 == 0 && !((uintptr_t)g.A & 15) && !((uintptr_t)g.A2 & 15);
     if (g.K % BK != 0 || g.N % 8 != 0 || g.lda % 8 != 0 || g.ldw % 8 != 0) return false;
     if (g.im2col.ksz > 0 && (g.im2col.C % BK != 0 || g.im2col.ksz > 7)) return false;
     if (((uintptr_t)g.A | (uintptr_t)g.W) & 15) return false;
@@ -820,6 +1010,7 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (g.epi == EPI_ARGMAX) bn = 32;      // the partial layout is defined on 32-column tiles
     TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl_mid & 1) ? 2 : ((g_texocr_pdl >> 9) & 1), 0, 0, 0, 0, 0, 0};
     p.stages = 0; p.gn_part = nullptr; p.gn_cpg = 0; p.gn_rpi = 0;
+    p.g_hi = p.g_lo = nullptr; p.g_img_off = p.g_img_hw = nullptr; p.g_nimg = p.g_lin = p.g_lout = p.g_pad = 0;
     p.a_block_k = g.a_block_k; p.dbg = g.dbg;
     if (g.gn_part) {
         if (g.epi != EPI_STORE || g.dt_c != DT_F32 || g.bias || g.N % 32 != 0 || g.gn_rpi <= 0 || g.gn_rpi % 32 != 0 || g.M % g.gn_rpi != 0 ||
@@ -829,6 +1020,18 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     }
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
+    if (g.gather) {         // ragged implicit-GEMM convolution: A gathered by producer warps, W by TMA
+        const ConvGather& cg = *g.gather;
+        if (!split || g.epi != EPI_STORE || g.dt_c != DT_F32 || g.bias || cg.cin % BK != 0 || g.K != cg.ksz * cg.ksz * cg.cin)
+            return cudaErrorInvalidValue;
+        bn = g.N <= 64 ? 64 : 128;
+        p.cv_cpk = cg.cin / BK; p.cv_ksz = cg.ksz; p.cv_stride = cg.stride;
+        p.g_hi = (const bf16*)g.A; p.g_lo = (const bf16*)g.A2; p.g_img_off = cg.img_off; p.g_img_hw = cg.img_hw; p.g_nimg = cg.nimg;
+        p.g_lin = cg.lin; p.g_lout = cg.lout; p.g_pad = cg.pad;
+        if ((e = get_map(g.W, g.N, g.K, g.ldw, bn, &w)) != cudaSuccess) return e;
+        if ((e = get_map(g.W2, g.N, g.K, g.ldw, bn, &w2)) != cudaSuccess) return e;
+        return bn == 64 ? launch_gather<64>(w, w2, p, st) : launch_gather<128>(w, w2, p, st);
+    }
     const bool conv = g.im2col.ksz > 0;
     if (conv) {
         const GemmArgs::Im2col& c = g.im2col;
