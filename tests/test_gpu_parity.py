@@ -423,9 +423,18 @@ def test_groupnorm_partials_from_gemm_epilogue_bit_identical_to_block_kernel(m16
         a = synth.synth_images(2, 64, 384, seed=3).cuda()
         b = synth.synth_images(1, 48, 208, seed=4).cuda()
         uni = m16.encoder(a)                                              # fused partials
-        rag = eng.encode_packed([a[0], b[0], a[1]])                       # ragged -> block kernel
+        rag = eng.encode_packed([a[0], b[0], a[1]])                       # ragged, 48x208 has no multiple of 32 rows -> block kernel
         n = uni.shape[1]
         assert torch.equal(rag[0][:n], uni[0]) and torch.equal(rag[0][-n:], uni[1])
+        # ragged batch whose images all have a multiple of 32 rows at every level: partials from the epilogue, image looked up per row block
+        c = synth.synth_images(1, 64, 128, seed=8).cuda()
+        d = synth.synth_images(1, 32, 256, seed=9).cuda()
+        rag2 = eng.encode_packed([c[0], a[0], d[0], a[1]])
+        nc, nd = m16.encoder(c).shape[1], m16.encoder(d).shape[1]
+        assert torch.equal(rag2[0][:nc], m16.encoder(c)[0]) and torch.equal(rag2[0][nc:nc + n], uni[0])
+        assert torch.equal(rag2[0][nc + n:nc + n + nd], m16.encoder(d)[0]) and torch.equal(rag2[0][-n:], uni[1])
+        eng.set_option("gn_fused", 0)
+        assert torch.equal(eng.encode_packed([c[0], a[0], d[0], a[1]])[0], rag2[0])
     finally:
         eng.set_option("gn_fused", 1)
         eng.set_option("gemm_epi_warps", 8)

@@ -18,6 +18,8 @@ int plan_geometry(texocr_handle* h, const int32_t* hw, int B, EncGeom& g, cudaSt
         const long next = (long)g.img_off[b] + (long)H * W;
         if (next > 0x7fffffffL / 64) return fail(h, TEXOCR_ERR_ARG, "batch too large: more than 2^31 stem activations");
         g.img_off[b + 1] = (int)next;
+        for (int l = 0; l <= 4; ++l)
+            if ((((long)(H >> l) * (W >> l)) & 31) != 0) g.rows32[l] = false;
         const int n = (H / 16) * (W / 16) + 1;
         g.tok_off[b + 1] = g.tok_off[b] + n;
         g.max_tok = std::max(g.max_tok, n);
@@ -175,9 +177,9 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
     const int depths[3] = {2, 4, 6};
     // conv: split GEMM, through im2col unless 1x1/s1
     // GroupNorm statistics of a convolution's fp32 output: block partial sums (gn_block.cuh) left by the GEMM epilogue when
-    // every image has the same size and a multiple of 32 pixel rows at the output level, by the stand-alone kernel otherwise
+    // every image of the batch has a multiple of 32 pixel rows at the output level, by the stand-alone kernel otherwise
     // (identical bits either way), then one small kernel that adds an image's blocks in order.
-    auto fused_ok = [&](int level) { return h->gn_fused && g.uni_h > 0 && (((long)(g.uni_h >> level) * (g.uni_w >> level)) % 32) == 0; };
+    auto fused_ok = [&](int level) { return h->gn_fused && g.rows32[level]; };
     auto conv = [&](const ConvW& cw, Pair in, int lin, int lout, float* out, float* stt) -> int {
         const long M = g.P[lout];
         const int K = cw.k * cw.k * cw.cin;
@@ -201,7 +203,11 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
         }
         if (gather) { ga.lda = cw.cin; ga.gather = &cg; }
         const bool fused = fused_ok(lout);
-        if (fused) { ga.gn_part = h->gn_part.as<float>(); ga.gn_rpi = (g.uni_h >> lout) * (g.uni_w >> lout); }
+        if (fused) {
+            ga.gn_part = h->gn_part.as<float>();
+            if (g.uni_h > 0) ga.gn_rpi = (g.uni_h >> lout) * (g.uni_w >> lout);
+            else { ga.gn_rpi = 0; ga.gn_img_off = g.d_img_off; ga.gn_nimg = B; ga.gn_level = lout; }
+        }
         if (!tc_gemm_supported(ga)) return fail(h, TEXOCR_ERR_ARG, "backbone conv %s not supported by the tcgen05 GEMM", cw.name.c_str());
         LAUNCH(KC_CONV, 1, gemm_bytes(ga, 4), gemm_flops(ga), launch_gemm_tc(ga, st));
         if (!fused)

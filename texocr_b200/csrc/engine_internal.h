@@ -77,6 +77,7 @@ struct EncGeom {
     long P[5] = {0, 0, 0, 0, 0};
     int ntok = 0, max_tok = 0;
     int uni_h = 0, uni_w = 0;          // > 0: every image has this size (enables the TMA im2col convolutions)
+    bool rows32[5] = {true, true, true, true, true};      // level L: every image has a multiple of 32 pixel rows (GroupNorm partials in the GEMM epilogue)
     const int* d_img_off = nullptr; const int* d_img_hw = nullptr; const int* d_tok_off = nullptr;
 };
 int plan_geometry(texocr_handle* h, const int32_t* hw, int B, EncGeom& g, cudaStream_t st);

@@ -67,8 +67,9 @@ struct GemmArgs {
     int a_block_k;
     // tcgen05 path, EPI_STORE / fp32 output of a convolution over same-size images of gn_rpi pixel rows each (gn_rpi % 32 == 0):
     // the epilogue also leaves the GroupNorm(32) partial sums of every 32-row block, gn_part[(row >> 5) + image][32][2]
-    // (gn_block.cuh; summed per image by launch_gn_finalize_blocks).  null = off
-    float* gn_part; int gn_rpi;
+    // (gn_block.cuh; summed per image by launch_gn_finalize_blocks).  null = off.  gn_rpi == 0: images of different sizes, every one a
+    // multiple of 32 rows at this level (gn_img_off / gn_nimg / gn_level: the offset table the image of a row block is looked up in)
+    float* gn_part; int gn_rpi; const int* gn_img_off; int gn_nimg, gn_level;
     // debug (engine option attn_trace): per-CTA residency sums of the launch: [0] ns waiting for the predecessor grid,
     // [1] ns from there to CTA exit, [2] CTAs.  null = off
     unsigned long long* dbg;

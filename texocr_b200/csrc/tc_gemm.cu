@@ -46,6 +46,7 @@ struct TcParams {
     // GroupNorm partial sums of the fp32 output (EPI_STORE, M rows = same-size images of gn_rpi rows each, gn_rpi % 32 == 0):
     // gn_part[(row >> 5) + image][32][2], see gn_block.cuh.  null = off
     float* gn_part; int gn_cpg, gn_rpi;
+    const int* gn_img_off; int gn_nimg, gn_level;      // gn_rpi == 0: images of different sizes, each a multiple of 32 rows at this level
     // ragged implicit-GEMM convolution (tc_conv_gather_kernel): the split-bf16 NHWC activation and the batch geometry
     const bf16* g_hi; const bf16* g_lo; const int* g_img_off; const int* g_img_hw; int g_nimg, g_lin, g_lout, g_pad;
 };
@@ -247,6 +248,13 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
                               rows_ok, (PAIRS ? (nv >> 1) : nv) * 4, rq);
     };
     if (RES_AHEAD) res_fetch(cfirst);
+    // GroupNorm partials: the slot of this warp's row block (image index by division, or by a search of the offset table for ragged
+    // batches), looked up while the MMAs are still running
+    int gn_slot = 0;
+    if constexpr (EPI == EPI_STORE && std::is_same<TC, float>::value && CW == 32) {
+        if (p.gn_part && rows_ok > 0)
+            gn_slot = (mrow0 >> 5) + (p.gn_rpi > 0 ? mrow0 / p.gn_rpi : find_image(p.gn_img_off, p.gn_nimg, p.gn_level, mrow0));
+    }
     mbar_wait(tmem_full, parity);
     if (p.late_trigger == 2) pdl_launch_dependents();           // one-tile kernel: what is left of this CTA is about as long as the dependent's launch + prologue
     if (dbg_t0) atomicAdd(p.dbg + 6, gtime_ns() - dbg_t0);      // debug: epilogue warp entry -> accumulator complete
@@ -327,8 +335,7 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
             if (p.gn_part && nvalid == 32) {                    // convolution output: GroupNorm partial sums of the tile on its way out
                 float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
                 stage_copy_gn(stg, gdst, (size_t)p.ldc * 4, lane, rows_ok, gs, gq);
-                const int slot = (mrow0 >> 5) + mrow0 / p.gn_rpi;
-                gn_block_finish(gs, gq, lane, p.gn_cpg, n, p.gn_part + (size_t)slot * 64);
+                gn_block_finish(gs, gq, lane, p.gn_cpg, n, p.gn_part + (size_t)gn_slot * 64);
                 done = true;
             }
         }
@@ -1009,14 +1016,15 @@ cudaError_t launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
     }
     if (g.epi == EPI_ARGMAX) bn = 32;      // the partial layout is defined on 32-column tiles
     TcParams p{g.C, g.M, g.N, g.K, g.ldc, g.bias, g.res, g.ldres, (g_texocr_pdl_mid & 1) ? 2 : ((g_texocr_pdl >> 9) & 1), 0, 0, 0, 0, 0, 0};
-    p.stages = 0; p.gn_part = nullptr; p.gn_cpg = 0; p.gn_rpi = 0;
+    p.stages = 0; p.gn_part = nullptr; p.gn_cpg = 0; p.gn_rpi = 0; p.gn_img_off = nullptr; p.gn_nimg = 0; p.gn_level = 0;
     p.g_hi = p.g_lo = nullptr; p.g_img_off = p.g_img_hw = nullptr; p.g_nimg = p.g_lin = p.g_lout = p.g_pad = 0;
     p.a_block_k = g.a_block_k; p.dbg = g.dbg;
     if (g.gn_part) {
-        if (g.epi != EPI_STORE || g.dt_c != DT_F32 || g.bias || g.N % 32 != 0 || g.gn_rpi <= 0 || g.gn_rpi % 32 != 0 || g.M % g.gn_rpi != 0 ||
-            g.N / 32 > 32 || (g.N / 32) & (g.N / 32 - 1))
+        if (g.epi != EPI_STORE || g.dt_c != DT_F32 || g.bias || g.N % 32 != 0 || g.M % 32 != 0 || g.N / 32 > 32 || (g.N / 32) & (g.N / 32 - 1))
             return cudaErrorInvalidValue;
+        if (g.gn_rpi > 0 ? (g.gn_rpi % 32 != 0 || g.M % g.gn_rpi != 0) : (!g.gn_img_off || g.gn_nimg <= 0)) return cudaErrorInvalidValue;
         p.gn_part = g.gn_part; p.gn_cpg = g.N / 32; p.gn_rpi = g.gn_rpi;
+        p.gn_img_off = g.gn_img_off; p.gn_nimg = g.gn_nimg; p.gn_level = g.gn_level;
     }
     CUtensorMap a, w, a2, w2;
     cudaError_t e;
