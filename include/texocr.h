@@ -147,7 +147,11 @@ typedef struct {
 } texocr_profile_row;
 TEXOCR_API int texocr_profile_enable(texocr_handle* h, int32_t on);
 TEXOCR_API int texocr_profile_read(texocr_handle* h, texocr_profile_row* rows, int32_t cap);
-/* Tuning switches (name = "cuda_graph" | "tcgen05" | ...); returns TEXOCR_ERR_ARG for unknown names. */
+/* Tuning switches (name = "cuda_graph" | "tcgen05" | ...); returns TEXOCR_ERR_ARG for unknown names.  Round-2 additions (all default on,
+ * results are bit-identical either way; the tests toggle them): "gemm_epi_warps" 4 | 8 epilogue warps per tcgen05 GEMM CTA, "gn_fused"
+ * GroupNorm partial sums from the convolution GEMM's epilogue, "gemm_bn256" 128 x 256 tiles for the wide convolutions, "conv_gather"
+ * cp.async-gathered implicit GEMMs for ragged batches (0 = explicit im2col buffer), "pdl_mid" bit mask of kernel families that release
+ * their programmatic dependent late (1 GEMM, 2 decode attention, 4 LayerNorm). */
 TEXOCR_API int texocr_set_option(texocr_handle* h, const char* name, int64_t value);
 /* Debug tap: copy an internal activation of the last texocr_encode call to `out` (host or device).
  * name = "backbone" -> float32 [sum h_i*w_i, 1024] (NHWC pixels).  Returns element count or <0. */
