@@ -277,6 +277,12 @@ def class_table(rows, peaks):
     return out
 
 
+def auto_in_flight(steps: int) -> int:
+    """Batches in flight for a job of `steps` batches per GPU: 6 unless another count in 5..8 leaves fewer replicas idle in the last
+    round (ties: nearest to 6).  20 batches over 6 replicas end with two replicas busy for a whole batch latency; over 5 they divide."""
+    return min((5, 6, 7, 8), key=lambda n: ((-steps) % n, abs(n - 6)))
+
+
 def dominant_kernel_roofline(rows, by_class, shares, tot, peaks, peaks_src, traffic_db):
     """`roofline` of the bench line: the kernel with the largest share of one eagerly launched batch (roles that are the same kernel
     instantiation grouped), its algorithmic FLOPs / bytes per launch over its CUDA-event time, against the measured peak."""
@@ -401,10 +407,8 @@ def main():
     rows_per_batch = img_host.shape[0]
     out_host = torch.empty((rows_per_batch, MAX_LEN), dtype=torch.int64).pin_memory()
     stream = torch.cuda.current_stream()
-    if args.in_flight <= 0:          # 6 unless another count in 5..8 leaves fewer replicas idle in the last round (ties: nearest to 6)
-        def idle(n):
-            return (-args.steps) % n
-        args.in_flight = min((5, 6, 7, 8), key=lambda n: (idle(n), abs(n - 6)))
+    if args.in_flight <= 0:
+        args.in_flight = auto_in_flight(args.steps)
     n_fly = max(1, min(args.in_flight, args.steps))
     pipe = None
     if n_fly > 1:

@@ -126,6 +126,30 @@ def test_sampled_generate_matches_reference_loop(gn, sd, m32, m16):
     assert torch.equal(outs[0], outs[1])
 
 
+def test_topk_filter_keeps_exactly_k_on_ties(m32):
+    """torch.topk + scatter (utils.py:85-91) keeps exactly k = int(0.1 * vocab) logits.  With many values tied at the k-th largest one, the
+    kernel keeps the ties at the lowest indices: no draw may ever land on a later tie."""
+    eng = m32.engine()
+    V = m32.dims.vocab
+    k = int((1 - 0.9) * V)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    logits = torch.full((64, V), -5.0, device="cuda")
+    top = torch.randperm(V, device="cuda", generator=g)[: k - 10]
+    logits[:, top] = 2.0 + torch.rand(64, k - 10, device="cuda", generator=g)         # k - 10 clear winners
+    tied = torch.arange(V, device="cuda")[~torch.isin(torch.arange(V, device="cuda"), top)][::7][:40]
+    logits[:, tied] = 1.0                                                             # 40 values tied at the threshold: 10 of them survive
+    allowed = set(top.tolist()) | set(sorted(tied.tolist())[:10])
+    try:
+        eng.set_sampling(1.5, 0.9, seed=3)        # flat-ish distribution: the ties carry real probability mass
+        seen = set()
+        for step in range(40):
+            seen |= set(eng.debug_sample_step(logits, step=step, call=1).cpu().tolist())
+        assert seen <= allowed, sorted(seen - allowed)
+        assert seen & set(sorted(tied.tolist())[:10])                                 # ... and the kept ties are actually drawn
+    finally:
+        eng.set_sampling(0.0)
+
+
 def test_set_sampling_validation(m32):
     eng = m32.engine()
     with pytest.raises(RuntimeError, match="threshold"):

@@ -206,3 +206,28 @@ def test_absorbed_attention_weight_folding_is_the_same_function():
     ya = ca @ wvo.astype(np.float64).T
     assert np.abs(sa - sc).max() < 1e-4 * np.abs(sc).max()                            # fp32 storage of the folded matrices
     assert np.abs(ya - y_il).max() < 1e-4 * np.abs(y_il).max()
+
+
+def test_bench_roofline_groups_roles_of_one_kernel_and_in_flight_rule():
+    """bench.py host logic: the `roofline` object names the dominant KERNEL -- the query projection and the block-diagonal value
+    projection are one tc_gemm_kernel instantiation, so their classes are added before the maximum is taken -- and the number of
+    batches in flight is chosen so that the job's batches divide over the replicas."""
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    import bench
+    assert [bench.auto_in_flight(k) for k in (12, 20, 16, 30, 7, 25)] == [6, 5, 8, 6, 7, 5]
+    peaks = {"hbm_gbs": 6551.4, "bf16_tflops": 1653.6, "bf16_tflops_sustained": 1372.5}
+    mk = lambda name, ms, n, by, fl: {"name": name, "ms": ms, "launches": n, "bytes": by * n, "flops": fl * n}
+    rows = [mk("dec_gemm_wo", 21.8, 2048, 2.1e6, 268e6), mk("dec_gemm_q", 19.2, 2048, 3.4e6, 537e6), mk("dec_gemm_vproj", 18.0, 2048, 2.9e6, 134e6),
+            mk("dec_attn_self", 17.7, 1024, 33e6, 0.5e9), mk("dec_attn_cross", 16.4, 1024, 25e6, 0.4e9), mk("conv_gemm", 5.2, 39, 6e8, 3.8e10)]
+    tot = sum(r["ms"] for r in rows)
+    shares = {r["name"]: round(r["ms"] / tot, 4) for r in rows}
+    r = bench.dominant_kernel_roofline(rows, bench.class_table(rows, peaks), shares, tot, peaks, "measured", {})
+    assert r["class"] == "gemm64_store_bf16" and r["launches"] == 4096 and r["bound"] == "tensor"
+    assert abs(r["achieved"] - (537e6 + 134e6) * 2048 / 37.2e-3 / 1e12) < 0.1 and abs(r["frac"] - r["achieved"] / 1372.5) < 1e-3
+    assert abs(r["share_of_batch_kernel_time"] - 37.2 / tot) < 1e-3 and r["traffic"] is None
+    # one role clearly ahead: no grouping needed
+    rows[0]["ms"] = 60.0
+    tot = sum(x["ms"] for x in rows)
+    r = bench.dominant_kernel_roofline(rows, bench.class_table(rows, peaks), {x["name"]: x["ms"] / tot for x in rows}, tot, peaks, "measured",
+                                       {"dec_gemm_wo": {"dram_bytes_per_launch": 1612032}})
+    assert r["class"] == "dec_gemm_wo" and r["traffic"] == 1612032

@@ -112,10 +112,32 @@ TX_DEVINL int sample_row(const float* __restrict__ l, int V, int k, float inv_te
 #pragma unroll
     for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
     mx = warp_max(mx);
+    // exactly k logits survive (torch.topk + scatter, utils.py:85-91): everything above the k-th largest value, and of the values equal
+    // to it the lowest indices until k are kept (lanes own ascending index ranges: an exclusive warp scan of the per-lane tie counts)
+    int n_gt = 0, n_eq = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const bool in = i < per && i0 + i < V;
+        n_gt += (in && order_key(v[i]) > prefix) ? 1 : 0;
+        n_eq += (in && order_key(v[i]) == prefix) ? 1 : 0;
+    }
+    int tot_gt = n_gt, eq_before = n_eq;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot_gt += __shfl_xor_sync(0xffffffffu, tot_gt, o);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, eq_before, o);
+        if (lane >= o) eq_before += t;
+    }
+    eq_before -= n_eq;                            // ties in lower lanes (= at lower indices)
+    int eq_left = k - tot_gt - eq_before;         // ties this lane may still keep
     float part = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const bool keep = i < per && i0 + i < V && order_key(v[i]) >= prefix;
+        const bool in = i < per && i0 + i < V;
+        const uint32_t key = order_key(v[i]);
+        bool keep = in && key > prefix;
+        if (in && key == prefix) { keep = eq_left > 0; --eq_left; }
         v[i] = keep ? expf((v[i] - mx) * inv_temp) : 0.f;
         part += v[i];
     }
