@@ -1,7 +1,7 @@
 #!/bin/bash
 # end-of-round ncu --set full captures of the kernels that changed in the second session
 cd "$(dirname "$0")/.."
-NCU="ncu --set full --clock-control none --import-source on --kernel-name-base demangled"
+NCU="ncu --set full --clock-control none --kernel-name-base demangled"
 CMD="python scripts/profile_generate.py --batch 512 --max-len 48 --warm 0 --no-graph --branches 1"
 # decode Q' GEMM with eight epilogue warps (late in the call: decode steps), conv GEMM with GroupNorm partials (3x3, K = 576), 16-byte GroupNorm apply
 timeout 600 $NCU -k 'regex:tc_gemm_kernel<\(int\)64, \(int\)0, __nv_bfloat16, \(int\)1, \(int\)0, \(int\)2>' -s 400 -c 2 -o gpurun_out/r2b_dec_q_gemm -f $CMD > gpurun_out/r2b_ncu_q.log 2>&1
@@ -21,5 +21,10 @@ rag = [synth.synth_images(1, 64, w, seed=500 + i)[0].cuda() for i, w in enumerat
 m.encoder(rag); torch.cuda.synchronize()
 PY
 timeout 600 $NCU -k 'regex:tc_conv_gather_kernel' -s 1 -c 3 -o gpurun_out/r2b_conv_gather -f python /tmp/ragged_enc.py > gpurun_out/r2b_ncu_gather.log 2>&1
-ls -la gpurun_out/r2b_*.ncu-rep
-tail -2 gpurun_out/r2b_ncu_q.log gpurun_out/r2b_ncu_conv.log gpurun_out/r2b_ncu_gn.log gpurun_out/r2b_ncu_gather.log
+# the reports stay on the box (64 MiB limit on what comes back): only their summaries travel
+for n in dec_q_gemm conv_gemm gn_apply8 conv_gather; do
+  echo "## $n" >> gpurun_out/r2b_ncu_summary.md
+  python scripts/ncu_summary.py gpurun_out/r2b_$n.ncu-rep >> gpurun_out/r2b_ncu_summary.md 2>&1
+  rm -f gpurun_out/r2b_$n.ncu-rep
+done
+cat gpurun_out/r2b_ncu_summary.md | cut -c1-400
