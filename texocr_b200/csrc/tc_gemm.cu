@@ -730,7 +730,6 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     } else {
         // ---- gather producers: thread r owns row r of every A tile
         const int r = (int)threadIdx.x - 192;
-        const uint32_t row_off = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
         const int cin = p.cv_cpk * BK, ksz = p.cv_ksz, stride = p.cv_stride;
         // k-blocks between issue and publication.  NST - 1 would keep every stage in flight but couples the MMA of k-block j to the
         // release of k-block j - 1 (measured: 6.5 ms of convolutions per config-2 batch against 5.7 ms with one stage of slack)
@@ -759,11 +758,18 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                 const size_t src = ok ? base + ((size_t)iy * win + ix) * cin + cc : 0;
                 const uint32_t nbytes = ok ? 16u : 0u;
                 mbar_wait(&empty[s], ph ^ 1);
-                const uint32_t d_hi = smem_u32(smem + s * S::STAGE) + row_off, d_lo = d_hi + S::A_BYTES;
+                // the copies are issued transposed: eight neighbouring lanes fetch the eight 16-byte chunks of ONE row (one 128-byte line per
+                // quarter warp instead of 32 half-used sectors per instruction); the row's source offset comes from its owner lane by shuffle
+                const uint32_t d_base = smem_u32(smem + s * S::STAGE) + (uint32_t)(r & ~31) * 128u;
+                const uint32_t ch = (uint32_t)lane & 7u;
 #pragma unroll
-                for (uint32_t j = 0; j < 8; ++j) {
-                    cp_async16(d_hi + ((j ^ sw) << 4), p.g_hi + src + j * 8, nbytes);
-                    cp_async16(d_lo + ((j ^ sw) << 4), p.g_lo + src + j * 8, nbytes);
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + (lane >> 3);
+                    const unsigned long long s_i = __shfl_sync(0xffffffffu, (unsigned long long)src, rr);
+                    const uint32_t nb_i = __shfl_sync(0xffffffffu, nbytes, rr);
+                    const uint32_t dst = d_base + (uint32_t)rr * 128u + ((ch ^ ((uint32_t)rr & 7u)) << 4);
+                    cp_async16(dst, p.g_hi + s_i + ch * 8, nb_i);
+                    cp_async16(dst + S::A_BYTES, p.g_lo + s_i + ch * 8, nb_i);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (it >= LAG) {       // publish k-block it - LAG: its copies have landed once at most LAG groups are pending
