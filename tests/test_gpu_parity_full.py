@@ -147,6 +147,34 @@ def test_bf16_encoder_more_shapes(golden, m16, sd, O):
     assert worst < BF16_TOL, worst
 
 
+def test_tensor_core_stem_vs_ffma_stem(golden, m16, sd, O):
+    """bf16 tier: the stem convolution runs as a tcgen05 implicit GEMM (bf16x3: ~16 mantissa bits per operand, GroupNorm partials from
+    its epilogue); option stem_tc = 0 selects the FFMA kernel of the fp32 tier + the stand-alone statistics pass.  Both within the
+    bf16 tolerance of the reference golden / the oracle, and within 5e-3 of each other, for a same-size and a ragged batch; a ragged
+    batch gives the rows of the per-image runs bit for bit."""
+    eng = m16.engine()
+    img = _img(golden, "a").cuda()
+    imgs = [synth.synth_images(1, h, w, seed=40 + i)[0].cuda() for i, (h, w) in enumerate(((64, 384), (16, 16), (160, 1008), (48, 208)))]
+    try:
+        outs = {}
+        for flag in (1, 0):
+            eng.set_option("stem_tc", flag)
+            outs[flag] = (m16.encoder(img).cpu(), eng.encode_packed(imgs)[0].cpu())
+            assert rel_max(outs[flag][0].numpy(), golden["enc_a"]) < BF16_TOL, flag
+        for a, b in zip(outs[1], outs[0]):
+            assert torch.isfinite(a).all() and rel_max(a.numpy(), b.numpy()) < 5e-3
+        eng.set_option("stem_tc", 1)
+        off = 0
+        for im in imgs:
+            single = m16.encoder(im[None])[0].cpu()
+            assert torch.equal(single, outs[1][1][off:off + single.shape[0]])
+            ref = O.encoder_forward(sd, im[None].cpu())[0]
+            assert rel_max(single.numpy(), ref.numpy()) < BF16_TOL
+            off += single.shape[0]
+    finally:
+        eng.set_option("stem_tc", 1)
+
+
 def test_alternating_entry_points_share_no_stale_graph(m16, dims):
     """decoder.generate(enc=...) and model.generate(src) with the same batch, max_len and eos replay different captured
     graphs: the cross-attention launches bake the device pointer of the memory offsets, which the two entry points place

@@ -57,6 +57,7 @@ struct texocr_handle {
 
     // ---- packed weights
     float* stem_w = nullptr; float* stem_g = nullptr; float* stem_b = nullptr;
+    void* stem_w_hi = nullptr; void* stem_w_lo = nullptr;      // bf16 tier: [64][64] split-bf16 filter bank of the tensor-core stem (49 taps + zero padding)
     std::vector<ConvW> convs;                 // the 39 non-stem convolutions in execution order
     void* proj_w = nullptr; void* proj_w_lo = nullptr; float* proj_b = nullptr; int proj_k = 0;
     float* cls = nullptr; float* pos = nullptr;
@@ -114,6 +115,7 @@ struct texocr_handle {
     bool use_tcgen05 = true;
     int gn_fused = 1;             // bf16 tier: GroupNorm partial sums in the epilogue of the producing convolution GEMM (same-size batches whose
                                   // images have a multiple of 32 pixel rows at every level); 0 = always the stand-alone block kernel
+    bool use_stem_tc = true;      // bf16 tier: stem convolution on the tensor cores (tc_stem_kernel) instead of the FFMA kernel
     bool use_conv_gather = true;  // bf16 tier, ragged batches: 3x3 / strided convolutions as implicit GEMMs with cp.async-gathered A tiles
     bool use_im2col_tma = true;   // bf16 tier, same-size batches: 3x3 / strided convolutions as implicit GEMMs (TMA im2col loads)
     // bf16 tier generate loop: cross-attention streams the [S,256] encoder memory once for all heads instead of per-head K/V

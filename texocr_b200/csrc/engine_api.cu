@@ -434,6 +434,7 @@ int texocr_set_option(texocr_handle* h, const char* name, int64_t value) {
     if (!strcmp(name, "gn_fused")) { h->gn_fused = (int)value; return 0; }
     if (!strcmp(name, "im2col_tma")) { h->use_im2col_tma = value != 0; return 0; }
     if (!strcmp(name, "conv_gather")) { h->use_conv_gather = value != 0; return 0; }
+    if (!strcmp(name, "stem_tc")) { h->use_stem_tc = value != 0; return 0; }
     if (!strcmp(name, "tcgen05")) {
         h->use_tcgen05 = value != 0;
         drop_graphs(h);

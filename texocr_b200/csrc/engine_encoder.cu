@@ -155,17 +155,24 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
     ENSURE(h->rawDs, (size_t)g.P[2] * 256 * 4);
     ENSURE(h->col, (size_t)g.P[2] * 576 * 4);
     ENSURE(h->gn_partial, (size_t)B * 32 * 32 * 2 * 8);
-    ENSURE(h->gn_part, (size_t)((g.P[2] >> 5) + B + 1) * 64 * 4);
+    ENSURE(h->gn_part, (size_t)((g.P[1] >> 5) + B + 1) * 64 * 4);
     for (int i = 0; i < 4; ++i) ENSURE(h->gn_stats[i], (size_t)B * 32 * 2 * 4);
     float* stats[4] = {h->gn_stats[0].as<float>(), h->gn_stats[1].as<float>(), h->gn_stats[2].as<float>(), h->gn_stats[3].as<float>()};
     double* partial = h->gn_partial.as<double>();
     struct Pair { char* hi; char* lo; };
     auto pair_of = [](DevBuf& b, size_t elems) { Pair p; p.hi = (char*)b.p; p.lo = (char*)b.p + elems * 2; return p; };
 
-    LAUNCH(KC_STEM, 1, (double)g.P[0] * 4 + (double)g.P[1] * 64 * 4, 2.0 * 49 * 64 * g.P[1],
-           launch_stem_conv(d_img, h->stem_w, h->raw1.as<float>(), g.d_img_off, g.d_img_hw, B, (int)g.P[1], st));
-    LAUNCH(KC_GN_STATS, 2, (double)g.P[1] * 64 * 4, 0.0,
-           launch_gn_stats(h->raw1.as<float>(), 64, 1, g.d_img_off, B, nchunk_for(g.P[1], B), partial, stats[0], st));
+    if (h->use_stem_tc && h->stem_w_hi) {      // implicit GEMM on the tensor cores, GroupNorm partials from its epilogue
+        LAUNCH(KC_STEM, 1, (double)g.P[0] * 4 + (double)g.P[1] * 64 * 4, 2.0 * 49 * 64 * g.P[1],
+               launch_stem_tc(d_img, h->stem_w_hi, h->stem_w_lo, h->raw1.as<float>(), g.d_img_off, g.d_img_hw, B, g.P[1], h->gn_part.as<float>(), st));
+        LAUNCH(KC_GN_STATS, 1, (double)((g.P[1] >> 5) + B) * 256, 0.0,
+               launch_gn_finalize_blocks(h->gn_part.as<float>(), 64, 1, g.d_img_off, B, stats[0], st));
+    } else {
+        LAUNCH(KC_STEM, 1, (double)g.P[0] * 4 + (double)g.P[1] * 64 * 4, 2.0 * 49 * 64 * g.P[1],
+               launch_stem_conv(d_img, h->stem_w, h->raw1.as<float>(), g.d_img_off, g.d_img_hw, B, (int)g.P[1], st));
+        LAUNCH(KC_GN_STATS, 2, (double)g.P[1] * 64 * 4, 0.0,
+               launch_gn_stats(h->raw1.as<float>(), 64, 1, g.d_img_off, B, nchunk_for(g.P[1], B), partial, stats[0], st));
+    }
     Pair x = pair_of(h->act2, (size_t)g.P[2] * 64);
     LAUNCH(KC_GN_APPLY, 1, (double)g.P[1] * 64 * 4 + (double)g.P[2] * 64 * 4, 0.0,
            launch_gn_apply_maxpool(h->raw1.as<float>(), stats[0], h->stem_g, h->stem_b, nullptr, x.hi, x.lo, g.d_img_off,

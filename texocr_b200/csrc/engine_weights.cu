@@ -193,6 +193,11 @@ int finalize_weights(texocr_handle* h) {
             standardise_reorder(*w, 64, 1, 7, ws);
             for (int o = 0; o < 64; ++o) for (int t = 0; t < 49; ++t) wt[t * 64 + o] = ws[o * 49 + t];
             if ((r = upload_f32(h, wt, &h->stem_w))) return r;
+            if (h->dt == DT_BF16) {      // tensor-core stem: [64 out][64 k] with k = tap for k < 49, zero otherwise
+                std::vector<float> wk(64 * 64, 0.f);
+                for (int o = 0; o < 64; ++o) for (int t = 0; t < 49; ++t) wk[o * 64 + t] = ws[o * 49 + t];
+                if ((r = upload_split(h, wk, &h->stem_w_hi, &h->stem_w_lo))) return r;
+            }
             GETW(g, bb + "stem.1.weight", 64);
             GETW(b, bb + "stem.1.bias", 64);
             if ((r = upload_f32(h, g->data, &h->stem_g))) return r;
