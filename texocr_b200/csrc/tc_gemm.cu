@@ -794,14 +794,14 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 // ------------------------------------------------------------------------------------------------ stem convolution on the tensor cores
 // model/resnet.py:219 (StdConv 7x7 / stride 2, one input channel, TF-SAME padding (2,3), 64 output channels) as an implicit GEMM
 // with K = 49 taps padded to 64, bf16x3: the standardised filter bank (8 + 8 KB of hi / lo bf16) stays in shared memory for the whole
-// kernel, four producer warps build the A tiles -- thread = output pixel: 49 image loads, split into hi / lo bf16, eight 16-byte
-// stores per half into the 128-byte-swizzled rows -- and the usual MMA issuer / eight epilogue warps follow; the epilogue leaves the
+// kernel, eight producer warps build the A tiles -- thread = output pixel: 49 image loads, split into hi / lo bf16, eight 16-byte
+// stores per half into the 128-byte-swizzled rows -- and the usual MMA issuer / four epilogue warps follow; the epilogue leaves the
 // GroupNorm partial sums of the 64-channel output (every image has a multiple of 64 level-1 pixels, so this works for any batch).
 // The FFMA kernel it replaces in the bf16 tier ran at 43 % of the fp32 SIMT peak (0.63 ms per 512 images) plus a statistics pass.
 struct SmemStem {
     static constexpr int A_BYTES = BM * BK * 2, W_BYTES = 64 * BK * 2;
     static constexpr int STAGE = 2 * A_BYTES, STAGES = 4;
-    static constexpr int STG = 8 * STG_WARP;
+    static constexpr int STG = 4 * STG_WARP;
     static constexpr int TOTAL = 2 * W_BYTES + STAGES * STAGE + STG + 1024 + 256;
 };
 struct StemParams {
@@ -831,7 +831,7 @@ tc_stem_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -874,21 +874,23 @@ tc_stem_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 umma_commit(&tmem_full[buf]);
             }
         }
-    } else if (warp >= 2 && warp < 10) {
+    } else if (warp >= 2 && warp < 6) {
         int i = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
-            epilogue_tile<BN, EPI_STORE, float, 2, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, tile * BM, 0, p, stg, (uint32_t)((i >> 1) & 1));
+            epilogue_tile<BN, EPI_STORE, float, 1, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, tile * BM, 0, p, stg, (uint32_t)((i >> 1) & 1));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
-    } else if (warp >= 10) {
-        // ---- producers: thread r builds row r (one output pixel) of every A tile
-        const int r = (int)threadIdx.x - 320;
+    } else if (warp >= 6) {
+        // ---- producers: two groups of four warps take alternate tiles of this CTA (a thread builds its row start to finish, so one
+        // group alone is one tile per ~2.5 us and SM); thread r of a group builds row r (one output pixel) of its A tiles
+        const int grp = (warp - 6) >> 2;
+        const int r = ((int)threadIdx.x - 192) & 127;
         const uint32_t sw = (uint32_t)(r & 7);
-        int i = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
+        int i = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < tiles; tile += 2 * gridDim.x, i += 2) {
             const int s = i % NST, ph = (i / NST) & 1;
             const int m = tile * BM + r;
             float v[56];
