@@ -164,7 +164,8 @@ static int run_backbone_tc(texocr_handle* h, const float* d_img, const EncGeom& 
 
     if (h->use_stem_tc && h->stem_w_hi) {      // implicit GEMM on the tensor cores, GroupNorm partials from its epilogue
         LAUNCH(KC_STEM, 1, (double)g.P[0] * 4 + (double)g.P[1] * 64 * 4, 2.0 * 49 * 64 * g.P[1],
-               launch_stem_tc(d_img, h->stem_w_hi, h->stem_w_lo, h->raw1.as<float>(), g.d_img_off, g.d_img_hw, B, g.P[1], h->gn_part.as<float>(), st));
+               launch_stem_tc(d_img, h->stem_w_hi, h->stem_w_lo, h->raw1.as<float>(), g.d_img_off, g.d_img_hw, B, g.P[1],
+                              g.uni_h > 0 ? (g.uni_h >> 1) * (g.uni_w >> 1) : 0, h->gn_part.as<float>(), st));
         LAUNCH(KC_GN_STATS, 1, (double)((g.P[1] >> 5) + B) * 256, 0.0,
                launch_gn_finalize_blocks(h->gn_part.as<float>(), 64, 1, g.d_img_off, B, stats[0], st));
     } else {

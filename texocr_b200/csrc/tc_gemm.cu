@@ -198,7 +198,7 @@ TX_DEVINL void stage_put(uint8_t* stg, int lane, const uint4* rq) {
 
 template <int BN, int EPI, typename TC, int EW, bool AHEAD = false>
 TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, int lane, int m0, int n0, const TcParams& p,
-                             uint8_t* smem_idle, uint32_t parity = 0, unsigned long long dbg_t0 = 0ull) {
+                             uint8_t* smem_idle, uint32_t parity = 0, unsigned long long dbg_t0 = 0ull, int* gn_hint = nullptr) {
     constexpr int CW = (EW == 2 && BN == 32) ? 16 : 32;         // columns per tcgen05.ld chunk
     const int q = warp & 3;                                     // TMEM lane quarter of this warp
     const int ew = warp - 2, eg = ew >> 2;                      // epilogue warp / warpgroup index
@@ -252,8 +252,15 @@ TX_DEVINL void epilogue_tile(uint64_t* tmem_full, uint32_t tmem_base, int warp, 
     // batches), looked up while the MMAs are still running
     int gn_slot = 0;
     if constexpr (EPI == EPI_STORE && std::is_same<TC, float>::value && CW == 32) {
-        if (p.gn_part && rows_ok > 0)
-            gn_slot = (mrow0 >> 5) + (p.gn_rpi > 0 ? mrow0 / p.gn_rpi : find_image(p.gn_img_off, p.gn_nimg, p.gn_level, mrow0));
+        if (p.gn_part && rows_ok > 0) {
+            int bimg;
+            if (p.gn_rpi > 0) bimg = mrow0 / p.gn_rpi;
+            else {
+                bimg = find_image_from(p.gn_img_off, p.gn_nimg, p.gn_level, mrow0, gn_hint ? *gn_hint : -1);
+                if (gn_hint) *gn_hint = bimg;
+            }
+            gn_slot = (mrow0 >> 5) + bimg;
+        }
     }
     mbar_wait(tmem_full, parity);
     if (p.late_trigger == 2) pdl_launch_dependents();           // one-tile kernel: what is left of this CTA is about as long as the dependent's launch + prologue
@@ -599,11 +606,11 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             }
         }
     } else {
-        int i = 0;
+        int i = 0, gn_hint = -1;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            epilogue_tile<BN, EPI, TC, EW, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
+            epilogue_tile<BN, EPI, TC, EW, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1), 0ull, &gn_hint);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);              // all of this warp's tcgen05.ld of the buffer have completed
@@ -718,11 +725,11 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             }
         }
     } else if (warp < 6) {
-        int i = 0;
+        int i = 0, gn_hint = -1;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
             const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-            epilogue_tile<BN, EPI_STORE, float, 1, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1));
+            epilogue_tile<BN, EPI_STORE, float, 1, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, m0, n0, p, stg, (uint32_t)((i >> 1) & 1), 0ull, &gn_hint);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -734,14 +741,15 @@ tc_conv_gather_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         // k-blocks between issue and publication.  NST - 1 would keep every stage in flight but couples the MMA of k-block j to the
         // release of k-block j - 1 (measured: 6.5 ms of convolutions per config-2 batch against 5.7 ms with one stage of slack)
         constexpr int LAG = NST > 2 ? NST - 2 : 1;
-        int it = 0;
+        int it = 0, b_hint = -1;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int m = (tile / n_tiles) * BM + r;
             int oy = 0, ox = 0, hin = 0, win = 0;
             size_t base = 0;
             const bool row_ok = m < p.M;
             if (row_ok) {
-                const int b = find_image(p.g_img_off, p.g_nimg, p.g_lout, m);
+                const int b = find_image_from(p.g_img_off, p.g_nimg, p.g_lout, m, b_hint);
+                b_hint = b;
                 const int H = p.g_img_hw[2 * b], W = p.g_img_hw[2 * b + 1];
                 const int wo = W >> p.g_lout;
                 hin = H >> p.g_lin; win = W >> p.g_lin;
@@ -806,6 +814,7 @@ struct SmemStem {
 };
 struct StemParams {
     const float* img; const int* img_off; const int* img_hw; int nimg;
+    int rpi;           // > 0: every image has this many level-1 pixels (same-size batch)
 };
 
 __global__ void __launch_bounds__(448, 1)
@@ -875,10 +884,10 @@ tc_stem_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
         }
     } else if (warp >= 2 && warp < 6) {
-        int i = 0;
+        int i = 0, gn_hint = -1;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int buf = i & 1;
-            epilogue_tile<BN, EPI_STORE, float, 1, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, tile * BM, 0, p, stg, (uint32_t)((i >> 1) & 1));
+            epilogue_tile<BN, EPI_STORE, float, 1, true>(&tmem_full[buf], tmem_base + (uint32_t)(buf * BN), warp, lane, tile * BM, 0, p, stg, (uint32_t)((i >> 1) & 1), 0ull, &gn_hint);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -889,7 +898,7 @@ tc_stem_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const int grp = (warp - 6) >> 2;
         const int r = ((int)threadIdx.x - 192) & 127;
         const uint32_t sw = (uint32_t)(r & 7);
-        int i = grp;
+        int i = grp, b_hint = -1;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < tiles; tile += 2 * gridDim.x, i += 2) {
             const int s = i % NST, ph = (i / NST) & 1;
             const int m = tile * BM + r;
@@ -897,7 +906,8 @@ tc_stem_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 #pragma unroll
             for (int t = 0; t < 56; ++t) v[t] = 0.f;
             if (m < p.M) {
-                const int b = find_image(sp.img_off, sp.nimg, 1, m);
+                const int b = sp.rpi > 0 ? m / sp.rpi : find_image_from(sp.img_off, sp.nimg, 1, m, b_hint);      // same-size batch: a division
+                b_hint = b;
                 const int H = sp.img_hw[2 * b], W = sp.img_hw[2 * b + 1], W1 = W >> 1;
                 const int local = m - (sp.img_off[b] >> 2);
                 const int oy = local / W1, ox = local - oy * W1;
@@ -1142,14 +1152,14 @@ cudaError_t launch_epi(const GemmArgs& g, const CUtensorMap& a, const CUtensorMa
 // Stem convolution of the bf16 tier (tc_stem_kernel): img = ragged fp32 images, w_hi / w_lo = [64][64] bf16 (49 standardised taps + 15
 // zero columns per output channel), raw1 [total_p1, 64] fp32, gn_part = GroupNorm block partials of raw1 (gn_block.cuh).
 cudaError_t launch_stem_tc(const float* img, const void* w_hi, const void* w_lo, float* raw1, const int* img_off, const int* img_hw, int nimg,
-                           long total_p1, float* gn_part, cudaStream_t st) {
+                           long total_p1, int uniform_rpi, float* gn_part, cudaStream_t st) {
     if (total_p1 <= 0) return cudaSuccess;
     if (total_p1 % 32 != 0 || total_p1 > 0x7fffffffL) return cudaErrorInvalidValue;
     TcParams p{raw1, (int)total_p1, 64, 64, 64, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
     p.stages = 0; p.a_block_k = 0; p.dbg = nullptr;
-    p.gn_part = gn_part; p.gn_cpg = 2; p.gn_rpi = 0; p.gn_img_off = img_off; p.gn_nimg = nimg; p.gn_level = 1;
+    p.gn_part = gn_part; p.gn_cpg = 2; p.gn_rpi = uniform_rpi > 0 ? uniform_rpi : 0; p.gn_img_off = img_off; p.gn_nimg = nimg; p.gn_level = 1;
     p.g_hi = p.g_lo = nullptr; p.g_img_off = p.g_img_hw = nullptr; p.g_nimg = p.g_lin = p.g_lout = p.g_pad = 0;
-    StemParams sp{img, img_off, img_hw, nimg};
+    StemParams sp{img, img_off, img_hw, nimg, uniform_rpi > 0 ? uniform_rpi : 0};
     CUtensorMap w, w2;
     cudaError_t e;
     if ((e = get_map(w_hi, 64, 64, 64, 64, &w)) != cudaSuccess) return e;

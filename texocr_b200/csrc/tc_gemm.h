@@ -18,4 +18,4 @@ cudaError_t tma_map_3d_bf16(const void* ptr, int d0, long d1, long d2, long stri
 // Stem convolution of the bf16 tier as a tcgen05 implicit GEMM (7x7 / stride 2, one input channel, K = 49 taps padded to 64, bf16x3), with the
 // GroupNorm block partials of its output (gn_block.cuh).  w_hi / w_lo: [64][64] bf16.
 cudaError_t launch_stem_tc(const float* img, const void* w_hi, const void* w_lo, float* raw1, const int* img_off, const int* img_hw, int nimg,
-                           long total_p1, float* gn_part, cudaStream_t st);
+                           long total_p1, int uniform_rpi /* level-1 pixels per image of a same-size batch, else 0 */, float* gn_part, cudaStream_t st);
