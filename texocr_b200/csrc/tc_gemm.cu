@@ -626,13 +626,15 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
 // ------------------------------------------------------------------------------------------------ ragged implicit-GEMM convolution
 // Batches of different-size images cannot use the TMA im2col loads (one regular [N][H][W][C] box per tensor map).  Same persistent
-// kernel, bf16x3 operands, fp32 store epilogue -- but the A tiles are gathered by four producer warps, thread = output pixel of
-// the tile: the pixel's image is located once per tile (binary search over the offset table), then every k-block (filter tap,
-// 64-channel chunk) is one 128-byte row per operand half, copied with eight 16-byte cp.async (zero-fill for taps outside the
-// image: TF-SAME padding) straight into the 128-byte-swizzled layout the MMA descriptors expect.  A stage is published
-// STAGES - 2 k-blocks late (cp.async.wait_group -> fence.proxy.async -> mbarrier arrive): the copies of the following k-blocks are
-// in flight while it lands, and one stage of slack stays between the MMA issuer and the producers.  W tiles still come by TMA.  Replaces the explicit im2col buffer (72 bytes of traffic per input element of a
-// 3x3 convolution) for ragged batches.
+// kernel, bf16x3 operands, fp32 store epilogue -- but the A tiles are gathered by four producer warps.  Thread r owns output pixel r
+// of the tile: it locates the pixel's image once per tile (a forward step from the previous tile's image) and computes, per k-block
+// (filter tap, 64-channel chunk), the source offset of the pixel's 128-byte row (or "outside the image": TF-SAME padding = zero
+// fill).  The copies themselves are issued transposed: eight neighbouring lanes fetch the eight 16-byte chunks of ONE row (offsets by
+// shuffle from the owner lane), so a quarter warp reads one full 128-byte line, straight into the 128-byte-swizzled layout the MMA
+// descriptors expect.  A stage is published STAGES - 2 k-blocks late (cp.async.wait_group -> fence.proxy.async -> mbarrier arrive):
+// the copies of the following k-blocks are in flight while it lands, and one stage of slack stays between the MMA issuer and the
+// producers.  W tiles still come by TMA.  Replaces the explicit im2col buffer (72 bytes of traffic per input element of a 3x3
+// convolution) for ragged batches.
 template <int BN> struct SmemG {
     static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
     static constexpr int STAGE = 2 * (A_BYTES + W_BYTES);
