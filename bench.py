@@ -488,7 +488,7 @@ def main():
         if not strong:
             ms_1 = timed(step_device, min(args.steps, 6))
             serial = {"value": world * B * min(args.steps, 6) / (ms_1 / 1e3), "unit": UNIT, "ms_per_step": ms_1 / min(args.steps, 6),
-                      "note": "the same batches, one model.generate call at a time (6 decode branches per batch): what a caller of the "
+                      "note": "the same batches, one model.generate call at a time (one decode branch per 128 rows): what a caller of the "
                               "reference's own loop (test.py:27-40) gets without the pipeline"}
     done_eq = sum(len(job_plan(args.total, B, r, world)) for r in range(world)) * B if strong else world * B * args.steps
     value = done_eq / (ms / 1e3)
@@ -689,7 +689,7 @@ def main():
         "config": {"workload": workload,
                    "batch_per_gpu": B, "max_len": MAX_LEN, "image": [H, W], "precision": args.precision,
                    "parallelism": f"dp{world} (independent shards, token-id all_gather)",
-                   "batches_in_flight": n_fly, "decode_branches_per_batch": args.branches if n_fly > 1 else 6,
+                   "batches_in_flight": n_fly, "decode_branches_per_batch": args.branches if n_fly > 1 else max(1, min(8, (B + 64) // 128)),
                    "total_equations": done_eq if strong else None,
                    "l2_policy": "working set per batch in flight (0.25 GB latent attention cache + 0.2 GB encoder memory / decode buffers + >= 3 GB encoder activations) exceeds the 126 MB L2 many times over; no explicit flush"},
         "e2e": e2e, "one_batch_at_a_time": serial, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline,

@@ -76,7 +76,7 @@ struct texocr_handle {
     cudaEvent_t geom_ev = nullptr, hop_in = nullptr, hop_out = nullptr;
     cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
     cudaStream_t branch_stream[16] = {nullptr}; cudaEvent_t join_ev[16] = {nullptr}; cudaEvent_t fork_ev = nullptr;
-    int decode_branches = 0;                   // 0 = automatic (one branch per ~86 rows, at most 8)
+    int decode_branches = 0;                   // 0 = automatic (one branch per 128 rows = one GEMM row tile, at most 8)
     DevBuf img_stage;                          // device copy of host images
     DevBuf raw1, act2, actA, actB, rawMid, actMid, rawMid2, actMid2, raw3, rawDs;
     DevBuf gn_partial, gn_stats[4];

@@ -174,8 +174,9 @@ int sampling_k(const texocr_handle* h) { return (int)((1.0 - h->samp_threshold) 
 
 struct BranchPlan { int n; int row0[MAX_BRANCH]; int rows[MAX_BRANCH]; };
 static BranchPlan plan_branches(texocr_handle* h, int B) {
-    // ~86 rows per branch (6 branches at B = 512: measured 97.2 ms per generate vs 99.5 with 8 and 104.7 with 4), at most 8
-    int n = h->decode_branches > 0 ? h->decode_branches : std::min(8, std::max(1, (B + 85) / 86));
+    // one 128-row GEMM tile per branch (4 branches at B = 512: measured 85.4 ms per generate vs 88.6 with 3, 89.3 with 6 and 94.2 with 8
+    // at the end of round 2; round 1, before the 8-warp epilogues and the late PDL release, preferred ~86 rows), at most 8
+    int n = h->decode_branches > 0 ? h->decode_branches : std::min(8, std::max(1, (B + 64) / 128));
     n = std::max(1, std::min(std::min(n, MAX_BRANCH), B));
     BranchPlan p;
     p.n = n;
