@@ -175,6 +175,20 @@ def test_tensor_core_stem_vs_ffma_stem(golden, m16, sd, O):
         eng.set_option("stem_tc", 1)
 
 
+def test_many_tiny_images_in_one_ragged_batch(m16, m32):
+    """Hundreds of 16x16 / 16x32 / 32x16 images in one batch: a 128-row tile of the persistent kernels spans up to 128 images here, so the
+    image lookup of the producers / epilogues takes its binary-search path (more than 8 images ahead of the previous tile's) as well as
+    the forward-step one.  Rows of the batch equal the per-image runs bit for bit, on both tiers."""
+    shapes = [(16, 16), (16, 32), (32, 16)]
+    imgs = [synth.synth_images(1, *shapes[i % 3], seed=3000 + i)[0].cuda() for i in range(331)]
+    for m in (m16, m32):
+        outs = m.encoder(imgs)
+        assert len(outs) == len(imgs) and all(torch.isfinite(o).all() for o in outs)
+        for i in (0, 1, 2, 57, 130, 329, 330):
+            single = m.encoder(imgs[i][None])[0]
+            assert torch.equal(single, outs[i]), i
+
+
 def test_alternating_entry_points_share_no_stale_graph(m16, dims):
     """decoder.generate(enc=...) and model.generate(src) with the same batch, max_len and eos replay different captured
     graphs: the cross-attention launches bake the device pointer of the memory offsets, which the two entry points place
